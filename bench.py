@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""Headline benchmark: factor-messages/sec per FGNN layer (BASELINE.json `metric`).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference            # the CPU restatement of the reference path
+
+Workload (`config.workload`): BASELINE.json configs[1] -- synthetic MAP-inference factor graph,
+100 000 variables, 300 000 pairwise + 50 000 order-3 factors, 5 stacked FGNN layers, fp32,
+C = O = 64, T = 16 edge types (the synthetic scripts' value, train_syn_hop_factor.py:170-172).
+One STEP = one pass of the hot path over that graph: for each of the 5 layers, for each factor
+type, the Variable->Factor call and the Factor->Variable call of FactorNN's layer body
+(factor_mpnn_sp.py:142-151) = 20 `fgnn_mp_forward` launches.  A MESSAGE is one real
+(destination, slot) evaluation in one direction; per layer = sum_types 2*F*K = 1 500 000.
+
+Prints ONE JSON line (rank 0).  `value` = messages/s with inputs resident in HBM; `e2e` = the
+same through the public module API with HOST buffers (pinned), H2D of the step's inputs and D2H
+of the resulting variable features inside the timed region.  `roofline` is the HBM roofline of
+the message-passing kernel: algorithmic bytes (SURVEY 8d formula) / CUDA-event time, against
+MEASURED_PEAKS.json.  `cpu_baseline` times oracle/ (the C restatement of the reference's
+algorithm, OpenMP) on a bounded 1/2-scale sample of the same workload on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "factor_messages_per_sec_per_fgnn_layer"
+UNIT = "messages/s"
+FALLBACK_HBM_GBS = 6650.0        # B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--vars", type=int, default=100_000)
+    ap.add_argument("--pairwise", type=int, default=300_000)
+    ap.add_argument("--high", type=int, default=50_000)
+    ap.add_argument("--high-order", type=int, default=3)
+    ap.add_argument("--layers", type=int, default=5)
+    ap.add_argument("--edge-types", type=int, default=16)
+    ap.add_argument("--dim", type=int, default=64)
+    ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--local-band", type=int, default=0, help="0 = uniform-random incidence (primary)")
+    ap.add_argument("--cpu-sample-scale", type=int, default=2, help="cpu_baseline runs on 1/scale of the graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------
+
+def build_graph(args, scale=1):
+    from fgnn_b200 import graphs
+    return graphs.synthetic_map_graph(args.vars // scale, args.pairwise // scale, args.high // scale,
+                                      args.high_order, seed=args.seed, local_band=args.local_band)
+
+
+def layer_weights(args, n_types, rng):
+    """Per layer / type / direction: filters ~U(-0.01,0.01), bias ~U(0,0.05) (mp_nn.py:49,53), BN
+    running stats randomised, folded to scale/shift."""
+    C = O = args.dim
+    T = args.edge_types
+    ws = []
+    for _ in range(args.layers):
+        per_type = []
+        for _ in range(n_types):
+            d = {}
+            for direction in ("v2f", "f2v"):
+                rv = rng.uniform(0.5, 1.5, O).astype(np.float32)
+                rm = rng.uniform(-0.05, 0.05, O).astype(np.float32)
+                scale = (1.0 / np.sqrt(rv + 1e-5)).astype(np.float32)
+                d[direction] = dict(filters=rng.uniform(-0.01, 0.01, (C, O * T)).astype(np.float32),
+                                    bias=rng.uniform(0, 0.05, O).astype(np.float32),
+                                    scale=scale, shift=(-rm * scale).astype(np.float32), rm=rm, rv=rv)
+            per_type.append(d)
+        ws.append(per_type)
+    return ws
+
+
+def host_inputs(args, types, rng):
+    C, T = args.dim, args.edge_types
+    x_v = rng.random((1, types[0].n_vars, C), dtype=np.float32)              # node-major [B,N,C]
+    x_f = [np.abs(rng.standard_normal((1, t.n_factors, C))).astype(np.float32) for t in types]
+    et_v2f = [rng.standard_normal((1, T, t.n_factors, t.order)).astype(np.float32) for t in types]
+    et_f2v = []
+    for t in types:
+        e = rng.standard_normal((1, T, t.n_vars, t.kv)).astype(np.float32)
+        e[np.broadcast_to(t.pad_f2v[None, None], e.shape)] = 0.0               # reference padding: etype = 0
+        et_f2v.append(e)
+    return dict(x_v=x_v, x_f=x_f, et_v2f=et_v2f, et_f2v=et_f2v,
+                idx_v2f=[t.idx_v2f[None] for t in types], idx_f2v=[t.idx_f2v[None] for t in types])
+
+
+def algorithmic_bytes_per_layer(args, types):
+    """per core call 4*M*K (idx as int32) + s*T*M*K (etype) + s*C*N_src + s*O*M."""
+    s, C, O, T = 4, args.dim, args.dim, args.edge_types
+    total = 0
+    for t in types:
+        total += 4 * t.n_factors * t.order + s * T * t.n_factors * t.order + s * C * t.n_vars + s * O * t.n_factors
+        total += 4 * t.n_vars * t.kv + s * T * t.n_vars * t.kv + s * C * t.n_factors + s * O * t.n_vars
+    return total
+
+
+def workload_name(args):
+    return (f"synthetic MAP inference: {args.vars} vars, {args.pairwise} pairwise + {args.high} order-{args.high_order} "
+            f"factors, {args.layers} FGNN layers, C=O={args.dim}, T={args.edge_types}, fp32, "
+            f"{'uniform-random' if not args.local_band else f'band-{args.local_band}'} incidence")
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle's C restatement of the reference algorithm (bounded sample)
+# ---------------------------------------------------------------------------------------------
+
+def cpu_layer_pass(args, types, inp, weights, threads=0):
+    """One FGNN layer (all types, both directions) on the CPU oracle; returns seconds."""
+    from oracle import fgnn_oracle as orc
+    t0 = time.perf_counter()
+    x_v = np.ascontiguousarray(inp["x_v"].transpose(0, 2, 1))[..., None]
+    for j, ty in enumerate(types):
+        w = weights[j]
+        x_f = np.ascontiguousarray(inp["x_f"][j].transpose(0, 2, 1))[..., None]
+        for direction, x, idx, et in (("v2f", x_v, inp["idx_v2f"][j], inp["et_v2f"][j]),
+                                      ("f2v", x_f, inp["idx_f2v"][j], inp["et_f2v"][j])):
+            p = w[direction]
+            bn = dict(weight=np.ones_like(p["rv"]), bias=np.zeros_like(p["rv"]), running_mean=p["rm"], running_var=p["rv"])
+            orc.mp_conv_forward_c(x, idx, et, p["filters"], p["bias"], bn, extension=0, aggregator="max",
+                                  threads=threads)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(args, passes=5):
+    from oracle import fgnn_oracle as orc
+    orc.build_c()
+    scale = args.cpu_sample_scale
+    rng = np.random.default_rng(args.seed + 1)
+    types = build_graph(args, scale)
+    inp = host_inputs(args, types, rng)
+    weights = layer_weights(args, len(types), rng)[0]
+    cores = orc.c_threads()
+    cpu_layer_pass(args, types, inp, weights)                 # warm-up
+    times = [cpu_layer_pass(args, types, inp, weights) for _ in range(passes)]
+    msgs = sum(t.real_messages for t in types)
+    return dict(value=msgs / (sum(times) / len(times)), unit=UNIT, cores=cores, kind="port",
+                sample=(f"1 FGNN layer on a 1/{scale}-scale instance of the workload ({types[0].n_vars} vars, "
+                        f"{msgs} messages), oracle/fgnn_oracle.c (C restatement of mp_nn.py:115-175, OpenMP, "
+                        f"{cores} threads), mean of {passes} passes after 1 warm-up")), sum(times)
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores (the oracle port; the reference
+    itself is Python-over-ATen and /root/reference does not exist on the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import fgnn_oracle as orc
+    orc.build_c()
+    scale = args.cpu_sample_scale
+    rng = np.random.default_rng(args.seed + 1)
+    types = build_graph(args, scale)
+    inp = host_inputs(args, types, rng)
+    weights = layer_weights(args, len(types), rng)
+    msgs = sum(t.real_messages for t in types)
+    steps = max(1, min(args.steps, 3))
+    warm = 1
+    for _ in range(warm):
+        cpu_layer_pass(args, types, inp, weights[0])
+    t0 = time.perf_counter()
+    for s in range(steps):
+        for l in range(args.layers):
+            cpu_layer_pass(args, types, inp, weights[l])
+    dt = time.perf_counter() - t0
+    value = msgs * args.layers * steps / dt
+    cores = orc.c_threads()
+    sample = (f"each step = {args.layers} FGNN layers on a 1/{scale}-scale instance of the workload "
+              f"({types[0].n_vars} vars, {msgs} messages/layer)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    import fgnn_b200
+    from fgnn_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    kernel = {"auto": _lib.KERNEL_AUTO, "simt": _lib.KERNEL_SIMT, "tcgen05": _lib.KERNEL_TCGEN05}[args.kernel]
+
+    rng = np.random.default_rng(args.seed + 1)
+    types = build_graph(args)
+    inp = host_inputs(args, types, rng)
+    weights = layer_weights(args, len(types), rng)
+    msgs_layer = sum(t.real_messages for t in types)
+    bytes_layer = algorithmic_bytes_per_layer(args, types)
+    J, L, C = len(types), args.layers, args.dim
+
+    if world > 1:
+        from fgnn_b200 import parallel
+        plan = parallel.ShardedLayerPlan(types, rank, world, dev)
+    else:
+        plan = None
+
+    def to_dev(a, pin=False):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        return t.pin_memory() if pin else t.to(dev)
+
+    def nm(t):                                   # node-major [1,N,C] memory viewed as the API's [1,C,N,1]
+        return t.permute(0, 2, 1).unsqueeze(-1)
+
+    W = [[{d: {k: to_dev(v) for k, v in weights[l][j][d].items() if k in ("filters", "bias", "scale", "shift")}
+           for d in ("v2f", "f2v")} for j in range(J)] for l in range(L)]
+    ws = [[{d: torch.zeros(C * C * args.edge_types * 4 + 4096, dtype=torch.uint8, device=dev) for d in ("v2f", "f2v")}
+           for j in range(J)] for l in range(L)]
+    d_in = dict(x_v=to_dev(inp["x_v"]), x_f=[to_dev(a) for a in inp["x_f"]],
+                et_v2f=[to_dev(a) for a in inp["et_v2f"]], et_f2v=[to_dev(a) for a in inp["et_f2v"]],
+                idx_v2f=[to_dev(a) for a in inp["idx_v2f"]], idx_f2v=[to_dev(a) for a in inp["idx_f2v"]])
+    # ping-pong feature buffers, node-major
+    buf_v = [torch.empty_like(d_in["x_v"]) for _ in range(2)]
+    buf_f = [[torch.empty_like(x) for x in d_in["x_f"]] for _ in range(2)]
+
+    def call(x, idx, et, w, out, accumulate, wsb, l, j, d):
+        fgnn_b200.mp_forward(nm(x), idx, et, w["filters"], w["bias"], w["scale"], w["shift"], extension=0,
+                             aggregator=_lib.AGG_MAX, activation=_lib.ACT_RELU, kernel=kernel, out=nm(out),
+                             accumulate=accumulate, workspace=wsb, filters_version=1 + l * 16 + j * 2 + (d == "f2v"))
+
+    def step(src):
+        """src: dict of device tensors (x_v, x_f, tables).  Returns the final variable features."""
+        x_v, x_f = src["x_v"], src["x_f"]
+        for l in range(L):
+            nv, nf = buf_v[l & 1], buf_f[l & 1]
+            if plan is not None:
+                plan.layer(l, x_v, x_f, src, W[l], nv, nf, kernel)
+            else:
+                for j in range(J):
+                    call(x_v, src["idx_v2f"][j], src["et_v2f"][j], W[l][j]["v2f"], nf[j], False, ws[l][j]["v2f"], l, j, "v2f")
+                    call(x_f[j], src["idx_f2v"][j], src["et_f2v"][j], W[l][j]["f2v"], nv, j > 0, ws[l][j]["f2v"], l, j, "f2v")
+            x_v, x_f = nv, nf
+        return x_v
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -----------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step(d_in)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = fgnn_b200.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step(d_in)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = fgnn_b200.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    ms_step = ms / args.steps
+    value = msgs_layer * L / (ms_step * 1e-3)
+
+    # ---- end to end through the module API with host buffers --------------------------------
+    e2e = None
+    if not args.no_e2e:
+        mods = []
+        for l in range(L):
+            row = []
+            for j in range(J):
+                pair = {}
+                for d in ("v2f", "f2v"):
+                    m = fgnn_b200.mp_conv_v2(C, C, args.edge_types, extension=fgnn_b200.mp_conv_type.NO_EXTENSION,
+                                             aggregtor="max")
+                    p = weights[l][j][d]
+                    m.load_state_dict({"filters": torch.from_numpy(p["filters"]), "bias": torch.from_numpy(p["bias"]),
+                                       "bn.weight": torch.ones(C), "bn.bias": torch.zeros(C),
+                                       "bn.running_mean": torch.from_numpy(p["rm"]), "bn.running_var": torch.from_numpy(p["rv"]),
+                                       "bn.num_batches_tracked": torch.tensor(0)})
+                    m.kernel = kernel
+                    pair[d] = m.to(dev).eval().enable_weight_cache()
+                row.append(pair)
+            mods.append(row)
+        pinned = dict(x_v=to_dev(inp["x_v"], True), x_f=[to_dev(a, True) for a in inp["x_f"]],
+                      et_v2f=[to_dev(a, True) for a in inp["et_v2f"]], et_f2v=[to_dev(a, True) for a in inp["et_f2v"]],
+                      idx_v2f=[to_dev(a, True) for a in inp["idx_v2f"]], idx_f2v=[to_dev(a, True) for a in inp["idx_f2v"]])
+        host_out = torch.empty((1, types[0].n_vars, C), dtype=torch.float32).pin_memory()
+        h2d = sum(t.numel() * t.element_size() for v in pinned.values() for t in (v if isinstance(v, list) else [v]))
+        d2h = host_out.numel() * 4
+
+        def e2e_step():
+            src = {k: ([t.to(dev, non_blocking=True) for t in v] if isinstance(v, list) else v.to(dev, non_blocking=True))
+                   for k, v in pinned.items()}
+            x_v, x_f = nm(src["x_v"]), [nm(x) for x in src["x_f"]]
+            with torch.no_grad():
+                for l in range(L):
+                    nv, nf = None, []
+                    for j in range(J):
+                        nf.append(mods[l][j]["v2f"](x_v, src["idx_v2f"][j], src["et_v2f"][j]))
+                        y = mods[l][j]["f2v"](x_f[j], src["idx_f2v"][j], src["et_f2v"][j])
+                        nv = y if nv is None else nv + y
+                    x_v, x_f = nv, nf
+            host_out.copy_(x_v[..., 0].permute(0, 2, 1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        if world == 1:
+            for _ in range(2):
+                e2e_step()
+            k = max(3, min(args.steps, 10))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(k):
+                e2e_step()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / k
+            e2e = {"value": msgs_layer * L / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                   "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": k,
+                   "api": "fgnn_b200.mp_conv_v2.forward (20 module calls), pinned host tensors in, pinned host tensor out"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = hbm_peak()
+    achieved = bytes_layer * L / (ms_step * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "messages_per_layer": msgs_layer, "layers": L,
+                   "kernel": args.kernel, "l2": "per-step working set (~%d MB/layer) exceeds the 126 MB L2; no explicit flush"
+                   % (bytes_layer // 1_000_000), "parallelism": ("factor-sharded x%d + NCCL max-all-reduce per layer" % world)
+                   if world > 1 else "single GPU"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "fgnn mp kernel (avg over the step's launches)",
+                     "algorithmic_bytes_per_launch": bytes_layer * L / max(launches / args.steps, 1),
+                     "avg_launch_us": ms_step * 1e3 / max(launches / args.steps, 1)},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"], _ = cpu_baseline(args)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,78 @@
+// Shared device-side definitions for the fgnn_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fgnn_b200.h"
+
+namespace fgnn {
+
+// Device-side view of one message-passing call (fgnn_mp_args after validation).
+struct MpParams {
+  const float* x;
+  const void* idx;
+  const float* et;
+  const float* W;      // filters [Kc, O*T]
+  const float* bias;   // or nullptr
+  const float* scale;  // folded eval-BN or nullptr
+  const float* shift;
+  float* out;
+  int64_t x_sb, x_sc, x_sn;
+  int64_t idx_sb, et_sb;
+  int64_t o_sb, o_so, o_sm, o_sk;
+  int B, N, M, K, C, O, T;
+  int ext, agg, act, idx64, mask_neg, accumulate;
+  float gamma, slope;
+};
+
+__device__ __forceinline__ int64_t load_index(const void* idx, int idx64, int64_t off) {
+  return idx64 ? reinterpret_cast<const int64_t*>(idx)[off]
+               : (int64_t) reinterpret_cast<const int32_t*>(idx)[off];
+}
+
+__device__ __forceinline__ float apply_epilogue(float v, int o, const MpParams& p) {
+  if (p.bias) v += p.bias[o];                                 // mp_nn.py:165-168
+  if (p.scale) v = fmaf(v, p.scale[o], p.shift[o]);           // mp_nn.py:169-170 (eval BN, folded)
+  if (p.act == FGNN_ACT_RELU) v = fmaxf(v, 0.f);              // mp_nn.py:172-173
+  else if (p.act == FGNN_ACT_LEAKY_RELU) v = v >= 0.f ? v : v * p.slope;
+  return v;
+}
+
+// Online aggregator over the K slots of one destination (mp_nn.py:73-87).
+struct AggState {
+  float a;   // max: running max | softmax: running max of gamma*e | mean: running sum
+  float s;   // softmax: running sum of exp(gamma*e - a) | mean: live-slot count
+  __device__ __forceinline__ void init(int agg) {
+    a = (agg == FGNN_AGG_MEAN) ? 0.f : -INFINITY;
+    s = 0.f;
+  }
+  __device__ __forceinline__ void push(float e, int agg, float gamma) {
+    if (agg == FGNN_AGG_MAX) {
+      a = fmaxf(a, e);
+    } else if (agg == FGNN_AGG_SOFTMAX) {
+      const float z = gamma * e;
+      const float m = fmaxf(a, z);
+      s = s * expf(a - m) + expf(z - m);   // a = -inf on first push: exp(-inf) = 0
+      a = m;
+    } else {
+      a += e;
+      s += 1.f;
+    }
+  }
+  __device__ __forceinline__ float finish(int agg, float gamma) const {
+    if (agg == FGNN_AGG_MAX) return a;
+    if (agg == FGNN_AGG_SOFTMAX) return s > 0.f ? (logf(s) + a) / gamma : -INFINITY;
+    return s > 0.f ? a / s : 0.f;
+  }
+};
+
+void count_launch();
+
+int launch_mp_simt(const MpParams& p, cudaStream_t stream);
+
+// tensor-core path (mp_tc.cu)
+bool tc_supported(const fgnn_mp_args* a);
+size_t tc_workspace_bytes(const fgnn_mp_args* a);
+int launch_mp_tc(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream);
+
+}  // namespace fgnn

@@ -1,0 +1,180 @@
+"""The callers that define "one FGNN layer", rebuilt around the native message-passing core.
+
+Mirrors of /root/reference/lib/model/mpnn/factor_mpnn_sp.py (`FVModule` :14-22, `FactorNN` :25-178),
+base_model.py (`iid_mapping*` :43-90) and sequential.py (`mp_sequential` :21-39) with the same
+constructor arguments, forward signatures and state_dict keys, so a checkpoint written by the
+reference loads here and vice versa.  Only the `mp_conv_v2` inside them differs: it is
+fgnn_b200.mp_conv_v2 (one sm_100a kernel per call).  The per-node 1x1 maps and norms either side
+of the core stay in PyTorch.
+"""
+import torch
+
+from .mp_nn import base_mp_nn, mp_conv_residual, mp_conv_type, mp_conv_v2
+
+
+class iid_mapping(torch.nn.Module):
+    """1x1 conv + LeakyReLU per node (base_model.py:43-60)."""
+
+    def __init__(self, nin, nout, bias=True):
+        super().__init__()
+        self.main = torch.nn.Sequential(torch.nn.Conv2d(nin, nout, 1, bias=bias),
+                                        torch.nn.LeakyReLU(inplace=True))
+
+    def forward(self, x):
+        return self.main(x)
+
+
+class iid_mapping_bn(torch.nn.Module):
+    """1x1 conv + BatchNorm + ReLU per node (base_model.py:63-80)."""
+
+    def __init__(self, nin, nout, bias=True, bn=True):
+        super().__init__()
+        self.main = torch.nn.Sequential(torch.nn.Conv2d(nin, nout, 1, bias=bias),
+                                        torch.nn.BatchNorm2d(nout), torch.nn.ReLU(inplace=True))
+
+    def forward(self, x):
+        return self.main(x)
+
+
+class _InstanceNorm2d(torch.nn.InstanceNorm2d):
+    """InstanceNorm2d that also accepts a single spatial element (the LDPC "global" factor has
+    one): PyTorch 1.0, which the reference targets, returned (x - x)/sqrt(eps) = 0 there, newer
+    versions raise (SURVEY 8c shim 1)."""
+
+    def forward(self, x):
+        if x.shape[-1] * x.shape[-2] == 1 and not self.track_running_stats:
+            return torch.zeros_like(x)
+        return super().forward(x)
+
+
+class iid_mapping_in(torch.nn.Module):
+    """1x1 conv + InstanceNorm + ReLU per node (base_model.py:83-90)."""
+
+    def __init__(self, nin, nout, bias=True):
+        super().__init__()
+        self.main = torch.nn.Sequential(torch.nn.Conv2d(nin, nout, 1, bias=bias),
+                                        _InstanceNorm2d(nout), torch.nn.ReLU())
+
+    def forward(self, x):
+        return self.main(x)
+
+
+class mp_sequential(base_mp_nn):
+    """nn.Sequential that passes (x, *graph) to message-passing children (sequential.py:9-39)."""
+
+    def __init__(self, *module_list):
+        super().__init__()
+        self.module_list = []
+        for i, mod in enumerate(module_list):
+            self.add_module(str(i), mod)
+            self.module_list.append(mod)
+
+    def forward(self, node_feature, *argv):
+        extra = []
+        for m in self.module_list:
+            node_feature = m(node_feature, *argv) if isinstance(m, base_mp_nn) else m(node_feature)
+            if isinstance(node_feature, tuple):
+                extra += list(node_feature[1:])
+                node_feature = node_feature[0]
+        return node_feature if not extra else (node_feature, extra)
+
+
+class FVModule(torch.nn.Module):
+    """The FV module: mp_conv_v2(NO_EXTENSION, max) (factor_mpnn_sp.py:14-22)."""
+
+    def __init__(self, nin, nout, nedge_types, with_bn=True):
+        super().__init__()
+        self.main_module = mp_conv_v2(nin, nout, nedge_types, bn=with_bn,
+                                      extension=mp_conv_type.NO_EXTENSION, aggregtor='max')
+
+    def forward(self, n_or_f_feature, nn_idx, etype):
+        return self.main_module(n_or_f_feature, nn_idx, etype)
+
+
+class FactorNN(torch.nn.Module):
+    """Stacked FGNN with split Variable->Factor / Factor->Variable tables (factor_mpnn_sp.py:25-178).
+
+    Per layer `i` and factor type `j`:  nfeature = v2v_i(x_v) + sum_j f2v_ij(x_fj, idx_f2v_j, et_f2v_j);
+    nffeature_j = f2f_ij(x_fj) + v2f_ij(x_v, idx_v2f_j, et_v2f_j); residual when nin == nout; skip links.
+    """
+
+    def __init__(self, node_feature_dim, factor_feature_dim_list, dim_mapping_list, netype_list,
+                 nclass=2, gnn_immediate_dim=64, max_mpnn_dim=128, final_filter=None, skip_link={},
+                 aggregator='max', ret_high=False):
+        super().__init__()
+        self.node_feature_dim = node_feature_dim
+        self.map_dim = dim_mapping_list[0]
+        self.final_filter = final_filter
+        self.node_mapping_module = iid_mapping(node_feature_dim, self.map_dim)
+        self.nfactor_types = len(factor_feature_dim_list)
+        self.factor_mapping_modules = []
+        for j, dim in enumerate(factor_feature_dim_list):
+            m = iid_mapping_bn(dim, self.map_dim)
+            self.factor_mapping_modules.append(m)
+            self.add_module('factor_mapping_modules_{}'.format(j), m)
+        self.f2v_modules, self.v2f_modules, self.f2f_modules, self.v2v_modules = [], [], [], []
+        self.dim_mapping_list = dim_mapping_list
+        none = mp_conv_type.NO_EXTENSION
+        for i in range(len(dim_mapping_list) - 1):
+            nin, nout = dim_mapping_list[i], dim_mapping_list[i + 1]
+            self.v2v_modules.append(iid_mapping_in(nin, nout))
+            self.add_module('v2v_{}'.format(i), self.v2v_modules[-1])
+            f2v, v2f, f2f = [], [], []
+            for j in range(self.nfactor_types):
+                netype = netype_list[j]
+                f2f.append(iid_mapping_in(nin, nout))
+
+                def core():
+                    if nin == nout:                                    # factor_mpnn_sp.py:79-83
+                        return mp_conv_residual(nin, gnn_immediate_dim, netype, extension=none,
+                                                with_residual=False, aggregator=aggregator)
+                    if nin <= max_mpnn_dim and nout <= max_mpnn_dim:   # :85-89
+                        return mp_conv_v2(nin, nout, netype, extension=none, aggregtor=aggregator)
+                    return mp_conv_residual(nin, gnn_immediate_dim, netype, extension=none,   # :90-94
+                                            with_residual=False, nout=nout, aggregator=aggregator)
+                f2v.append(core())
+                v2f.append(core())
+                self.add_module('f2v_{}_{}'.format(i, j), f2v[-1])
+                self.add_module('v2f_{}_{}'.format(i, j), v2f[-1])
+                self.add_module('f2f_{}_{}'.format(i, j), f2f[-1])
+            self.f2f_modules.append(f2f)
+            self.f2v_modules.append(f2v)
+            self.v2f_modules.append(v2f)
+        self.skip_link = skip_link
+        self.ret_high = ret_high
+        final_dim = nclass if nclass > 2 else 1
+        self.final_classifier = torch.nn.Sequential(
+            torch.nn.Conv2d(dim_mapping_list[-1], 128, 1), _InstanceNorm2d(128),
+            torch.nn.ReLU(inplace=True), torch.nn.Conv2d(128, final_dim, 1, bias=True))
+
+    def mpnn_forward(self, mpnn, node_feature, nn_idx, efeature):
+        if isinstance(mpnn, base_mp_nn):
+            return mpnn(node_feature, nn_idx, efeature)
+        return mpnn(node_feature)
+
+    def forward(self, node_feature, hop_features, nn_idx_f2v, nn_idx_v2f, etype_f2v, etype_v2f):
+        x_v = self.node_mapping_module(node_feature)
+        x_f = [m(f) for f, m in zip(hop_features, self.factor_mapping_modules)]
+        history = []
+        for i in range(len(self.v2f_modules)):
+            nin, nout = self.dim_mapping_list[i], self.dim_mapping_list[i + 1]
+            new_v = self.v2v_modules[i](x_v)
+            new_f = [m(f) for f, m in zip(x_f, self.f2f_modules[i])]
+            for j in range(len(self.f2v_modules[i])):
+                new_v = new_v + self.mpnn_forward(self.f2v_modules[i][j], x_f[j],
+                                                  nn_idx_f2v[j].long(), etype_f2v[j])
+                new_f[j] = new_f[j] + self.v2f_modules[i][j](x_v, nn_idx_v2f[j].long(), etype_v2f[j])
+            if nin == nout:
+                x_v = x_v + new_v
+                x_f = [a + b for a, b in zip(new_f, x_f)]
+            else:
+                x_v, x_f = new_v, new_f
+            if i in self.skip_link.keys():
+                old_v, old_f = history[self.skip_link[i]]
+                x_v = x_v + old_v
+                x_f = [a + b for a, b in zip(old_f, x_f)]
+            history.append([x_v, x_f])
+        res = self.final_classifier(x_v)
+        if self.final_filter is not None:
+            res = self.final_filter(res, node_feature)
+        return (res, x_f) if self.ret_high else res

@@ -1,0 +1,143 @@
+"""Seeded synthetic factor-graph index tables in the reference's input layout (host side, numpy).
+
+The hot path takes dense rectangular neighbour tables `nn_idx [M, K]` (int64) per factor type and
+direction, exactly as the reference's table builders emit them:
+  * Variable->Factor: `idx_v2f [F, K]`  -- row f lists the K variables of factor f;
+  * Factor->Variable: `idx_f2v [N, Kv]` -- row v lists the (up to Kv) factors variable v is in;
+    unused slots hold a VALID index (0) whose edge-type vector is all-zero, so the slot contributes a
+    0-valued message that takes part in the max -- the reference's padding convention
+    (lib/data/ldpc_dataset.py:36-37; last slot of generate_knn_table, train_syn_fixed_pw_hop.py:86-101).
+`real_*` counts exclude padding (the message count of the metric).
+"""
+import numpy as np
+
+
+class FactorType:
+    """Tables of one factor type: F factors of order K over N variables."""
+
+    def __init__(self, idx_v2f, idx_f2v, pad_f2v, name):
+        self.idx_v2f = np.ascontiguousarray(idx_v2f, dtype=np.int64)      # [F, K]  values in [0, N)
+        self.idx_f2v = np.ascontiguousarray(idx_f2v, dtype=np.int64)      # [N, Kv] values in [0, F)
+        self.pad_f2v = np.ascontiguousarray(pad_f2v, dtype=bool)          # [N, Kv] True = padding slot
+        self.name = name
+
+    @property
+    def n_factors(self):
+        return self.idx_v2f.shape[0]
+
+    @property
+    def order(self):
+        return self.idx_v2f.shape[1]
+
+    @property
+    def n_vars(self):
+        return self.idx_f2v.shape[0]
+
+    @property
+    def kv(self):
+        return self.idx_f2v.shape[1]
+
+    @property
+    def real_messages(self):
+        """Real (destination, slot) evaluations per FGNN layer, both directions: 2 * F * K."""
+        return 2 * self.n_factors * self.order
+
+
+def _var_side_table(idx_v2f, n_vars, kv=None):
+    """Transpose a [F,K] factor->variables table into the padded [N,Kv] variable->factors table."""
+    F, K = idx_v2f.shape
+    flat_v = idx_v2f.reshape(-1)
+    flat_f = np.repeat(np.arange(F, dtype=np.int64), K)
+    order = np.argsort(flat_v, kind="stable")
+    v_sorted, f_sorted = flat_v[order], flat_f[order]
+    deg = np.bincount(flat_v, minlength=n_vars)
+    kmax = int(deg.max()) if deg.size else 0
+    if kv is None:
+        kv = max(kmax, 1)
+    if kmax > kv:
+        raise ValueError(f"a variable has {kmax} incident factors, table width is {kv}")
+    start = np.concatenate([[0], np.cumsum(deg)[:-1]])
+    slot = np.arange(v_sorted.size) - np.repeat(start, deg)
+    idx = np.zeros((n_vars, kv), dtype=np.int64)
+    pad = np.ones((n_vars, kv), dtype=bool)
+    idx[v_sorted, slot] = f_sorted
+    pad[v_sorted, slot] = False
+    return idx, pad
+
+
+def random_factor_type(n_vars, n_factors, order, rng, local_band=0, name="factors"):
+    """`n_factors` factors of `order` distinct-ish variables each, built from random permutations
+    so that variable degrees are as even as possible (n_factors*order / n_vars, +-1).
+    local_band > 0: every factor's variables lie within a window of that many consecutive
+    variables (graphs with index locality: chains, kNN, LDPC-like)."""
+    total = n_factors * order
+    if local_band > 0:
+        base = rng.integers(0, n_vars, size=n_factors)
+        offs = rng.integers(0, local_band, size=(n_factors, order))
+        offs[:, 0] = 0
+        idx_v2f = (base[:, None] + offs) % n_vars
+    else:
+        reps = -(-total // n_vars)
+        pool = np.concatenate([rng.permutation(n_vars) for _ in range(reps)])[:total]
+        # column-major fill: column j of the table is (a slice of) one permutation, so the
+        # variables of one factor come from different permutations
+        idx_v2f = pool.reshape(order, n_factors).T
+    idx_f2v, pad = _var_side_table(idx_v2f, n_vars)
+    return FactorType(idx_v2f, idx_f2v, pad, name)
+
+
+def synthetic_map_graph(n_vars, n_pairwise, n_high, high_order, seed=0, local_band=0):
+    """The synthetic MAP-inference graph of BASELINE.json configs[1]/[3]: `n_pairwise` order-2
+    factors plus `n_high` factors of order `high_order` over `n_vars` variables."""
+    rng = np.random.default_rng(seed)
+    types = [random_factor_type(n_vars, n_pairwise, 2, rng, local_band, "pairwise")]
+    if n_high > 0:
+        types.append(random_factor_type(n_vars, n_high, high_order, rng, local_band,
+                                        f"order{high_order}"))
+    return types
+
+
+def chain_knn_table(n, k):
+    """Chain-MRF neighbour table with the semantics of the reference's generate_knn_table
+    (train_syn_fixed_pw_hop.py:86-101): node i lists its k//2 left neighbours i-k//2..i-1 and its
+    k//2 - 1 right neighbours i+1..i+k//2-1, clamped to [0, n-1]; the edge feature is the signed
+    distance i - j after clamping; the last slot is never filled and stays (index 0, feature 0) --
+    the reference's pad.  Returns (nn_idx [1,n,k] int64, efeature [1,1,n,k] float32)."""
+    hk = k // 2
+    offs = np.concatenate([np.arange(-hk, 0), np.arange(1, hk)]).astype(np.int64)   # k-1 offsets
+    i = np.arange(n, dtype=np.int64)[:, None]
+    j = np.clip(i + offs[None, :], 0, n - 1)
+    idx = np.zeros((1, n, k), dtype=np.int64)
+    ef = np.zeros((1, 1, n, k), dtype=np.float32)
+    idx[0, :, :offs.size] = j
+    ef[0, 0, :, :offs.size] = (i - j).astype(np.float32)
+    return idx, ef
+
+
+def parse_alist(text):
+    """Parse a MacKay `alist` parity-check description (the format of
+    ldpc_codes/96.3.963/96.3.963, read by lib/data/ldpc_dataset.py:26-49).  Returns
+    (var_to_checks [N, max_col_w], check_to_vars [M, max_row_w]) 0-based, -1 = unused slot."""
+    tok = text.split()
+    pos = 0
+
+    def take(n):
+        nonlocal pos
+        vals = [int(t) for t in tok[pos:pos + n]]
+        pos += n
+        return vals
+    n, m = take(2)
+    cw, rw = take(2)
+    col_w = take(n)
+    row_w = take(m)
+    v2c = -np.ones((n, cw), dtype=np.int64)
+    c2v = -np.ones((m, rw), dtype=np.int64)
+    for i in range(n):
+        vals = take(cw)
+        for j in range(col_w[i]):
+            v2c[i, j] = vals[j] - 1
+    for i in range(m):
+        vals = take(rw)
+        for j in range(row_w[i]):
+            c2v[i, j] = vals[j] - 1
+    return v2c, c2v

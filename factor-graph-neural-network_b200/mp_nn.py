@@ -1,0 +1,357 @@
+"""Host-side mirror of the reference's message-passing module, backed by libfgnn_b200.so.
+
+`mp_conv_v2` keeps the constructor / forward / state_dict surface of the reference class
+(/root/reference/lib/model/mpnn/mp_nn.py:13-175) -- including the misspelt `aggregtor` kwarg, the
+public attributes `.nin .nou .nedge_types .extension .filters .bias .bn .activation_fn .aggregtor`
+and the `base_mp_nn` marker base (base_model.py:4-16) that callers dispatch on -- but its forward
+marshals raw device pointers and the current CUDA stream into ONE C-ABI call
+(`fgnn_mp_forward`, include/fgnn_b200.h) instead of the ATen op chain
+permute -> mm -> repeat -> gather -> bmm -> max -> bias -> BN -> ReLU.
+
+There is no CPU or PyTorch fallback: a CPU tensor, a missing library or a failing call raises.
+Autograd and train-mode BatchNorm statistics are not part of this boundary:
+forward under `torch.no_grad()` / `.eval()` is the contract; train-mode BN is served by running
+the kernel up to the bias add and handing the result to the module's own `bn`.
+"""
+import ctypes
+from enum import Enum
+
+import torch
+
+from . import _lib
+
+SyncBatchNorm = torch.nn.BatchNorm2d      # the reference's alias (mp_nn.py:4)
+
+
+class mp_conv_type(Enum):                 # mp_nn.py:7-10
+    NO_EXTENSION = 0
+    ORIG_WITH_NEIGHBOR = 1
+    ORIG_WITH_DIFF = 2
+
+
+class base_mp_nn(torch.nn.Module):
+    """Marker base class callers dispatch on with isinstance (base_model.py:4-16)."""
+    NO_EXTENSION = 0
+    ORIG_WITH_NEIGHBOR = 1
+    ORIG_WITH_DIFF = 2
+
+    def __init__(self):
+        super().__init__()
+        self.is_mp_nn = True
+
+
+_SOFTMAX_GAMMA = 3.0                      # agg_softmax default gamma, mp_nn.py:80
+
+# nn_idx tables are static across layers and steps; validating them (the reference gets this from
+# ATen's gather, mp_nn.py:111) costs a device sync, so remember which tables already passed.
+_validated_tables = {}
+_VALIDATED_MAX = 256
+
+
+def _table_key(nn_idx, n_src):
+    return (nn_idx.data_ptr(), tuple(nn_idx.shape), tuple(nn_idx.stride()), nn_idx._version,
+            nn_idx.device.index, n_src)
+
+
+def clear_table_cache():
+    _validated_tables.clear()
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _fold_bn(bn):
+    """Eval-mode BatchNorm2d folded to y = x * scale + shift (mp_nn.py:169-170)."""
+    rv, rm = bn.running_var, bn.running_mean
+    scale = torch.rsqrt(rv.float() + bn.eps)
+    if bn.weight is not None:
+        scale = scale * bn.weight.detach().float()
+    shift = -rm.float() * scale
+    if bn.bias is not None:
+        shift = shift + bn.bias.detach().float()
+    return scale.contiguous(), shift.contiguous()
+
+
+class _Workspace:
+    """Per-device scratch for the tensor-core kernel's split-bf16 weight image."""
+    bufs = {}
+
+    @classmethod
+    def get(cls, device, nbytes):
+        key = (device.index, )
+        buf = cls.bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+            cls.bufs[key] = buf
+        return buf
+
+
+def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=None, *,
+               extension=0, aggregator=_lib.AGG_MAX, activation=_lib.ACT_RELU, act_slope=0.01,
+               gamma=_SOFTMAX_GAMMA, kernel=_lib.KERNEL_AUTO, mask_negative=False, validate=True,
+               out=None, accumulate=False, workspace=None, filters_version=0):
+    """Functional form of the hot path: one `fgnn_mp_forward` call on x's device / current stream.
+
+    x [B,C,N,1] or [B,C,N] (any strides; node-major == channels_last is the fast layout),
+    nn_idx [B,M,K] int64/int32, etype [B,T,M,K], filters [C or 2C, O*T] fp32.
+    Returns [B,O,M,1] ([B,O,M,K] for AGG_NONE) with node-major (channels_last) memory.
+    """
+    if not x.is_cuda:
+        raise RuntimeError("fgnn_b200: mp_conv_v2.forward needs CUDA tensors (there is no CPU "
+                           "fallback for this path; the CPU oracle lives under oracle/ for tests)")
+    lib = _lib.lib()
+    if x.dim() == 4:
+        if x.shape[3] != 1:
+            raise ValueError("x must be [B, nin, N, 1]")
+        x3 = x[..., 0]
+    elif x.dim() == 3:
+        x3 = x
+    else:
+        raise ValueError("x must be [B, nin, N, 1]")
+    if x3.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("fgnn_b200: x must be float32 or bfloat16")
+    dev = x.device
+    B, C, N = x3.shape
+    if nn_idx.dim() != 3 or etype.dim() != 4:
+        raise ValueError("nn_idx must be [B,M,K] and etype [B,T,M,K]")
+    assert B == nn_idx.shape[0]                       # mp_nn.py:100
+    _, M, K = nn_idx.shape
+    T = etype.shape[1]
+    if tuple(etype.shape) != (B, T, M, K):
+        raise ValueError(f"etype shape {tuple(etype.shape)} does not match [B={B},T,M={M},K={K}]")
+    if nn_idx.device != dev or etype.device != dev or filters.device != dev:
+        raise RuntimeError("fgnn_b200: x, nn_idx, etype and the module must be on the same device")
+    if nn_idx.dtype not in (torch.int64, torch.int32):
+        nn_idx = nn_idx.long()
+    # index table: rows contiguous, batch stride free (0 for .expand()-ed tables)
+    if nn_idx.stride(2) != 1 or nn_idx.stride(1) != K:
+        nn_idx = nn_idx.contiguous()
+    idx_sb = nn_idx.stride(0) if B > 1 else M * K
+    if etype.dtype != x3.dtype:
+        etype = etype.to(x3.dtype)
+    if etype.stride(3) != 1 or etype.stride(2) != K or etype.stride(1) != M * K:
+        etype = etype.contiguous()
+    et_sb = etype.stride(0) if B > 1 else T * M * K
+    OT = filters.shape[1]
+    if OT % T != 0:
+        raise ValueError("filters.shape[1] must be nou * nedge_types")
+    O = OT // T
+    rows = C if extension == 0 else 2 * C
+    if filters.shape[0] != rows:
+        raise RuntimeError(f"fgnn_b200: filters has {filters.shape[0]} rows, expected {rows}")
+    filters = filters.detach()
+    if filters.dtype != torch.float32 or not filters.is_contiguous():
+        filters = filters.float().contiguous()
+    if bias is not None:
+        bias = bias.detach().float().contiguous()
+    Kout = K if aggregator == _lib.AGG_NONE else 1
+    out_given = out
+    if out is None:
+        out = torch.empty((B, O, M, Kout), dtype=x3.dtype, device=dev,
+                          memory_format=torch.channels_last)
+    elif tuple(out.shape) != (B, O, M, Kout) or out.dtype != x3.dtype or out.device != dev:
+        raise ValueError("out has the wrong shape, dtype or device")
+    if B * M * K == 0 or N == 0:
+        if N == 0 and B * M * K > 0:
+            raise IndexError("fgnn_b200: nn_idx entry out of range (no source nodes)")
+        return out
+
+    if validate:
+        key = _table_key(nn_idx, N)
+        if key not in _validated_tables:
+            flag = torch.empty(2, dtype=torch.int32, device=dev)
+            lo = -(2 ** 63) if mask_negative else 0
+            with torch.cuda.device(dev):
+                rc = lib.fgnn_check_index_range(
+                    _ptr(nn_idx), _lib.I64 if nn_idx.dtype == torch.int64 else _lib.I32,
+                    nn_idx.numel() if nn_idx.stride(0) != 0 else M * K, lo, N, _ptr(flag),
+                    ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            _lib.check(rc, "check_index_range")
+            if len(_validated_tables) >= _VALIDATED_MAX:
+                _validated_tables.clear()
+            _validated_tables[key] = True
+
+    a = _lib.MpArgs()
+    a.x, a.idx, a.etype, a.filters = x3.data_ptr(), nn_idx.data_ptr(), etype.data_ptr(), filters.data_ptr()
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.bn_scale = bn_scale.data_ptr() if bn_scale is not None else None
+    a.bn_shift = bn_shift.data_ptr() if bn_shift is not None else None
+    a.out = out.data_ptr()
+    a.x_sb, a.x_sc, a.x_sn = x3.stride(0), x3.stride(1), x3.stride(2)
+    a.idx_sb, a.et_sb = idx_sb, et_sb
+    a.out_sb, a.out_so, a.out_sm, a.out_sk = out.stride(0), out.stride(1), out.stride(2), out.stride(3)
+    a.B, a.N, a.M, a.K, a.C, a.O, a.T = B, N, M, K, C, O, T
+    a.extension, a.aggregator, a.activation = int(extension), int(aggregator), int(activation)
+    a.dtype = _lib.F32 if x3.dtype == torch.float32 else _lib.BF16
+    a.idx_dtype = _lib.I64 if nn_idx.dtype == torch.int64 else _lib.I32
+    a.kernel = int(kernel)
+    a.flags = (_lib.FLAG_MASK_NEGATIVE if mask_negative else 0) | (_lib.FLAG_ACCUMULATE if accumulate else 0)
+    if accumulate and out_given is None:
+        raise ValueError("accumulate=True needs an `out` tensor to add into")
+    a.gamma, a.act_slope = float(gamma), float(act_slope)
+    a.filters_version = int(filters_version)
+    a.workspace, a.workspace_bytes = None, 0
+    with torch.cuda.device(dev):
+        need = lib.fgnn_mp_workspace_bytes(ctypes.byref(a))
+        if need:
+            ws = workspace if workspace is not None and workspace.numel() >= need else _Workspace.get(dev, need)
+            a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+            if ws is not workspace:
+                a.filters_version = 0        # shared scratch: never trust a cached weight image
+        rc = lib.fgnn_mp_forward(ctypes.byref(a),
+                                 ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "mp_forward")
+    return out
+
+
+class mp_conv_v2(base_mp_nn):
+    """Message passing layer (VF and FV module of FGNN); reference mp_nn.py:13-175.
+
+    out[b,o,m] = act(BN(bias[o] + AGG_k sum_t etype[b,t,m,k] * (xin(b,m,k) . filters[:, o*T+t])))
+    """
+
+    def __init__(self, nin, nou, nedge_types, bias=True, bn=True,
+                 extension=mp_conv_type.ORIG_WITH_DIFF, activation_fn='relu', aggregtor='softmax'):
+        super().__init__()
+        self.nin = nin
+        self.nou = nou
+        self.nedge_types = nedge_types
+        self.extension = extension
+        if extension == mp_conv_type.NO_EXTENSION:
+            rows = nin
+        elif extension in (mp_conv_type.ORIG_WITH_DIFF, mp_conv_type.ORIG_WITH_NEIGHBOR):
+            rows = 2 * nin
+        else:
+            raise ValueError("extension must one of mp_conv_type")          # mp_nn.py:47-48
+        self.filters = torch.nn.Parameter(torch.zeros(rows, nou * nedge_types, dtype=torch.float32))
+        self.filters.data.uniform_(-0.01, 0.01)                             # mp_nn.py:49
+        if bias:
+            self.bias = torch.nn.Parameter(torch.zeros(nou))
+            self.bias.data.uniform_(0, 0.05)                                # mp_nn.py:53
+        else:
+            self.bias = None
+        self.bn = SyncBatchNorm(nou) if bn else None
+        if isinstance(activation_fn, torch.nn.Module):
+            self.activation_fn = activation_fn
+        elif activation_fn == 'relu':
+            self.activation_fn = torch.nn.ReLU(inplace=True)
+        else:
+            self.activation_fn = None
+        # aggregator: the reference stores a closure; we keep a callable of the same meaning on
+        # `.aggregtor` (public attribute) and the enum the kernel takes on `._agg`.
+        self._agg = None
+        if isinstance(aggregtor, str):
+            if aggregtor == 'max':
+                self._agg = _lib.AGG_MAX
+                self.aggregtor = lambda v: torch.max(v, dim=3, keepdim=True)[0]
+            elif aggregtor == 'softmax':
+                self._agg = _lib.AGG_SOFTMAX
+                self.aggregtor = lambda v, gamma=_SOFTMAX_GAMMA: \
+                    1.0 / gamma * torch.logsumexp(gamma * v, dim=3, keepdim=True)
+            elif aggregtor == 'mean':
+                self._agg = _lib.AGG_MEAN
+                self.aggregtor = lambda v: torch.mean(v, dim=3, keepdim=True)
+            # any other string leaves .aggregtor unset, like the reference (AttributeError at forward)
+        else:
+            self.aggregtor = aggregtor
+            if aggregtor is None:
+                self._agg = _lib.AGG_NONE
+        self.kernel = _lib.KERNEL_AUTO
+        self._ws = None
+
+    # -- kernel-side description of the epilogue ------------------------------------------------
+    def _activation_code(self):
+        act = self.activation_fn
+        if act is None:
+            return _lib.ACT_NONE, 0.0, None
+        if isinstance(act, torch.nn.ReLU):
+            return _lib.ACT_RELU, 0.0, None
+        if isinstance(act, torch.nn.LeakyReLU):
+            return _lib.ACT_LEAKY_RELU, float(act.negative_slope), None
+        return _lib.ACT_NONE, 0.0, act                 # arbitrary Module: applied after the kernel
+
+    def _filters_version(self):
+        # changes whenever `filters` is re-assigned, moved or written in place through autograd-visible ops
+        f = self.filters
+        return ((f._version + 1) * 1000003 + (f.data_ptr() >> 4)) & 0x7fffffffffffffff or 1
+
+    def _workspace_for(self, x):
+        """Private scratch so the split-bf16 image of `filters` is cached across calls."""
+        return self._ws if self._ws is not None and self._ws.device == x.device else None
+
+    def forward(self, x, nn_idx, etype):
+        aggregtor = self.aggregtor                        # AttributeError for an unknown string
+        if self.training and torch.is_grad_enabled() and (
+                self.filters.requires_grad or x.requires_grad or etype.requires_grad):
+            # eval-mode forwards (the scripts' test phases call model.eval() without no_grad, e.g.
+            # train_syn_fixed_pw_hop.py:313) just return a tensor outside the autograd graph
+            raise NotImplementedError(
+                "fgnn_b200.mp_conv_v2 is forward-only (autograd is outside this boundary, SURVEY 8b/8f): "
+                "call .eval() or torch.no_grad(), or use the reference module for training")
+        ext = self.extension.value if isinstance(self.extension, mp_conv_type) else int(self.extension)
+        act_code, slope, post_act = self._activation_code()
+        fused_agg = self._agg if self._agg is not None else _lib.AGG_NONE
+        custom_agg = self._agg is None and aggregtor is not None          # user callable
+        bn_train = self.bn is not None and (self.bn.training or self.bn.running_mean is None)
+        fuse_tail = not custom_agg and not bn_train
+        scale = shift = None
+        if fuse_tail and self.bn is not None:
+            scale, shift = _fold_bn(self.bn)
+        ws = self._workspace_for(x)
+        out = mp_forward(
+            x, nn_idx, etype, self.filters,
+            bias=self.bias if (fuse_tail or not custom_agg) else None,
+            bn_scale=scale, bn_shift=shift, extension=ext, aggregator=fused_agg,
+            activation=act_code if fuse_tail else _lib.ACT_NONE, act_slope=slope,
+            kernel=self.kernel, workspace=ws,
+            filters_version=self._filters_version() if ws is not None else 0)
+        if fuse_tail:
+            return post_act(out) if post_act is not None else out
+        # tail in PyTorch: user aggregator and/or train-mode batch statistics (mp_nn.py:162-173)
+        if custom_agg:
+            out = aggregtor(out)
+            if self.bias is not None:
+                out = out + self.bias.view(1, self.nou, 1, 1)
+        if self.bn is not None:
+            out = self.bn(out)
+        if self.activation_fn is not None:
+            out = self.activation_fn(out)
+        return out
+
+    def enable_weight_cache(self, device=None):
+        """Give this module a private workspace so the tensor-core kernel converts `filters`
+        to its split-bf16 image once per weight version instead of once per call."""
+        device = torch.device(device) if device is not None else self.filters.device
+        if device.type != "cuda":
+            raise RuntimeError("enable_weight_cache needs a CUDA device")
+        rows = self.filters.shape[0]
+        nbytes = rows * self.nou * self.nedge_types * 4 + 4096
+        self._ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        return self
+
+
+class mp_conv_residual(base_mp_nn):
+    """conv1 (1x1 + BN + LeakyReLU) -> mp_conv_v2 -> conv2 (1x1 + BN + LeakyReLU) [+ residual];
+    reference mp_nn_residual.py:8-56.  The 1x1 maps stay in PyTorch."""
+
+    def __init__(self, nin, nmed, netype, extension=mp_conv_type.ORIG_WITH_DIFF, with_residual=True,
+                 with_hop=False, aggregator='max', nout=None):
+        super().__init__()
+        self.conv1 = torch.nn.Sequential(torch.nn.Conv2d(nin, nmed, 1), SyncBatchNorm(nmed),
+                                         torch.nn.LeakyReLU(inplace=True))
+        self.mp_conv = mp_conv_v2(nmed, nmed, netype, extension=extension, aggregtor=aggregator)
+        if nout is None:
+            nout = nin
+        self.conv2 = torch.nn.Sequential(torch.nn.Conv2d(nmed, nout, 1), SyncBatchNorm(nout),
+                                         torch.nn.LeakyReLU(inplace=True))
+        self.with_residual = with_residual
+        self.with_hop = with_hop
+
+    def forward(self, node_feature, nn_idx, etype):
+        nfeature = self.conv1(node_feature)
+        nfeature = self.mp_conv(nfeature, nn_idx, etype)
+        nfeature = self.conv2(nfeature)
+        if self.with_residual:
+            nfeature = nfeature + node_feature
+        return nfeature

@@ -1,0 +1,156 @@
+/* fgnn_b200 -- C ABI of the B200-native FGNN message-passing hot path.
+ *
+ * This is the drop-in boundary for ONE path of zzhang1987/Factor-Graph-Neural-Network: the
+ * Variable->Factor / Factor->Variable message-passing layer `mp_conv_v2.forward`
+ * (reference lib/model/mpnn/mp_nn.py:115-175) with its gather (mp_nn.py:92-113), aggregators
+ * (mp_nn.py:73-87) and bias / BatchNorm / activation epilogue (mp_nn.py:165-173).
+ *
+ * The reference has no FFI of its own on this path (it is Python over ATen), so the entry points
+ * below are what a ctypes binding inside the reference's `mp_conv_v2.forward` calls; the binding
+ * is shown in INTEGRATION.md and implemented in factor-graph-neural-network_b200/mp_nn.py.
+ *
+ * Conventions: plain C, no torch types; every pointer in fgnn_mp_args is a DEVICE pointer unless
+ * the function name ends in `_host`; functions never allocate device memory, never synchronise the
+ * device (except the `_host` and `_check_` helpers, which say so) and never throw: they return 0 or
+ * a negative fgnn_status.  All launches go to the `stream` argument (a cudaStream_t).  Re-entrant.
+ */
+#ifndef FGNN_B200_H_
+#define FGNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FGNN_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum fgnn_status {
+  FGNN_OK = 0,
+  FGNN_ERR_INVALID_ARG = -1,    /* NULL pointer, non-positive dimension, unknown enum value       */
+  FGNN_ERR_INDEX_RANGE = -2,    /* nn_idx entry outside [0,N) (reference: ATen gather error)      */
+  FGNN_ERR_SHAPE = -3,          /* extension mode with M != N (reference requires M == N,
+                                   mp_nn.py:136-159), or filters rows != C / 2C                    */
+  FGNN_ERR_UNSUPPORTED = -4,    /* shape/dtype the selected kernel cannot run                      */
+  FGNN_ERR_WORKSPACE = -5,      /* workspace too small (see fgnn_mp_workspace_bytes)               */
+  FGNN_ERR_CUDA = -6,           /* a CUDA runtime call failed; fgnn_last_cuda_error() has the code */
+  FGNN_ERR_NO_DEVICE = -7       /* no sm_100 device                                                */
+} fgnn_status;
+
+/* mp_conv_type, reference mp_nn.py:7-10 (same integer values; also base_model.py:6-8) */
+typedef enum fgnn_extension {
+  FGNN_NO_EXTENSION = 0,
+  FGNN_ORIG_WITH_NEIGHBOR = 1,
+  FGNN_ORIG_WITH_DIFF = 2
+} fgnn_extension;
+
+/* aggregtor, reference mp_nn.py:68-90 */
+typedef enum fgnn_aggregator {
+  FGNN_AGG_MAX = 0,      /* agg_max, mp_nn.py:73-75                              */
+  FGNN_AGG_SOFTMAX = 1,  /* 1/gamma * logsumexp(gamma * x), mp_nn.py:80-83       */
+  FGNN_AGG_MEAN = 2,     /* mp_nn.py:87                                          */
+  FGNN_AGG_NONE = 3      /* aggregtor=None: output keeps the K axis, mp_nn.py:162 */
+} fgnn_aggregator;
+
+typedef enum fgnn_activation {
+  FGNN_ACT_NONE = 0,
+  FGNN_ACT_RELU = 1,     /* mp_nn.py:63-64 */
+  FGNN_ACT_LEAKY_RELU = 2 /* slope in act_slope; used when the module was given nn.LeakyReLU */
+} fgnn_activation;
+
+typedef enum fgnn_dtype { FGNN_F32 = 0, FGNN_BF16 = 1 } fgnn_dtype;
+typedef enum fgnn_index_dtype { FGNN_I64 = 0, FGNN_I32 = 1 } fgnn_index_dtype;
+
+typedef enum fgnn_kernel {
+  FGNN_KERNEL_AUTO = 0,    /* tensor-core kernel when the shape qualifies, else SIMT */
+  FGNN_KERNEL_SIMT = 1,    /* fp32 CUDA-core kernel, every shape                    */
+  FGNN_KERNEL_TCGEN05 = 2  /* tcgen05/TMEM kernel; FGNN_ERR_UNSUPPORTED if the shape does not qualify */
+} fgnn_kernel;
+
+enum {
+  /* a negative nn_idx entry marks an EMPTY slot that is excluded from the aggregate (shard-local
+     F2V tables); a destination with no live slot yields -inf (max/softmax) or 0 (mean).
+     Without this flag negative entries are out of range, as in the reference. */
+  FGNN_FLAG_MASK_NEGATIVE = 1u,
+  /* out += result instead of out = result: fuses the caller's `nfeature = nfeature + nv`
+     (FactorNN, factor_mpnn_sp.py:147,151) into the store.  Not valid with FGNN_AGG_NONE. */
+  FGNN_FLAG_ACCUMULATE = 2u
+};
+
+/* One message-passing call: out[b,o,m] = act(BN(bias[o] + AGG_k sum_t etype[b,t,m,k] *
+ *                                     sum_c xin(b,m,k)[c] * filters[c, o*T+t]))
+ * with xin = x[b,:,idx[b,m,k]] (NO_EXTENSION), [x[b,:,m] || x[b,:,idx]] (NEIGHBOR) or
+ * [x[b,:,m] || x[b,:,m]-x[b,:,idx]] (DIFF).  Strides are in ELEMENTS. */
+typedef struct fgnn_mp_args {
+  const void* x;          /* logical [B,C,N]: element (b,c,n) at x[b*x_sb + c*x_sc + n*x_sn]            */
+  const void* idx;        /* logical [B,M,K] int64|int32: (b,m,k) at idx[b*idx_sb + m*K + k]; idx_sb may be 0 */
+  const void* etype;      /* logical [B,T,M,K]: (b,t,m,k) at etype[b*et_sb + (t*M + m)*K + k]; et_sb may be 0   */
+  const float* filters;   /* [C or 2C, O*T] fp32, row-major, column o*T+t (mp_nn.py:41-46)              */
+  const float* bias;      /* [O] or NULL (mp_nn.py:51-55)                                               */
+  const float* bn_scale;  /* [O] or NULL: gamma / sqrt(running_var + eps)  (eval BatchNorm folded)      */
+  const float* bn_shift;  /* [O] or NULL: beta - running_mean * bn_scale                                */
+  void* out;              /* logical [B,O,M,Kout]: (b,o,m,k) at out[b*out_sb + o*out_so + m*out_sm + k*out_sk] */
+  void* workspace;        /* device scratch, >= fgnn_mp_workspace_bytes(args), 256-byte aligned, or NULL */
+  size_t workspace_bytes;
+  int64_t x_sb, x_sc, x_sn;
+  int64_t idx_sb, et_sb;
+  int64_t out_sb, out_so, out_sm, out_sk;
+  int32_t B, N, M, K, C, O, T;
+  int32_t extension;      /* fgnn_extension   */
+  int32_t aggregator;     /* fgnn_aggregator  */
+  int32_t activation;     /* fgnn_activation  */
+  int32_t dtype;          /* fgnn_dtype of x / etype / out (filters, bias, bn always fp32) */
+  int32_t idx_dtype;      /* fgnn_index_dtype */
+  int32_t kernel;         /* fgnn_kernel      */
+  uint32_t flags;
+  float gamma;            /* softmax aggregator temperature (reference: 3)  */
+  float act_slope;        /* LeakyReLU negative slope                      */
+  int64_t filters_version;/* any value that changes when `filters` changes (the tensor-core path caches
+                             its bf16 weight image in the workspace keyed on it); 0 = never cache */
+} fgnn_mp_args;
+
+int fgnn_version(void);
+const char* fgnn_strerror(int status);
+int fgnn_last_cuda_error(void);          /* cudaError_t of the last failed runtime call on this thread */
+
+/* Scratch the call needs (0 for the SIMT kernel with node-major x). */
+size_t fgnn_mp_workspace_bytes(const fgnn_mp_args* args);
+
+/* Which kernel FGNN_KERNEL_AUTO resolves to for these args (FGNN_KERNEL_SIMT / _TCGEN05), or <0. */
+int fgnn_mp_select_kernel(const fgnn_mp_args* args);
+
+/* The hot path.  Replaces mp_conv_v2.forward (mp_nn.py:115-175).  Asynchronous on `stream`. */
+int fgnn_mp_forward(const fgnn_mp_args* args, void* stream);
+
+/* Same call with HOST buffers (x, idx, etype, out in fgnn_mp_args are host pointers; filters/bias/bn
+ * host too).  Allocates device buffers, copies in, runs, copies out, frees, synchronises.  This is
+ * the end-to-end entry a non-PyTorch caller binds. */
+int fgnn_mp_forward_host(const fgnn_mp_args* host_args);
+
+/* Index validation the reference gets for free from ATen's gather (mp_nn.py:111): returns
+ * FGNN_ERR_INDEX_RANGE if any entry of idx[count] is outside [lo, N).  Synchronises `stream`.
+ * `scratch` = 8 bytes of device memory. */
+int fgnn_check_index_range(const void* idx, int idx_dtype, int64_t count, int64_t lo, int64_t n,
+                           void* scratch, void* stream);
+
+/* Elementwise epilogue out = act(bn(in + bias)) on a node-major [rows, O] buffer, used after the
+ * cross-GPU max-all-reduce of the raw aggregate (the epilogue is non-linear, so it runs after the
+ * reduce; reference mp_nn.py:165-173).  In-place allowed.  -inf inputs (no live slot on any shard)
+ * stay -inf before bias is added. */
+int fgnn_epilogue_forward(const float* in, float* out, int64_t rows, int32_t O, const float* bias,
+                          const float* bn_scale, const float* bn_shift, int32_t activation,
+                          float act_slope, void* stream);
+
+/* Layout helper: channel-major [B,C,N] -> node-major [B,N,C] (the reference's
+ * x.permute(0,2,3,1).contiguous(), mp_nn.py:125). */
+int fgnn_to_node_major(const float* x, float* out, int32_t B, int32_t C, int32_t N, int64_t x_sb,
+                       int64_t x_sc, int64_t x_sn, void* stream);
+
+/* Number of kernels this library has launched since load (all threads). */
+uint64_t fgnn_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FGNN_B200_H_ */

@@ -1,0 +1,285 @@
+"""Parity of the CUDA path (through the C ABI) with the golden vectors of the real reference and
+with the CPU oracle on seeded inputs.  Tolerance: 1e-4 relative, fp32 (north_star); decisions
+(argmax / sign) bit-exact."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import fgnn_b200
+from fgnn_b200 import _lib, graphs
+from oracle import fgnn_oracle as orc
+from tests.util import RTOL, assert_close, bn_of, load_npz, load_unit_cases, rel_err, sub_sd
+
+pytestmark = pytest.mark.gpu
+CASES = load_unit_cases()
+DEV = "cuda:0"
+KERNELS = {"auto": _lib.KERNEL_AUTO, "simt": _lib.KERNEL_SIMT}
+
+
+def t(a, dev=DEV):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def module_for(case, kernel="auto"):
+    m = case["meta"]
+    mod = fgnn_b200.mp_conv_v2(m["C"], m["O"], m["T"], bias=m.get("bias", True), bn=m.get("bn", True),
+                               extension=fgnn_b200.mp_conv_type(m["ext"]),
+                               activation_fn=m.get("act", "relu"), aggregtor=m["agg"])
+    mod.load_state_dict({k: torch.from_numpy(v) for k, v in case["sd"].items()})
+    mod.kernel = KERNELS[kernel]
+    return mod.to(DEV).eval()
+
+
+@pytest.mark.parametrize("kernel", ["auto", "simt"])
+@pytest.mark.parametrize("case", CASES, ids=[c["meta"]["name"] for c in CASES])
+def test_unit_cases_vs_reference_golden(case, kernel):
+    mod = module_for(case, kernel)
+    before = fgnn_b200.launch_count()
+    with torch.no_grad():
+        y = mod(t(case["x"]), t(case["idx"]), t(case["etype"]))
+    assert fgnn_b200.launch_count() > before, "no fgnn_b200 kernel was launched"
+    assert tuple(y.shape) == case["out"].shape
+    assert_close(y.cpu().numpy(), case["out"], RTOL, case["meta"]["name"])
+
+
+@pytest.mark.parametrize("layout", ["channels_first", "channels_last", "x3d", "int32_idx", "expanded_tables"])
+def test_input_layouts(layout):
+    case = next(c for c in CASES if c["meta"]["name"] == "noext_rect")
+    mod = module_for(case)
+    x, idx, et = t(case["x"]), t(case["idx"]), t(case["etype"])
+    if layout == "channels_last":
+        x = x.contiguous(memory_format=torch.channels_last)
+    elif layout == "x3d":
+        x = x[..., 0]
+    elif layout == "int32_idx":
+        idx = idx.int()
+    elif layout == "expanded_tables":
+        # batch-replicated tables without the copy (.expand instead of the scripts' .repeat)
+        idx = idx[:1].expand(case["x"].shape[0], -1, -1)
+        et = et[:1].expand(case["x"].shape[0], -1, -1, -1)
+        ref = orc.mp_conv_forward(case["x"], np.repeat(case["idx"][:1], 2, 0), np.repeat(case["etype"][:1], 2, 0),
+                                  case["sd"]["filters"], case["sd"]["bias"], bn_of(case["sd"]), 0, "max")
+        with torch.no_grad():
+            y = mod(x, idx, et)
+        assert_close(y.cpu().numpy(), ref, RTOL, layout)
+        return
+    with torch.no_grad():
+        y = mod(x, idx, et)
+    assert_close(y.cpu().numpy(), case["out"], RTOL, layout)
+    assert y.stride(1) == 1                    # node-major (channels_last) output memory
+
+
+def test_error_behaviour():
+    case = CASES[0]
+    mod = module_for(case)
+    bad = case["idx"].copy()
+    bad[1, 3, 2] = case["x"].shape[2]
+    with torch.no_grad(), pytest.raises(IndexError):             # reference: ATen gather raises
+        mod(t(case["x"]), t(bad), t(case["etype"]))
+    bad[1, 3, 2] = -1
+    with torch.no_grad(), pytest.raises(IndexError):
+        mod(t(case["x"]), t(bad), t(case["etype"]))
+    ext = next(c for c in CASES if c["meta"]["ext"] == 2)
+    m2 = module_for(ext)
+    with torch.no_grad(), pytest.raises(_lib.FgnnError):         # extension modes need M == N
+        m2(t(ext["x"]), t(ext["idx"][:, :5]), t(ext["etype"][:, :, :5]))
+    with torch.no_grad(), pytest.raises(AssertionError):         # mp_nn.py:100
+        mod(t(case["x"]), t(case["idx"][:1]), t(case["etype"]))
+
+
+def test_custom_aggregator_and_train_mode_bn():
+    case = next(c for c in CASES if c["meta"]["name"] == "ext0_max")
+    m = case["meta"]
+    mod = fgnn_b200.mp_conv_v2(m["C"], m["O"], m["T"], extension=fgnn_b200.mp_conv_type(0),
+                               aggregtor=lambda v: torch.max(v, dim=3, keepdim=True)[0])
+    mod.load_state_dict({k: torch.from_numpy(v) for k, v in case["sd"].items()})
+    mod = mod.to(DEV).eval()
+    with torch.no_grad():
+        y = mod(t(case["x"]), t(case["idx"]), t(case["etype"]))
+    assert_close(y.cpu().numpy(), case["out"], RTOL, "callable aggregator")
+    # train-mode BN: batch statistics are computed by the module's own bn on the kernel's output
+    mod2 = module_for(case).train()
+    with torch.no_grad():
+        y2 = mod2(t(case["x"]), t(case["idx"]), t(case["etype"]))
+    raw = orc.mp_conv_forward(case["x"], case["idx"], case["etype"], case["sd"]["filters"], case["sd"]["bias"],
+                              None, 0, "max", None)
+    mu, var = raw.mean((0, 2, 3), keepdims=True), raw.var((0, 2, 3), keepdims=True)
+    ref = np.maximum((raw - mu) / np.sqrt(var + 1e-5) * case["sd"]["bn.weight"].reshape(1, -1, 1, 1)
+                     + case["sd"]["bn.bias"].reshape(1, -1, 1, 1), 0)
+    assert_close(y2.cpu().numpy(), ref, 5e-4, "train-mode bn")
+
+
+def test_host_buffer_entry_point():
+    """fgnn_mp_forward_host: the call a non-PyTorch caller binds (host pointers in, host pointers out)."""
+    case = next(c for c in CASES if c["meta"]["name"] == "core64_T4")
+    m, sd = case["meta"], case["sd"]
+    x = np.ascontiguousarray(case["x"][..., 0])
+    idx, et = np.ascontiguousarray(case["idx"]), np.ascontiguousarray(case["etype"])
+    scale = (sd["bn.weight"] / np.sqrt(sd["bn.running_var"] + 1e-5)).astype(np.float32)
+    shift = (sd["bn.bias"] - sd["bn.running_mean"] * scale).astype(np.float32)
+    out = np.empty((m["B"], m["O"], m["M"], 1), np.float32)
+    a = _lib.MpArgs()
+    a.x, a.idx, a.etype, a.filters = x.ctypes.data, idx.ctypes.data, et.ctypes.data, sd["filters"].ctypes.data
+    a.bias, a.bn_scale, a.bn_shift, a.out = sd["bias"].ctypes.data, scale.ctypes.data, shift.ctypes.data, out.ctypes.data
+    a.B, a.N, a.M, a.K, a.C, a.O, a.T = m["B"], m["N"], m["M"], m["K"], m["C"], m["O"], m["T"]
+    a.extension, a.aggregator, a.activation = 0, _lib.AGG_MAX, _lib.ACT_RELU
+    a.dtype, a.idx_dtype, a.kernel, a.gamma = _lib.F32, _lib.I64, _lib.KERNEL_AUTO, 3.0
+    _lib.check(_lib.lib().fgnn_mp_forward_host(ctypes.byref(a)), "mp_forward_host")
+    assert_close(out, case["out"], RTOL, "host entry")
+    idx[0, 0, 0] = m["N"]
+    assert _lib.lib().fgnn_mp_forward_host(ctypes.byref(a)) == _lib.ERR_INDEX_RANGE
+
+
+def test_cfg1_simple_gnn_map_labels_bit_exact():
+    """BASELINE configs[0]: train_syn_fixed_pw_hop.py simple_gnn, 128-variable chain, B=8."""
+    g = load_npz("cfg1_simple_gnn.npz")
+    T_ = fgnn_b200.mp_conv_type
+    model = fgnn_b200.mp_sequential(fgnn_b200.mp_conv_v2(2, 64, 16, extension=T_.ORIG_WITH_NEIGHBOR),
+                                    fgnn_b200.mp_conv_residual(64, 64, 16), torch.nn.Conv2d(64, 2, 1))
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sub_sd(g, "model").items()})
+    emodel = torch.nn.Sequential(torch.nn.Conv2d(1, 64, 1), torch.nn.ReLU(inplace=True), torch.nn.Conv2d(64, 16, 1))
+    emodel.load_state_dict({k: torch.from_numpy(v) for k, v in sub_sd(g, "emodel").items()})
+    model, emodel = model.to(DEV).eval(), emodel.to(DEV).eval()
+    idx, ef = graphs.chain_knn_table(128, 4)
+    B = g["x"].shape[0]
+    with torch.no_grad():
+        etype = emodel(t(ef))
+        logits = model(t(g["x"]), t(idx).repeat(B, 1, 1), etype.repeat(B, 1, 1, 1))
+    assert_close(logits.cpu().numpy(), g["logits"], RTOL, "logits")
+    labels = logits.squeeze(-1).argmax(1).cpu().numpy()
+    assert np.array_equal(labels, g["labels"]), "MAP labels differ from the reference"
+    assert 0 < labels.sum() < labels.size
+    print("cfg1 min |margin| =", float(g["min_margin"]), "max rel err =", rel_err(logits.cpu().numpy(), g["logits"]))
+
+
+def test_cfg1_factornn_decisions_bit_exact():
+    g = load_npz("cfg1_factornn.npz")
+    model = fgnn_b200.FactorNN(2, [4], [64, 64], [16], 2)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sub_sd(g, "model").items()})
+    model = model.to(DEV).eval()
+    B = g["node"].shape[0]
+    with torch.no_grad():
+        logit = model(t(g["node"]), [t(g["hop"])], [t(g["idx_f2v"]).repeat(B, 1, 1)],
+                      [t(g["idx_v2f"]).repeat(B, 1, 1)], [t(g["et_f2v"])], [t(g["et_v2f"])])
+    assert_close(logit.cpu().numpy(), g["logit"], RTOL, "logit")
+    assert np.array_equal((logit >= 0).cpu().numpy(), g["decision"])
+
+
+def test_ldpc_factornn_hard_decisions_bit_exact():
+    """BASELINE configs[2] shapes: 96.3.963 tables, check factors (T=4) + the global factor (T=1, K=96)."""
+    g = load_npz("ldpc_factornn.npz")
+    model = fgnn_b200.FactorNN(2, [6, 96], [64, 64, 128, 64], [4, 1], 2, skip_link={2: 0}, ret_high=True)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sub_sd(g, "model").items()})
+    model = model.to(DEV).eval()
+    B = g["node"].shape[0]
+    node = t(g["node"])
+    rep = lambda a: t(a)[None].repeat(B, 1, 1)
+    h_idx_v2f = torch.arange(96, device=DEV).reshape(1, 1, 96).repeat(B, 1, 1)
+    h_idx_f2v = torch.zeros(B, 96, 1, dtype=torch.long, device=DEV)
+    nhop = node[:, 0, :, :].reshape(B, 96, 1, 1)
+    with torch.no_grad():
+        res, nhops = model(node, [t(g["hop"]), nhop], [rep(g["idx_f2v"]), h_idx_f2v],
+                           [rep(g["idx_v2f"]), h_idx_v2f],
+                           [t(g["et_f2v"]), torch.ones(B, 1, 96, 1, device=DEV)],
+                           [t(g["et_v2f"]), torch.ones(B, 1, 1, 96, device=DEV)])
+        res = res + node[:, :1]
+    assert_close(res.cpu().numpy(), g["res"], RTOL, "res")
+    assert_close(nhops[0].cpu().numpy(), g["nhop0"], RTOL, "nhop0")
+    assert np.array_equal((res >= 0).cpu().numpy(), g["hard"])
+
+
+# ---------------------------------------------------------------------------------------------
+# seeded inputs vs the CPU oracle at sizes it finishes in seconds; properties at full size
+# ---------------------------------------------------------------------------------------------
+
+def _random_call(rng, B, N, M, K, C, O, T, pad_frac=0.1):
+    x = rng.standard_normal((B, C, N, 1)).astype(np.float32)
+    idx = rng.integers(0, N, (B, M, K))
+    et = rng.standard_normal((B, T, M, K)).astype(np.float32)
+    et[np.broadcast_to(rng.random((B, 1, M, K)) < pad_frac, et.shape)] = 0
+    W = (rng.uniform(-1, 1, (C, O * T)) * 0.3 / np.sqrt(C / 8)).astype(np.float32)
+    bias = rng.uniform(-0.2, 0.2, O).astype(np.float32)
+    bn = dict(weight=rng.uniform(0.8, 1.2, O).astype(np.float32), bias=rng.uniform(-0.2, 0.2, O).astype(np.float32),
+              running_mean=rng.uniform(-0.1, 0.1, O).astype(np.float32),
+              running_var=rng.uniform(0.5, 1.5, O).astype(np.float32))
+    return x, idx, et, W, bias, bn
+
+
+def _native(x, idx, et, W, bias, bn, agg=_lib.AGG_MAX, kernel=_lib.KERNEL_AUTO, **kw):
+    scale = bn["weight"] / np.sqrt(bn["running_var"] + 1e-5)
+    shift = bn["bias"] - bn["running_mean"] * scale
+    xt = t(x).contiguous(memory_format=torch.channels_last)
+    y = fgnn_b200.mp_forward(xt, t(idx), t(et), t(W), t(bias), t(scale.astype(np.float32)),
+                             t(shift.astype(np.float32)), extension=0, aggregator=agg, kernel=kernel, **kw)
+    return y
+
+
+@pytest.mark.parametrize("shape", [
+    dict(B=1, N=5000, M=15000, K=2, C=64, O=64, T=16),     # cfg-2 V2F pairwise at 1/20 scale
+    dict(B=1, N=15000, M=5000, K=6, C=64, O=64, T=16),     # cfg-2 F2V pairwise
+    dict(B=1, N=5000, M=2500, K=3, C=64, O=64, T=16),      # cfg-2 V2F order-3
+    dict(B=1, N=5000, M=15000, K=2, C=64, O=64, T=4),
+    dict(B=64, N=96, M=48, K=6, C=64, O=64, T=4),          # cfg-3 V2F
+    dict(B=64, N=48, M=96, K=3, C=64, O=64, T=4),          # cfg-3 F2V
+    dict(B=1, N=777, M=1001, K=5, C=64, O=64, T=16),       # ragged: M not a multiple of any tile
+    dict(B=3, N=130, M=257, K=1, C=64, O=64, T=1),
+    dict(B=1, N=300, M=129, K=16, C=128, O=64, T=4),
+    dict(B=1, N=300, M=500, K=2, C=64, O=128, T=16),
+], ids=lambda s: "B{B}_N{N}_M{M}_K{K}_C{C}_O{O}_T{T}".format(**s))
+@pytest.mark.parametrize("agg", ["max", "softmax", "mean"])
+def test_seeded_vs_oracle(shape, agg):
+    rng = np.random.default_rng(hash((shape["M"], shape["K"], shape["T"])) & 0xffff)
+    x, idx, et, W, bias, bn = _random_call(rng, **shape)
+    ref = orc.mp_conv_forward_c(x, idx, et, W, bias, bn, extension=0, aggregator=agg)
+    y = _native(x, idx, et, W, bias, bn, agg={"max": 0, "softmax": 1, "mean": 2}[agg])
+    assert_close(y.cpu().numpy(), ref, RTOL, f"{shape} {agg}")
+
+
+def test_masked_slots_and_epilogue_split_equal_fused():
+    """Shard-local tables: negative indices are empty slots excluded from the max; the
+    raw aggregate of two half-tables, max-combined and passed through fgnn_epilogue_forward,
+    equals the fused single call -- the 1-GPU == N-GPU identity of the factor-sharded layer."""
+    rng = np.random.default_rng(11)
+    x, idx, et, W, bias, bn = _random_call(rng, B=1, N=400, M=300, K=6, C=64, O=64, T=4, pad_frac=0.0)
+    full = _native(x, idx, et, W, bias, bn)
+    scale = (bn["weight"] / np.sqrt(bn["running_var"] + 1e-5)).astype(np.float32)
+    shift = (bn["bias"] - bn["running_mean"] * scale).astype(np.float32)
+    parts = []
+    for lo, hi in ((0, 200), (200, 400)):                 # two shards of the SOURCE nodes (factors)
+        local = np.where((idx >= lo) & (idx < hi), idx - lo, -1)
+        y = fgnn_b200.mp_forward(t(x[:, :, lo:hi]).contiguous(memory_format=torch.channels_last), t(local), t(et),
+                                 t(W), None, None, None, extension=0, aggregator=_lib.AGG_MAX,
+                                 activation=_lib.ACT_NONE, mask_negative=True)
+        parts.append(y)
+    red = torch.maximum(parts[0], parts[1])               # what ncclAllReduce(max) computes
+    rows = red.shape[0] * red.shape[2]
+    flat = red.permute(0, 2, 3, 1).contiguous()
+    _lib.check(_lib.lib().fgnn_epilogue_forward(
+        flat.data_ptr(), flat.data_ptr(), rows, 64, t(bias).data_ptr(), t(scale).data_ptr(), t(shift).data_ptr(),
+        _lib.ACT_RELU, 0.0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "epilogue")
+    got = flat.permute(0, 3, 1, 2)
+    assert torch.equal(got, full), "sharded max + epilogue differs from the fused call"
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE configs[1] full size (100K vars, 300K pairwise, T=16): properties that need no
+    full-size oracle -- (1) permuting the slots of every destination leaves the max unchanged,
+    (2) a 2 000-row sample of destinations matches the oracle run on just those rows,
+    (3) an all-zero edge type yields act(BN(bias)), (4) run-to-run bit-identical."""
+    rng = np.random.default_rng(2)
+    N, M, K, C, O, T = 100_000, 300_000, 2, 64, 64, 16
+    x, idx, et, W, bias, bn = _random_call(rng, 1, N, M, K, C, O, T)
+    y = _native(x, idx, et, W, bias, bn)
+    y2 = _native(x, idx, et, W, bias, bn)
+    assert torch.equal(y, y2)
+    yp = _native(x, idx[:, :, ::-1].copy(), et[:, :, :, ::-1].copy(), W, bias, bn)
+    assert torch.equal(y, yp)
+    rows = rng.choice(M, 2000, replace=False)
+    ref = orc.mp_conv_forward_c(x, idx[:, rows], et[:, :, rows], W, bias, bn, extension=0, aggregator="max")
+    assert_close(y[:, :, torch.from_numpy(rows).to(DEV)].cpu().numpy(), ref, RTOL, "sampled rows")
+    yz = _native(x, idx, np.zeros_like(et), W, bias, bn)
+    scale = bn["weight"] / np.sqrt(bn["running_var"] + 1e-5)
+    const = np.maximum(bias * scale + bn["bias"] - bn["running_mean"] * scale, 0).astype(np.float32)
+    assert_close(yz.cpu().numpy(), np.broadcast_to(const.reshape(1, O, 1, 1), (1, O, M, 1)), 1e-6, "zero etype")

@@ -1,0 +1,151 @@
+"""Host-side mirror of the reference interface (no GPU): constructor / state_dict / error
+behaviour, graph-table builders, the drop-in install, and the no-fallback rule."""
+import io
+import contextlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import fgnn_b200
+from fgnn_b200 import graphs
+from oracle import refload
+from tests.util import load_npz, load_unit_cases, sub_sd
+
+
+def test_constructor_surface_and_state_dict_keys():
+    m = fgnn_b200.mp_conv_v2(4, 8, 3)
+    assert (m.nin, m.nou, m.nedge_types) == (4, 8, 3)
+    assert m.extension == fgnn_b200.mp_conv_type.ORIG_WITH_DIFF          # reference default
+    assert m.filters.shape == (8, 24) and m.bias.shape == (8,)
+    assert isinstance(m.bn, torch.nn.BatchNorm2d) and isinstance(m.activation_fn, torch.nn.ReLU)
+    assert list(m.state_dict().keys()) == ["filters", "bias", "bn.weight", "bn.bias", "bn.running_mean",
+                                           "bn.running_var", "bn.num_batches_tracked"]
+    assert isinstance(m, fgnn_b200.base_mp_nn) and m.is_mp_nn
+    assert float(m.filters.detach().abs().max()) <= 0.01 and 0 <= float(m.bias.detach().min()) and float(m.bias.detach().max()) <= 0.05
+    n = fgnn_b200.mp_conv_v2(4, 8, 3, bias=False, bn=False, extension=fgnn_b200.mp_conv_type.NO_EXTENSION,
+                             activation_fn=None, aggregtor='max')
+    assert n.filters.shape == (4, 24) and n.bias is None and n.bn is None and n.activation_fn is None
+    assert list(n.state_dict().keys()) == ["filters"]
+
+
+def test_constructor_errors_match_reference():
+    with pytest.raises(ValueError, match="extension must one of mp_conv_type"):
+        fgnn_b200.mp_conv_v2(4, 8, 3, extension=7)
+    m = fgnn_b200.mp_conv_v2(4, 8, 3, aggregtor='median')        # unknown string: attribute stays unset
+    assert not hasattr(m, "aggregtor")
+
+
+def test_default_aggregators():
+    assert fgnn_b200.mp_conv_v2(2, 2, 1)._agg == fgnn_b200._lib.AGG_SOFTMAX         # mp_nn.py:26
+    assert fgnn_b200.mp_conv_residual(4, 4, 2).mp_conv._agg == fgnn_b200._lib.AGG_MAX  # mp_nn_residual.py:15
+    v = torch.randn(2, 3, 4, 5)
+    m = fgnn_b200.mp_conv_v2(2, 2, 1)
+    assert torch.allclose(m.aggregtor(v), torch.logsumexp(3 * v, 3, keepdim=True) / 3)
+
+
+def test_cpu_tensor_has_no_fallback():
+    m = fgnn_b200.mp_conv_v2(4, 8, 2).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU"):
+        m(torch.zeros(1, 4, 3, 1), torch.zeros(1, 3, 2, dtype=torch.long), torch.zeros(1, 2, 3, 2))
+
+
+def test_training_forward_is_refused():
+    m = fgnn_b200.mp_conv_v2(4, 8, 2).train()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 4, 3, 1), torch.zeros(1, 3, 2, dtype=torch.long), torch.zeros(1, 2, 3, 2))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                       "factor-graph-neural-network_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "fgnn_oracle" not in src, f
+
+
+def test_state_dicts_load_from_reference_fixtures():
+    for c in load_unit_cases():
+        m = c["meta"]
+        mod = fgnn_b200.mp_conv_v2(m["C"], m["O"], m["T"], bias=m.get("bias", True), bn=m.get("bn", True),
+                                   extension=fgnn_b200.mp_conv_type(m["ext"]),
+                                   activation_fn=m.get("act", "relu"), aggregtor=m["agg"])
+        mod.load_state_dict({k: torch.from_numpy(v) for k, v in c["sd"].items()})
+    g = load_npz("cfg1_factornn.npz")
+    fnn = fgnn_b200.FactorNN(2, [4], [64, 64], [16], 2)
+    fnn.load_state_dict({k: torch.from_numpy(v) for k, v in sub_sd(g, "model").items()})
+    g = load_npz("ldpc_factornn.npz")
+    fnn = fgnn_b200.FactorNN(2, [6, 96], [64, 64, 128, 64], [4, 1], 2, skip_link={2: 0}, ret_high=True)
+    fnn.load_state_dict({k: torch.from_numpy(v) for k, v in sub_sd(g, "model").items()})
+    # layer 1 (64 -> 128) is a bare core, layers 0 and 2 are residual wrappers (factor_mpnn_sp.py:79-94)
+    assert isinstance(fnn.f2v_modules[1][0], fgnn_b200.mp_conv_v2)
+    assert isinstance(fnn.f2v_modules[0][0], fgnn_b200.mp_conv_residual)
+
+
+def test_chain_knn_table_matches_reference_fixture():
+    g = load_npz("cfg1_simple_gnn.npz")
+    idx, ef = graphs.chain_knn_table(128, 4)
+    assert np.array_equal(idx, g["nn_idx"]) and np.array_equal(ef, g["efeature"])
+    assert (idx[0, :, 3] == 0).all() and (ef[0, 0, :, 3] == 0).all()     # the reference's pad slot
+
+
+def test_synthetic_graph_tables_are_consistent():
+    types = graphs.synthetic_map_graph(1000, 3000, 500, 3, seed=5)
+    pw, ho = types
+    assert pw.idx_v2f.shape == (3000, 2) and pw.idx_f2v.shape == (1000, 6) and not pw.pad_f2v.any()
+    assert ho.idx_v2f.shape == (500, 3) and ho.idx_f2v.shape == (1000, 2)
+    assert pw.real_messages + ho.real_messages == 2 * (3000 * 2 + 500 * 3)
+    for t in types:
+        assert t.idx_v2f.min() >= 0 and t.idx_v2f.max() < t.n_vars
+        assert t.idx_f2v.min() >= 0 and t.idx_f2v.max() < t.n_factors
+        # every non-pad (variable, slot) names a factor that lists the variable, and counts agree
+        v, s = np.nonzero(~t.pad_f2v)
+        assert (t.idx_v2f[t.idx_f2v[v, s]] == v[:, None]).any(1).all()
+        assert (~t.pad_f2v).sum() == t.n_factors * t.order
+        assert (t.idx_f2v[t.pad_f2v] == 0).all()
+    loc = graphs.synthetic_map_graph(1000, 3000, 0, 0, seed=5, local_band=16)[0]
+    span = (loc.idx_v2f.max(1) - loc.idx_v2f.min(1))
+    assert ((span < 16) | (span > 1000 - 16)).all()
+
+
+def test_parse_alist_small():
+    text = "4 2\n2 3\n1 2 1 2\n3 3\n1 0\n1 2\n2 0\n1 2\n1 2 4\n2 4 0\n"
+    v2c, c2v = graphs.parse_alist(text)
+    assert v2c.tolist() == [[0, -1], [0, 1], [1, -1], [0, 1]]
+    assert c2v.tolist() == [[0, 1, 3], [1, 3, -1]]
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree only exists in the build container")
+def test_parse_alist_matches_reference_ldpc_tables():
+    g = load_npz("ldpc_factornn.npz")
+    text = open(os.path.join(refload.REF_ROOT, "ldpc_codes", "96.3.963", "96.3.963")).read()
+    v2c, c2v = graphs.parse_alist(text)
+    assert np.array_equal(v2c, g["idx_f2v"]) and np.array_equal(c2v, g["idx_v2f"])
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree only exists in the build container")
+def test_install_drops_into_reference_package():
+    mpnn = refload.load()
+    orig = mpnn.mp_conv_v2
+    import sys
+    mods = {n: sys.modules["lib.model.mpnn." + n] for n in ("mp_nn", "mp_nn_residual", "factor_mpnn_sp", "factor_mpnn")}
+    saved = {n: m.mp_conv_v2 for n, m in mods.items()}
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref_keys = list(orig(8, 8, 2).state_dict().keys())     # before patching: the class finds itself by name
+    try:
+        native = fgnn_b200.install(mpnn)
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = mpnn.mp_conv_residual(8, 8, 2)                        # reference wrapper, native core
+            fnn = mpnn.FactorNN(2, [4], [16, 16], [2], 2)
+        assert isinstance(res.mp_conv, native) and isinstance(res.mp_conv, fgnn_b200.mp_conv_v2)
+        assert isinstance(res.mp_conv, sys.modules["lib.model.mpnn.base_model"].base_mp_nn)      # reference isinstance dispatch
+        assert isinstance(fnn.f2v_modules[0][0].mp_conv, native)
+        assert res.mp_conv.extension == mpnn.mp_conv_type.ORIG_WITH_DIFF
+        assert list(res.mp_conv.state_dict().keys()) == ref_keys
+    finally:
+        mpnn.mp_conv_v2 = orig
+        for n, v in saved.items():
+            mods[n].mp_conv_v2 = v

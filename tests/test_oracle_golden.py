@@ -1,0 +1,80 @@
+"""The CPU oracle (numpy restatement + C restatement) against the golden vectors produced by the
+real reference (tests/golden/make_golden.py).  This is what pins the oracle."""
+import numpy as np
+import pytest
+
+from oracle import fgnn_oracle as orc
+from tests.util import assert_close, bn_of, load_npz, load_unit_cases, sub_sd
+
+CASES = load_unit_cases()
+# the oracle's summation order differs from ATen's mm/bmm; fp32 round-off only
+ORACLE_RTOL = 2e-5
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["meta"]["name"] for c in CASES])
+@pytest.mark.parametrize("impl", ["numpy", "c"])
+def test_unit_cases(case, impl):
+    m, sd = case["meta"], case["sd"]
+    fn = orc.mp_conv_forward if impl == "numpy" else orc.mp_conv_forward_c
+    got = fn(case["x"], case["idx"], case["etype"], sd["filters"], sd.get("bias"), bn_of(sd),
+             extension=m["ext"], aggregator=m["agg"], activation=m.get("act", "relu"))
+    assert_close(got, case["out"], ORACLE_RTOL, m["name"])
+
+
+def test_out_of_range_index_raises():
+    c = CASES[0]
+    bad = c["idx"].copy()
+    bad[0, 0, 0] = c["x"].shape[2]
+    for fn in (orc.mp_conv_forward, orc.mp_conv_forward_c):
+        with pytest.raises(IndexError):
+            fn(c["x"], bad, c["etype"], c["sd"]["filters"], extension=c["meta"]["ext"], aggregator="max")
+
+
+def test_cfg1_simple_gnn_chain():
+    """BASELINE configs[0]: first layer (NEIGHBOR, softmax), the residual FGNN layer (DIFF, max),
+    1x1 classifier; MAP labels bit-exact."""
+    g = load_npz("cfg1_simple_gnn.npz")
+    sd = sub_sd(g, "model")
+    B = g["x"].shape[0]
+    idx = np.repeat(g["nn_idx"], B, 0)
+    et = np.repeat(g["etype"], B, 0)
+    s0 = {k[2:]: v for k, v in sd.items() if k.startswith("0.")}
+    h1 = orc.mp_conv_forward(g["x"], idx, et, s0["filters"], s0["bias"], bn_of(s0),
+                             extension=orc.ORIG_WITH_NEIGHBOR, aggregator="softmax")
+    assert_close(h1, g["h1"], ORACLE_RTOL, "h1")
+    s1 = {k[2:]: v for k, v in sd.items() if k.startswith("1.")}
+    h2 = orc.mp_conv_residual_forward(s1, h1, idx, et, orc.ORIG_WITH_DIFF, "max", True)
+    assert_close(h2, g["h2"], ORACLE_RTOL, "h2")
+    logits = orc.conv1x1(h2, sd["2.weight"], sd["2.bias"])
+    assert_close(logits, g["logits"], ORACLE_RTOL, "logits")
+    labels = logits[..., 0].argmax(1)
+    assert np.array_equal(labels, g["labels"])
+    assert 0 < labels.sum() < labels.size          # the check is not vacuous
+
+
+def test_cfg1_factornn():
+    g = load_npz("cfg1_factornn.npz")
+    sd = sub_sd(g, "model")
+    B = g["node"].shape[0]
+    logit = orc.factor_nn_forward(sd, g["node"], [g["hop"]], [np.repeat(g["idx_f2v"], B, 0)],
+                                  [np.repeat(g["idx_v2f"], B, 0)], [g["et_f2v"]], [g["et_v2f"]], [64, 64])
+    assert_close(logit, g["logit"], 5e-5, "logit")
+    assert np.array_equal(logit >= 0, g["decision"])
+
+
+def test_ldpc_factornn():
+    g = load_npz("ldpc_factornn.npz")
+    sd = sub_sd(g, "model")
+    B = g["node"].shape[0]
+    rep = lambda a: np.repeat(a[None], B, 0)
+    h_idx_v2f = np.tile(np.arange(96).reshape(1, 1, 96), (B, 1, 1))
+    h_idx_f2v = np.zeros((B, 96, 1), dtype=np.int64)
+    nhop = g["node"][:, 0].reshape(B, 96, 1, 1)
+    res, nhops = orc.factor_nn_forward(
+        sd, g["node"], [g["hop"], nhop], [rep(g["idx_f2v"]), h_idx_f2v], [rep(g["idx_v2f"]), h_idx_v2f],
+        [g["et_f2v"], np.ones((B, 1, 96, 1), np.float32)], [g["et_v2f"], np.ones((B, 1, 1, 96), np.float32)],
+        [64, 64, 128, 64], skip_link={2: 0}, ret_high=True)
+    res = res + g["node"][:, :1]
+    assert_close(res, g["res"], 5e-5, "res")
+    assert_close(nhops[0], g["nhop0"], 5e-5, "nhop0")
+    assert np.array_equal(res >= 0, g["hard"])
