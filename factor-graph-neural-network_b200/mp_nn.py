@@ -14,6 +14,7 @@ forward under `torch.no_grad()` / `.eval()` is the contract; train-mode BN is se
 the kernel up to the bias add and handing the result to the module's own `bn`.
 """
 import ctypes
+import weakref
 from enum import Enum
 
 import torch
@@ -43,14 +44,22 @@ class base_mp_nn(torch.nn.Module):
 _SOFTMAX_GAMMA = 3.0                      # agg_softmax default gamma, mp_nn.py:80
 
 # nn_idx tables are static across layers and steps; validating them (the reference gets this from
-# ATen's gather, mp_nn.py:111) costs a device sync, so remember which tables already passed.
+# ATen's gather, mp_nn.py:111) costs a device sync, so remember which tensor OBJECTS already passed
+# (identity + in-place version counter; a data_ptr is not an identity -- the caching allocator
+# hands the same address to the next table).
 _validated_tables = {}
-_VALIDATED_MAX = 256
 
 
-def _table_key(nn_idx, n_src):
-    return (nn_idx.data_ptr(), tuple(nn_idx.shape), tuple(nn_idx.stride()), nn_idx._version,
-            nn_idx.device.index, n_src)
+def _table_seen(nn_idx, n_src, mask_negative):
+    ent = _validated_tables.get(id(nn_idx))
+    return (ent is not None and ent[0]() is nn_idx and
+            ent[1:] == (nn_idx._version, nn_idx.data_ptr(), n_src, bool(mask_negative)))
+
+
+def _table_remember(nn_idx, n_src, mask_negative):
+    key = id(nn_idx)
+    ref = weakref.ref(nn_idx, lambda _r, key=key: _validated_tables.pop(key, None))
+    _validated_tables[key] = (ref, nn_idx._version, nn_idx.data_ptr(), n_src, bool(mask_negative))
 
 
 def clear_table_cache():
@@ -122,6 +131,7 @@ def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=Non
         raise ValueError(f"etype shape {tuple(etype.shape)} does not match [B={B},T,M={M},K={K}]")
     if nn_idx.device != dev or etype.device != dev or filters.device != dev:
         raise RuntimeError("fgnn_b200: x, nn_idx, etype and the module must be on the same device")
+    idx_user = nn_idx                                 # the caller's object: identity for the validation cache
     if nn_idx.dtype not in (torch.int64, torch.int32):
         nn_idx = nn_idx.long()
     # index table: rows contiguous, batch stride free (0 for .expand()-ed tables)
@@ -157,20 +167,16 @@ def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=Non
             raise IndexError("fgnn_b200: nn_idx entry out of range (no source nodes)")
         return out
 
-    if validate:
-        key = _table_key(nn_idx, N)
-        if key not in _validated_tables:
-            flag = torch.empty(2, dtype=torch.int32, device=dev)
-            lo = -(2 ** 63) if mask_negative else 0
-            with torch.cuda.device(dev):
-                rc = lib.fgnn_check_index_range(
-                    _ptr(nn_idx), _lib.I64 if nn_idx.dtype == torch.int64 else _lib.I32,
-                    nn_idx.numel() if nn_idx.stride(0) != 0 else M * K, lo, N, _ptr(flag),
-                    ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
-            _lib.check(rc, "check_index_range")
-            if len(_validated_tables) >= _VALIDATED_MAX:
-                _validated_tables.clear()
-            _validated_tables[key] = True
+    if validate and not _table_seen(idx_user, N, mask_negative):
+        flag = torch.empty(2, dtype=torch.int32, device=dev)
+        lo = -(2 ** 63) if mask_negative else 0
+        with torch.cuda.device(dev):
+            rc = lib.fgnn_check_index_range(
+                _ptr(nn_idx), _lib.I64 if nn_idx.dtype == torch.int64 else _lib.I32,
+                nn_idx.numel() if nn_idx.stride(0) != 0 else M * K, lo, N, _ptr(flag),
+                ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check(rc, "check_index_range")
+        _table_remember(idx_user, N, mask_negative)
 
     a = _lib.MpArgs()
     a.x, a.idx, a.etype, a.filters = x3.data_ptr(), nn_idx.data_ptr(), etype.data_ptr(), filters.data_ptr()

@@ -1,0 +1,114 @@
+"""GPU-box diagnostic: the tcgen05 kernel against the SIMT kernel and the CPU oracle on seeded
+shapes; prints error statistics per shape (used while bringing the kernel up).
+
+    python tools/tc_check.py [--big]
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import fgnn_b200  # noqa: E402
+from fgnn_b200 import _lib  # noqa: E402
+from oracle import fgnn_oracle as orc  # noqa: E402
+
+dev = "cuda:0"
+
+
+def run(B, N, M, K, T, agg=0, O=64, C=64, seed=0, oracle=True, mask=False):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((B, N, C)).astype(np.float32)
+    idx = rng.integers(0, N, (B, M, K))
+    if mask:
+        idx[rng.random(idx.shape) < 0.3] = -1
+    et = rng.standard_normal((B, T, M, K)).astype(np.float32)
+    W = (rng.uniform(-1, 1, (C, O * T)) * 0.1).astype(np.float32)
+    bias = rng.uniform(-0.2, 0.2, O).astype(np.float32)
+    scale = rng.uniform(0.8, 1.2, O).astype(np.float32)
+    shift = rng.uniform(-0.2, 0.2, O).astype(np.float32)
+    xt = torch.from_numpy(x).to(dev).permute(0, 2, 1).unsqueeze(-1)
+    args = (xt, torch.from_numpy(idx).to(dev), torch.from_numpy(et).to(dev), torch.from_numpy(W).to(dev),
+            torch.from_numpy(bias).to(dev), torch.from_numpy(scale).to(dev), torch.from_numpy(shift).to(dev))
+    kw = dict(extension=0, aggregator=agg, mask_negative=mask)
+    y_simt = fgnn_b200.mp_forward(*args, kernel=_lib.KERNEL_SIMT, **kw)
+    torch.cuda.synchronize()
+    try:
+        y_tc = fgnn_b200.mp_forward(*args, kernel=_lib.KERNEL_TCGEN05, **kw)
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        print(f"B{B} N{N} M{M} K{K} T{T} agg{agg}: TC FAILED: {e}")
+        return False
+    a, b = y_tc.float().cpu().numpy(), y_simt.cpu().numpy()
+    fin = np.isfinite(b)
+    same_inf = np.array_equal(np.isfinite(a), fin)
+    scale_ = max(np.abs(b[fin]).max(), 1e-30) if fin.any() else 1.0
+    err = np.abs(a[fin] - b[fin]).max() / scale_ if fin.any() and same_inf else float("nan")
+    msg = f"B{B} N{N} M{M} K{K} T{T} O{O} agg{agg} mask{int(mask)}: tc-vs-simt rel err {err:.3e} (scale {scale_:.3f}) inf-pattern {'ok' if same_inf else 'DIFFERS'}"
+    if oracle and not mask:
+        bn = dict(weight=scale, bias=shift, running_mean=np.zeros(O, np.float32), running_var=np.ones(O, np.float32) - 1e-5)
+        ref = orc.mp_conv_forward_c(np.ascontiguousarray(x.transpose(0, 2, 1))[..., None], idx, et, W, bias, bn,
+                                    extension=0, aggregator={0: "max", 1: "softmax", 2: "mean"}[agg])
+        msg += f" | tc-vs-oracle {np.abs(a - ref).max() / scale_:.3e} simt-vs-oracle {np.abs(b - ref).max() / scale_:.3e}"
+    if not (err <= 1e-4):
+        bad = np.argwhere(~(np.abs(a - b) <= 1e-4 * scale_))
+        msg += f" | BAD elements {len(bad)} of {a.size}; first {bad[:5].tolist()}"
+        r0 = bad[0]
+        msg += f" tc={a[tuple(r0)]:.5f} simt={b[tuple(r0)]:.5f}"
+        rows = np.unique(bad[:, 2])
+        chans = np.unique(bad[:, 1])
+        msg += f" | bad rows {len(rows)} (min {rows.min()} max {rows.max()}), bad channels {len(chans)} (min {chans.min()} max {chans.max()})"
+    print(msg, flush=True)
+    return err <= 1e-4
+
+
+def timeit(B, N, M, K, T, kernel, reps=10):
+    rng = np.random.default_rng(0)
+    x = torch.randn(B, N, 64, device=dev).permute(0, 2, 1).unsqueeze(-1)
+    idx = torch.from_numpy(rng.integers(0, N, (B, M, K))).to(dev)
+    et = torch.randn(B, T, M, K, device=dev)
+    W = torch.randn(64, 64 * T, device=dev) * 0.1
+    bias = torch.zeros(64, device=dev)
+    out = torch.empty(B, 64, M, 1, device=dev, memory_format=torch.channels_last)
+    ws = torch.zeros(64 * 64 * T * 4 + 4096, dtype=torch.uint8, device=dev)
+    f = lambda: fgnn_b200.mp_forward(x, idx, et, W, bias, None, None, extension=0, aggregator=0, kernel=kernel, out=out,
+                                     workspace=ws, filters_version=7)
+    for _ in range(3):
+        f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        f()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / reps * 1e3
+    byt = 4 * M * K * B + 4 * T * M * K * B + 4 * 64 * N * B + 4 * 64 * M * B
+    print(f"time B{B} N{N} M{M} K{K} T{T} kernel{kernel}: {us:9.1f} us  {B * M * K / us:8.1f} Mslots/s  "
+          f"{byt / us / 1e3:7.1f} GB/s algorithmic", flush=True)
+
+
+if __name__ == "__main__":
+    ok = True
+    ok &= run(1, 200, 128, 1, 16)
+    ok &= run(1, 200, 128, 2, 16)
+    ok &= run(1, 300, 256, 2, 4)
+    ok &= run(1, 300, 1000, 3, 16)
+    ok &= run(1, 300, 1000, 3, 1)
+    ok &= run(1, 300, 1000, 3, 2)
+    ok &= run(1, 300, 1000, 3, 8)
+    ok &= run(2, 96, 48, 6, 4)
+    ok &= run(1, 5000, 20000, 2, 16)
+    ok &= run(1, 5000, 20000, 6, 4, agg=1)
+    ok &= run(1, 5000, 20000, 6, 16, agg=1)
+    ok &= run(1, 5000, 20000, 3, 16, agg=2)
+    ok &= run(1, 500, 3000, 4, 16, mask=True)
+    ok &= run(1, 500, 3000, 4, 4, O=128)
+    print("ALL OK" if ok else "SOME FAILED")
+    if "--big" in sys.argv or ok:
+        for T in (16, 4):
+            for (N, M, K) in ((100_000, 300_000, 2), (300_000, 100_000, 6)):
+                timeit(1, N, M, K, T, _lib.KERNEL_TCGEN05)
+        timeit(1, 100_000, 300_000, 2, 16, _lib.KERNEL_SIMT, reps=3)
