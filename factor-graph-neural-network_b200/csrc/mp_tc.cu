@@ -15,12 +15,19 @@
 // and three MMAs xh*Wh + xl*Wh + xh*Wl accumulate in fp32 (error ~2^-16 relative, inside the
 // 1e-4 contract; plain TF32/bf16 is not -- SURVEY 7 hard part 2).
 //
-// CTA roles (288 threads, 1 CTA / SM, persistent over tiles):
-//   warps 0-3  epilogue   TMEM -> registers, edge-type contraction, aggregate, bias/BN/act, store
-//   warps 4-7  producers  gather x rows (128-bit coalesced: 16 lanes per 256-byte row), split to
-//                         bf16 hi/lo, write the UMMA K-major SWIZZLE_128B image of A into smem
-//   warp  8    MMA        one elected lane issues tcgen05.mma; owns the TMEM allocation
-// Pipelines: A stages (2) producers<->MMA, TMEM accumulator stages (2) MMA<->epilogue, all mbarrier.
+// CTA roles (416 threads, 1 CTA / SM, persistent over tiles); an ITEM is one (tile, k):
+//   warps 0-3   epilogue    TMEM -> registers, edge-type contraction, aggregate, bias/BN/act, store;
+//                           the next item's edge-type vector is prefetched during the current one
+//   warps 4-7   gatherers   cp.async (LDGSTS) 16-byte chunks of the 128 source rows straight into the
+//                           A stage: no register staging, every free stage's gather is in flight.
+//                           Raw fp32 chunk 2j of row r lands where bf16 chunk j of A_hi[r] will live,
+//                           chunk 2j+1 where chunk j of A_lo[r] will live
+//   warps 8-11  converters  in place, thread-local: read the two raw chunks (8 floats), write the
+//                           8 bf16 "hi" halves over the first and the 8 "lo" halves over the second
+//                           -> the UMMA K-major SWIZZLE_128B images of A_hi / A_lo
+//   warp  12    MMA         one elected lane issues tcgen05.mma; owns the TMEM allocation; brings the
+//                           stationary filter slice in with TMA bulk copies (cp.async.bulk)
+// Pipelines (all mbarrier): A stages (3-6) a_empty -> raw_full -> a_full; TMEM stages (2) t_full/t_empty.
 // The filters are stationary: each CTA keeps the split-bf16 image of its column slice
 // (O*T / S columns, S = column split across CTAs so the slice fits in shared memory) for its
 // whole lifetime; the image is produced once per weight version by w_split_kernel.
@@ -34,13 +41,16 @@ namespace tc {
 
 constexpr int kC = 64;                 // input channels (K dimension of the MMA), one 128-byte swizzle atom
 constexpr int kTileM = 128;            // destinations per tile == UMMA M == TMEM lanes
-constexpr int kEpiWarps = 4, kProdWarps = 4;
-constexpr int kThreads = (kEpiWarps + kProdWarps + 1) * 32;   // 288
-constexpr int kAStages = 2;
+constexpr int kEpiWarps = 4, kGatherWarps = 4, kConvWarps = 4;
+constexpr int kMmaWarp = kEpiWarps + kGatherWarps + kConvWarps;
+constexpr int kThreads = (kMmaWarp + 1) * 32;                 // 416
+constexpr int kMaxAStages = 6;
+constexpr int kNumBars = 3 * kMaxAStages + 5;                 // a_full, a_empty, raw_full, t_full[2], t_empty[2], w_full
+constexpr int kSmemBudget = 227 * 1024;
 constexpr int kAPartBytes = kTileM * kC * 2;                  // 16 KB: one bf16 part (hi or lo) of A
 constexpr int kAStageBytes = 2 * kAPartBytes;                 // hi + lo
 constexpr int kHeaderBytes = 256;                             // workspace header in front of the W image
-constexpr uint32_t kSpinLimit = 1u << 24;                     // watchdog: trap instead of hanging the GPU
+constexpr uint32_t kSpinLimit = 1u << 20;                     // watchdog: trap instead of hanging the GPU
 
 struct Header {                       // first bytes of the workspace
   int64_t version;                    // fgnn_mp_args.filters_version the image was built from
@@ -73,6 +83,28 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (done) break;
     if (++spins > kSpinLimit) __trap();
   }
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// 16-byte asynchronous copy global -> shared (LDGSTS); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier gets one (pre-counted) arrival when all of this thread's prior cp.async have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+// one lane of a converged warp (warp-uniform control flow keeps descriptors in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -132,9 +164,17 @@ __host__ __device__ constexpr uint32_t umma_idesc(int n) {
 }
 
 // Register re-balancing between warp groups (warps 0-3 epilogue, 4-7 producers): the kernel is
-// compiled for 168 registers/thread; the epilogue grows to 232, the producers shrink to 96.
+// compiled for 128 registers/thread (416 threads); setmaxnreg moves registers WITHIN the CTA's
+// launch allocation (416 x 128 = 53248), so 128*232 (epilogue) + 128*56 (gatherers) + 128*88
+// (converters) + 32*128 (MMA warp) = 52224 must fit in it -- an over-subscribed inc never returns.
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// A stages that fit beside a filter slice of `cols` columns (1 KB alignment slack, barriers, epilogue params)
+__host__ __device__ constexpr int a_stages(int cols) {
+  int n = (kSmemBudget - 1024 - 2 * cols * 128 - 2048) / kAStageBytes;
+  return n > kMaxAStages ? kMaxAStages : n;
+}
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
@@ -184,50 +224,56 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
   constexpr int CH = COLS / T;                 // output channels this CTA owns
   constexpr int CH_PER_LD = 16 / T;            // channels per 16-column TMEM load
   constexpr int TMEM_COLS = (2 * NC) < 32 ? 32 : 2 * NC;
-  static_assert(NC % 32 == 0 && NC <= 256 && 16 % T == 0 && CH <= 64, "unsupported shape");
+  constexpr int NST = a_stages(COLS);          // A stages that fit beside the filter slice
+  static_assert(NC % 32 == 0 && NC <= 256 && 16 % T == 0 && CH <= 64 && NST >= 2, "unsupported shape");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem;                                        // [2 parts][COLS rows][128 B]
-  uint8_t* sA = sB + 2 * COLS * 128;                         // [kAStages][2 parts][128 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + kAStages * kAStageBytes);
-  // bars: a_full[2], a_empty[2], t_full[2], t_empty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint8_t* sA = sB + 2 * COLS * 128;                         // [NST][2 parts][128 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + NST * kAStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+  float* s_epi = reinterpret_cast<float*>(tmem_slot + 4);    // [3][CH]: bias, BN scale, BN shift of this CTA's channels
   const uint32_t bar0 = smem_u32(bars);
-  auto a_full = [&](int s) { return bar0 + 8u * s; };
-  auto a_empty = [&](int s) { return bar0 + 8u * (2 + s); };
-  auto t_full = [&](int s) { return bar0 + 8u * (4 + s); };
-  auto t_empty = [&](int s) { return bar0 + 8u * (6 + s); };
+  auto a_full = [&](uint32_t s) { return bar0 + 8u * s; };
+  auto a_empty = [&](uint32_t s) { return bar0 + 8u * (kMaxAStages + s); };
+  auto raw_full = [&](uint32_t s) { return bar0 + 8u * (2 * kMaxAStages + s); };
+  auto t_full = [&](uint32_t s) { return bar0 + 8u * (3 * kMaxAStages + s); };
+  auto t_empty = [&](uint32_t s) { return bar0 + 8u * (3 * kMaxAStages + 2 + s); };
+  const uint32_t w_full = bar0 + 8u * (3 * kMaxAStages + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int split = blockIdx.x % S, worker = blockIdx.x / S;
   const int col0 = split * COLS;                             // first W column of this CTA
   const int ch0 = col0 / T;                                  // first output channel of this CTA
-  const int64_t rows_total = (int64_t)p.B * p.M;
+  const uint32_t rows_total = (uint32_t)p.B * (uint32_t)p.M;    // < 2^31 (tc_supported)
+  const uint32_t Mu = (uint32_t)p.M;
+  // (b, m) of flattened destination row g; B == 1 is the common (single graph) case
+  auto split_row = [&](uint32_t g, uint32_t& b, uint32_t& m) {
+    if (p.B == 1) { b = 0; m = g; } else { b = g / Mu; m = g - b * Mu; }
+  };
+  const int my_tiles = worker < n_tiles ? (n_tiles - worker + n_workers - 1) / n_workers : 0;
+  const uint32_t n_items = (uint32_t)my_tiles * (uint32_t)p.K;   // (tile, k) items of this CTA, in order
 
   // ---- one-time setup ---------------------------------------------------------------------
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(a_full(s), kProdWarps * 32);
+    for (int s = 0; s < kMaxAStages; ++s) {
+      mbar_init(a_full(s), kConvWarps * 32);
       mbar_init(a_empty(s), 1);
+      mbar_init(raw_full(s), kGatherWarps * 32);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(t_full(s), 1);
       mbar_init(t_empty(s), kEpiWarps * 32);
     }
+    mbar_init(w_full, 1);
     fence_barrier_init();
   }
-  if (warp == kEpiWarps + kProdWarps) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
-  // stationary B: this CTA's column slice of the split-bf16 filter image
-  {
-    const int OT = p.O * p.T;
-    const uint4* src_hi = reinterpret_cast<const uint4*>(wimg + kHeaderBytes + (size_t)col0 * 128);
-    const uint4* src_lo = reinterpret_cast<const uint4*>(wimg + kHeaderBytes + (size_t)OT * 128 + (size_t)col0 * 128);
-    uint4* dst = reinterpret_cast<uint4*>(sB);
-    constexpr int n16 = COLS * 128 / 16;
-    for (int i = tid; i < n16; i += kThreads) {
-      dst[i] = __ldg(src_hi + i);
-      dst[n16 + i] = __ldg(src_lo + i);
-    }
-    fence_proxy_async();
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  if (tid < CH) {
+    s_epi[tid] = p.bias ? p.bias[ch0 + tid] : 0.f;
+    s_epi[CH + tid] = p.scale ? p.scale[ch0 + tid] : 1.f;
+    s_epi[2 * CH + tid] = p.scale ? p.shift[ch0 + tid] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -241,12 +287,29 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     reg_inc<232>();
     const int r = tid;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int64_t et_st = (int64_t)p.M * p.K;                // stride between edge types
+    // edge-type vector + liveness of item (tile j, slot k) for this thread's row
+    float et_nx[T];
+    bool live_nx = false;
+    auto fetch = [&](int tile, int k) {
+      const uint32_t g = (uint32_t)tile * kTileM + r;
+      const bool ok = tile < n_tiles && g < rows_total;
+      uint32_t b = 0, m = 0;
+      if (ok) split_row(g, b, m);
+      const float* pe = p.et + (int64_t)b * p.et_sb + (int64_t)m * p.K + k;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        et_nx[t] = ok ? __ldg(pe) : 0.f;
+        pe += et_st;
+      }
+      live_nx = ok;
+      if (ok && p.mask_neg) live_nx = load_index(p.idx, p.idx64, (int64_t)b * p.idx_sb + (int64_t)m * p.K + k) >= 0;
+    };
+    fetch(worker, 0);
     uint32_t ct = 0;
     for (int tile = worker; tile < n_tiles; tile += n_workers) {
-      const int64_t g = (int64_t)tile * kTileM + r;
+      const uint32_t g = (uint32_t)tile * kTileM + r;
       const bool valid = g < rows_total;
-      const int b = valid ? (int)(g / p.M) : 0;
-      const int m = valid ? (int)(g % p.M) : 0;
       float acc[CH];                                         // max | running max of gamma*e | sum
       float acc2[AGG == FGNN_AGG_SOFTMAX ? CH : 1];          // softmax: running sum of exp
       float live_count = 0.f;
@@ -254,21 +317,13 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
       for (int c = 0; c < CH; ++c) acc[c] = (AGG == FGNN_AGG_MEAN) ? 0.f : -INFINITY;
 #pragma unroll
       for (int c = 0; c < (AGG == FGNN_AGG_SOFTMAX ? CH : 1); ++c) acc2[c] = 0.f;
-      const float* et_row = p.et + (int64_t)b * p.et_sb + (int64_t)m * p.K;
-      const int64_t et_st = (int64_t)p.M * p.K;              // stride between edge types
       for (int k = 0; k < p.K; ++k) {
-        // this slot's edge-type vector (issued before the accumulator wait so the loads overlap the MMA)
         float et[T];
-        bool live = valid;
-        if (valid && p.mask_neg) live = load_index(p.idx, p.idx64, (int64_t)b * p.idx_sb + (int64_t)m * p.K + k) >= 0;
-        {
-          const float* pe = et_row + k;                       // one live pointer, bumped per edge type
 #pragma unroll
-          for (int t = 0; t < T; ++t) {
-            et[t] = valid ? __ldg(pe) : 0.f;
-            pe += et_st;
-          }
-        }
+        for (int t = 0; t < T; ++t) et[t] = et_nx[t];
+        const bool live = live_nx;
+        // prefetch the next item's edge types: their latency hides behind this item's math
+        if (k + 1 < p.K) fetch(tile, k + 1); else fetch(tile + n_workers, 0);
 #pragma unroll
         for (int chunk = 0; chunk < NCH; ++chunk) {
           const uint32_t st = ct & 1;
@@ -308,6 +363,8 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
       }
       // finish: aggregate, bias / eval-BN / activation (mp_nn.py:162-173), store this row's channels
       if (valid) {
+        uint32_t b, m;
+        split_row(g, b, m);
         float* orow = p.out + (int64_t)b * p.o_sb + (int64_t)m * p.o_sm + ch0;
 #pragma unroll
         for (int c4 = 0; c4 < CH; c4 += 4) {
@@ -319,7 +376,12 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
             if (AGG == FGNN_AGG_MAX) a = acc[c];
             else if (AGG == FGNN_AGG_SOFTMAX) a = live_count > 0.f ? (logf(acc2[c]) + acc[c]) / p.gamma : -INFINITY;
             else a = live_count > 0.f ? acc[c] / live_count : 0.f;
-            if (a != -INFINITY) a = apply_epilogue(a, ch0 + c, p);
+            if (a != -INFINITY) {
+              if (p.bias) a += s_epi[c];                                     // mp_nn.py:165-168
+              if (p.scale) a = fmaf(a, s_epi[CH + c], s_epi[2 * CH + c]);    // mp_nn.py:169-170 (eval BN, folded)
+              if (p.act == FGNN_ACT_RELU) a = fmaxf(a, 0.f);                 // mp_nn.py:172-173
+              else if (p.act == FGNN_ACT_LEAKY_RELU) a = a >= 0.f ? a : a * p.slope;
+            }
             v[j] = a;
           }
           float4* dst = reinterpret_cast<float4*>(orow + c4);
@@ -331,101 +393,134 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
         }
       }
     }
-  } else if (warp < kEpiWarps + kProdWarps) {
+  } else if (warp < kEpiWarps + kGatherWarps) {
     // =====================================================================================
-    // PRODUCERS: gather + split the A operand of every (tile, k)
+    // GATHERERS: cp.async the 128 source rows of every item into its A stage (raw fp32 chunks)
     // =====================================================================================
-    reg_dec<96>();
+    reg_dec<56>();
     const int pw = warp - kEpiWarps;                         // rows pw*32 .. pw*32+31 of the tile
-    const int sub = lane >> 4, q = lane & 15;                // 16 lanes x float4 = one 256-byte row
-    uint32_t it = 0;
-    for (int tile = worker; tile < n_tiles; tile += n_workers) {
-      const int64_t g = (int64_t)tile * kTileM + pw * 32 + lane;   // the row this lane owns for index loads
-      const bool valid = g < rows_total;
-      const int b = valid ? (int)(g / p.M) : 0;
-      const int m = valid ? (int)(g % p.M) : 0;
-      const int64_t idx_off = (int64_t)b * p.idx_sb + (int64_t)m * p.K;
-      const int64_t x_base = (int64_t)b * p.x_sb;
-      for (int k = 0; k < p.K; ++k) {
-        int64_t src = -1;                                    // element offset of the source row, -1 = no row
-        if (valid) {
-          const int64_t n = load_index(p.idx, p.idx64, idx_off + k);
-          if (n >= 0 && n < p.N) src = x_base + n * p.x_sn;
-        }
-        const uint32_t st = it & 1;
-        mbar_wait(a_empty(st), ((it >> 1) & 1) ^ 1);
-        uint8_t* a_hi = sA + st * kAStageBytes;
-        uint8_t* a_lo = a_hi + kAPartBytes;
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-          const int rw = 2 * i + sub;                        // row within this warp's 32
-          const int64_t off = __shfl_sync(0xffffffffu, src, rw);
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (off >= 0) v = ldg_f4(p.x + off + q * 4);
-          const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
-          const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-          const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
-          const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
-          const int row = pw * 32 + rw;
-          const uint32_t o = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u +
-                             (uint32_t)(((q >> 1) ^ (row & 7)) * 16) + (uint32_t)(q & 1) * 8u;
-          *reinterpret_cast<uint2*>(a_hi + o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01),
-                                                           *reinterpret_cast<const uint32_t*>(&h23));
-          *reinterpret_cast<uint2*>(a_lo + o) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01),
-                                                           *reinterpret_cast<const uint32_t*>(&l23));
-        }
-        fence_proxy_async();                                 // generic-proxy stores -> visible to the MMA (async proxy)
-        mbar_arrive(a_full(st));
-        ++it;
+    const int sub = lane >> 4, q = lane & 15;                // 16 lanes x 16 B = one 256-byte row
+    // source row (b*N + n; x is batch-contiguous, checked by tc_supported) this lane owns for item i:
+    // row pw*32+lane of the tile; -1 = no row (tail of the last tile, masked or out-of-range slot)
+    auto source_of = [&](uint32_t i) -> int32_t {
+      if (i >= n_items) return -1;
+      const uint32_t j = i / (uint32_t)p.K, k = i - j * (uint32_t)p.K;
+      const uint32_t g = ((uint32_t)worker + j * (uint32_t)n_workers) * kTileM + pw * 32 + lane;
+      if (g >= rows_total) return -1;
+      uint32_t b, m;
+      split_row(g, b, m);
+      const int64_t n = load_index(p.idx, p.idx64, (int64_t)b * p.idx_sb + (int64_t)m * p.K + k);
+      return (n >= 0 && n < p.N) ? (int32_t)((int64_t)b * p.N + n) : -1;
+    };
+    const float* xq = p.x + q * 4;
+    const uint32_t sA_u = smem_u32(sA);
+    // raw chunk q (floats 4q..4q+3) of a row lands at bf16 chunk q/2 of the hi (q even) / lo (q odd) image
+    const uint32_t part_off = (uint32_t)(q & 1) * kAPartBytes;
+    int32_t src = source_of(0);
+    for (uint32_t i = 0; i < n_items; ++i) {
+      const uint32_t st = i % NST, use = i / NST;
+      const int32_t src_next = source_of(i + 1);             // index load of the next item: in flight during this one
+      mbar_wait(a_empty(st), (use & 1) ^ 1);
+      const uint32_t stage = sA_u + st * kAStageBytes + part_off;
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int rw = 2 * it + sub;
+        const int32_t row = __shfl_sync(0xffffffffu, src, rw);
+        const int rr = pw * 32 + rw;
+        const uint32_t dst = stage + (uint32_t)(rr >> 3) * 1024u + (uint32_t)(rr & 7) * 128u +
+                             (uint32_t)(((q >> 1) ^ (rr & 7)) * 16);
+        cp_async16(dst, xq + (int64_t)(row >= 0 ? row : 0) * kC, row >= 0 ? 16u : 0u);
       }
+      cp_async_arrive_noinc(raw_full(st));
+      src = src_next;
+    }
+  } else if (warp < kMmaWarp) {
+    // =====================================================================================
+    // CONVERTERS: raw fp32 -> split bf16, in place (thread-local: two 16-byte chunks in, two out)
+    // =====================================================================================
+    reg_dec<88>();
+    const int cr = tid - (kEpiWarps + kGatherWarps) * 32;    // row of the tile this thread converts
+    const uint32_t row_off = (uint32_t)(cr >> 3) * 1024u + (uint32_t)(cr & 7) * 128u;
+    for (uint32_t i = 0; i < n_items; ++i) {
+      const uint32_t st = i % NST, use = i / NST;
+      mbar_wait(raw_full(st), use & 1);
+      uint8_t* hi = sA + st * kAStageBytes + row_off;
+      uint8_t* lo = hi + kAPartBytes;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t o = (uint32_t)((j ^ (cr & 7)) * 16);
+        const float4 a = *reinterpret_cast<const float4*>(hi + o);      // channels 8j .. 8j+3
+        const float4 c = *reinterpret_cast<const float4*>(lo + o);      // channels 8j+4 .. 8j+7
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(c.x, c.y), h3 = __floats2bfloat162_rn(c.z, c.w);
+        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+        const float2 f2 = __bfloat1622float2(h2), f3 = __bfloat1622float2(h3);
+        const __nv_bfloat162 l0 = __floats2bfloat162_rn(a.x - f0.x, a.y - f0.y), l1 = __floats2bfloat162_rn(a.z - f1.x, a.w - f1.y);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(c.x - f2.x, c.y - f2.y), l3 = __floats2bfloat162_rn(c.z - f3.x, c.w - f3.y);
+        *reinterpret_cast<uint4*>(hi + o) = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                                                       *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+        *reinterpret_cast<uint4*>(lo + o) = make_uint4(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1),
+                                                       *reinterpret_cast<const uint32_t*>(&l2), *reinterpret_cast<const uint32_t*>(&l3));
+      }
+      fence_proxy_async();                                   // generic-proxy stores -> visible to the MMA (async proxy)
+      mbar_arrive(a_full(st));
     }
   } else {
     // =====================================================================================
-    // MMA ISSUER: one lane
+    // MMA ISSUER: the whole warp runs the loop (warp-uniform control flow, so addresses and
+    // descriptors live in uniform registers); one elected lane issues.  First: the stationary
+    // B operand (this CTA's column slice of the split-bf16 filter image) by TMA bulk copy.
     // =====================================================================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(NC);
-      const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-      uint32_t it = 0, ct = 0;
-      for (int tile = worker; tile < n_tiles; tile += n_workers) {
-        for (int k = 0; k < p.K; ++k) {
-          const uint32_t st = it & 1;
-          mbar_wait(a_full(st), (it >> 1) & 1);
-          tc_fence_after();
-          const uint32_t a_hi = sA_u + st * kAStageBytes, a_lo = a_hi + kAPartBytes;
-#pragma unroll
-          for (int chunk = 0; chunk < NCH; ++chunk) {
-            const uint32_t ts = ct & 1;
-            mbar_wait(t_empty(ts), ((ct >> 1) & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + ts * NC;
-            const uint32_t b_hi = sB_u + (uint32_t)chunk * NC * 128u, b_lo = b_hi + (uint32_t)COLS * 128u;
-            uint32_t accumulate = 0;
-#pragma unroll
-            for (int term = 0; term < 3; ++term) {           // xl*Wh + xh*Wl + xh*Wh
-              const uint32_t a = term == 0 ? a_lo : a_hi;
-              const uint32_t bb = term == 1 ? b_lo : b_hi;
-#pragma unroll
-              for (int ks = 0; ks < kC / 16; ++ks) {
-                umma_bf16(d_tmem, umma_desc_sw128(a + ks * 32), umma_desc_sw128(bb + ks * 32), idesc, accumulate);
-                accumulate = 1;
-              }
-            }
-            umma_commit(t_full(ts));                         // accumulator ready when these MMAs retire
-            ++ct;
-          }
-          umma_commit(a_empty(st));                          // A stage reusable when its readers retire
-          ++it;
-        }
+    const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+    if (elect_one()) {
+      const int OT = p.O * p.T;
+      constexpr uint32_t part = COLS * 128, piece = part < 32768u ? part : 32768u;
+      mbar_expect_tx(w_full, 2 * part);
+      for (int h = 0; h < 2; ++h) {
+        const uint8_t* src = wimg + kHeaderBytes + (size_t)h * OT * 128 + (size_t)col0 * 128;
+        for (uint32_t o = 0; o < part; o += piece) bulk_g2s(sB_u + h * part + o, src + o, piece, w_full);
       }
     }
     __syncwarp();
+    mbar_wait(w_full, 0);
+    constexpr uint32_t idesc = umma_idesc(NC);
+    // descriptor of a tile = constant high word + (address >> 4) in the low word
+    const uint64_t desc_hi = umma_desc_sw128(0);
+    uint32_t ct = 0;
+    for (uint32_t i = 0; i < n_items; ++i) {
+      const uint32_t st = i % NST, use = i / NST;
+      mbar_wait(a_full(st), use & 1);
+      const uint32_t a_hi = (sA_u + st * kAStageBytes) >> 4, a_lo = a_hi + (kAPartBytes >> 4);
+#pragma unroll
+      for (int chunk = 0; chunk < NCH; ++chunk) {
+        const uint32_t ts = ct & 1;
+        mbar_wait(t_empty(ts), ((ct >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + ts * NC;
+        const uint32_t b_hi = (sB_u + (uint32_t)chunk * NC * 128u) >> 4, b_lo = b_hi + ((uint32_t)COLS * 128u >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {             // xl*Wh + xh*Wl + xh*Wh
+            const uint32_t a = term == 0 ? a_lo : a_hi;
+            const uint32_t bb = term == 1 ? b_lo : b_hi;
+#pragma unroll
+            for (int ks = 0; ks < kC / 16; ++ks)
+              umma_bf16(d_tmem, desc_hi | (uint64_t)(a + ks * 2), desc_hi | (uint64_t)(bb + ks * 2), idesc,
+                        (term | ks) != 0);
+          }
+          umma_commit(t_full(ts));                           // accumulator ready when these MMAs retire
+          if (chunk == NCH - 1) umma_commit(a_empty(st));    // A stage reusable when its readers retire
+        }
+        __syncwarp();
+        ++ct;
+      }
+    }
   }
 
   // ---- teardown -----------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == kEpiWarps + kProdWarps) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
@@ -458,7 +553,9 @@ TcConfig pick_config(int T, int agg, int OT) {
 }
 
 size_t smem_bytes(const TcConfig& c) {
-  return 1024 + (size_t)2 * c.NC * c.NCH * 128 + (size_t)tc::kAStages * tc::kAStageBytes + 8 * 8 + 16;
+  const int cols = c.NC * c.NCH;
+  return 1024 + (size_t)2 * cols * 128 + (size_t)tc::a_stages(cols) * tc::kAStageBytes + tc::kNumBars * 8 + 16 +
+         3 * 64 * 4;
 }
 
 template <int T, int NC, int NCH>
@@ -484,14 +581,16 @@ bool tc_supported(const fgnn_mp_args* a) {
   if (a->extension != FGNN_NO_EXTENSION || a->dtype != FGNN_F32) return false;
   if (a->C != tc::kC) return false;
   if (a->aggregator == FGNN_AGG_NONE) return false;
-  if (a->x_sc != 1 || a->x_sn != a->C || (a->x_sb & 3)) return false;          // node-major, 16-byte rows
+  if (a->x_sc != 1 || a->x_sn != a->C) return false;                              // node-major rows
+  if (a->B > 1 && a->x_sb != (int64_t)a->N * a->C) return false;                  // batch-contiguous
+  if ((int64_t)a->B * a->N >= INT32_MAX) return false;
   if ((reinterpret_cast<uintptr_t>(a->x) & 15) || (reinterpret_cast<uintptr_t>(a->out) & 15)) return false;
   if (a->out_so != 1 || (a->out_sm & 3) || (a->out_sb & 3)) return false;
   if (a->O % 4) return false;
   const TcConfig c = pick_config(a->T, a->aggregator, a->O * a->T);
   if (!c.ok) return false;
-  if (smem_bytes(c) > 227 * 1024) return false;
-  if ((int64_t)a->B * a->M > (int64_t)INT32_MAX * 64) return false;
+  if (smem_bytes(c) > (size_t)tc::kSmemBudget || tc::a_stages(c.NC * c.NCH) < 2) return false;
+  if ((int64_t)a->B * a->M >= (int64_t)INT32_MAX - 256) return false;
   return true;
 }
 

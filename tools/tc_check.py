@@ -91,6 +91,10 @@ def timeit(B, N, M, K, T, kernel, reps=10):
 
 
 if __name__ == "__main__":
+    if "--profile" in sys.argv:           # two launches for ncu: V2F-pairwise shaped, T=16 and T=4
+        timeit(1, 100_000, 300_000, 2, 16, _lib.KERNEL_TCGEN05, reps=1)
+        timeit(1, 100_000, 300_000, 2, 4, _lib.KERNEL_TCGEN05, reps=1)
+        sys.exit(0)
     ok = True
     ok &= run(1, 200, 128, 1, 16)
     ok &= run(1, 200, 128, 2, 16)
