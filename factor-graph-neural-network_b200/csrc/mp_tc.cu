@@ -100,6 +100,15 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
 // one lane of a converged warp (warp-uniform control flow keeps descriptors in uniform registers)
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -231,9 +240,9 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem;                                        // [2 parts][COLS rows][128 B]
   uint8_t* sA = sB + 2 * COLS * 128;                         // [NST][2 parts][128 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + NST * kAStageBytes);
+  float* s_epi = reinterpret_cast<float*>(sA + NST * kAStageBytes);   // [3][64]: bias, BN scale, BN shift (16-byte aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + 3 * 64);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
-  float* s_epi = reinterpret_cast<float*>(tmem_slot + 4);    // [3][CH]: bias, BN scale, BN shift of this CTA's channels
   const uint32_t bar0 = smem_u32(bars);
   auto a_full = [&](uint32_t s) { return bar0 + 8u * s; };
   auto a_empty = [&](uint32_t s) { return bar0 + 8u * (kMaxAStages + s); };
@@ -270,7 +279,7 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
-  if (tid < CH) {
+  if (tid < CH) {                                             // absent bias / BN: exact identities (+0, *1, +0)
     s_epi[tid] = p.bias ? p.bias[ch0 + tid] : 0.f;
     s_epi[CH + tid] = p.scale ? p.scale[ch0 + tid] : 1.f;
     s_epi[2 * CH + tid] = p.scale ? p.shift[ch0 + tid] : 0.f;
@@ -338,9 +347,22 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
             if (gq + 1 < NC / 16) tmem_ld16(taddr + (gq + 1) * 16, d[(gq + 1) & 1]);
 #pragma unroll
             for (int q = 0; q < CH_PER_LD; ++q) {
-              float e = 0.f;
+              float e;
+              if (T >= 4) {                                  // four independent chains: FMA latency, not count, binds here
+                float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
 #pragma unroll
-              for (int t = 0; t < T; ++t) e = fmaf(et[t], __uint_as_float(d[gq & 1][q * T + t]), e);
+                for (int t = 0; t < T; t += 4) {
+                  e0 = fmaf(et[t], __uint_as_float(d[gq & 1][q * T + t]), e0);
+                  e1 = fmaf(et[(t + 1) % T], __uint_as_float(d[gq & 1][q * T + (t + 1) % T]), e1);
+                  e2 = fmaf(et[(t + 2) % T], __uint_as_float(d[gq & 1][q * T + (t + 2) % T]), e2);
+                  e3 = fmaf(et[(t + 3) % T], __uint_as_float(d[gq & 1][q * T + (t + 3) % T]), e3);
+                }
+                e = (e0 + e1) + (e2 + e3);
+              } else {
+                e = 0.f;
+#pragma unroll
+                for (int t = 0; t < T; ++t) e = fmaf(et[t], __uint_as_float(d[gq & 1][q * T + t]), e);
+              }
               const int c = chunk * (NC / T) + gq * CH_PER_LD + q;
               if (AGG == FGNN_AGG_MAX) {
                 acc[c] = live ? fmaxf(acc[c], e) : acc[c];
@@ -366,23 +388,25 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
         uint32_t b, m;
         split_row(g, b, m);
         float* orow = p.out + (int64_t)b * p.o_sb + (int64_t)m * p.o_sm + ch0;
+        const uint32_t epi_u = smem_u32(s_epi);
+        const float inv_gamma = 1.f / p.gamma, inv_live = live_count > 0.f ? 1.f / live_count : 0.f;
+        // negative-side slope of the activation: 1 = none, 0 = ReLU, slope = LeakyReLU
+        const float neg = p.act == FGNN_ACT_NONE ? 1.f : (p.act == FGNN_ACT_RELU ? 0.f : p.slope);
 #pragma unroll
         for (int c4 = 0; c4 < CH; c4 += 4) {
+          const float4 bi = lds_f4(epi_u + c4 * 4), sc = lds_f4(epi_u + (CH + c4) * 4), sh = lds_f4(epi_u + (2 * CH + c4) * 4);
+          const float bia[4] = {bi.x, bi.y, bi.z, bi.w}, sca[4] = {sc.x, sc.y, sc.z, sc.w}, shi[4] = {sh.x, sh.y, sh.z, sh.w};
           float v[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int c = c4 + j;
             float a;
             if (AGG == FGNN_AGG_MAX) a = acc[c];
-            else if (AGG == FGNN_AGG_SOFTMAX) a = live_count > 0.f ? (logf(acc2[c]) + acc[c]) / p.gamma : -INFINITY;
-            else a = live_count > 0.f ? acc[c] / live_count : 0.f;
-            if (a != -INFINITY) {
-              if (p.bias) a += s_epi[c];                                     // mp_nn.py:165-168
-              if (p.scale) a = fmaf(a, s_epi[CH + c], s_epi[2 * CH + c]);    // mp_nn.py:169-170 (eval BN, folded)
-              if (p.act == FGNN_ACT_RELU) a = fmaxf(a, 0.f);                 // mp_nn.py:172-173
-              else if (p.act == FGNN_ACT_LEAKY_RELU) a = a >= 0.f ? a : a * p.slope;
-            }
-            v[j] = a;
+            else if (AGG == FGNN_AGG_SOFTMAX) a = live_count > 0.f ? (logf(acc2[c]) + acc[c]) * inv_gamma : -INFINITY;
+            else a = acc[c] * inv_live;
+            float y = fmaf(a + bia[j], sca[j], shi[j]);      // bias, then eval BN folded to scale/shift
+            y = y >= 0.f ? y : y * neg;
+            v[j] = a == -INFINITY ? a : y;                   // no live slot on this shard: stay -inf
           }
           float4* dst = reinterpret_cast<float4*>(orow + c4);
           if (p.accumulate) {
@@ -400,27 +424,32 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     reg_dec<56>();
     const int pw = warp - kEpiWarps;                         // rows pw*32 .. pw*32+31 of the tile
     const int sub = lane >> 4, q = lane & 15;                // 16 lanes x 16 B = one 256-byte row
-    // source row (b*N + n; x is batch-contiguous, checked by tc_supported) this lane owns for item i:
-    // row pw*32+lane of the tile; -1 = no row (tail of the last tile, masked or out-of-range slot)
-    auto source_of = [&](uint32_t i) -> int32_t {
+    // index-table entry of the row this lane owns (row pw*32+lane of item i's tile); the load is
+    // issued one item ahead and only CONSUMED (range check -> source row) after the stage wait
+    auto index_of = [&](uint32_t i, int32_t& base) -> int64_t {
+      base = -1;
       if (i >= n_items) return -1;
       const uint32_t j = i / (uint32_t)p.K, k = i - j * (uint32_t)p.K;
       const uint32_t g = ((uint32_t)worker + j * (uint32_t)n_workers) * kTileM + pw * 32 + lane;
       if (g >= rows_total) return -1;
       uint32_t b, m;
       split_row(g, b, m);
-      const int64_t n = load_index(p.idx, p.idx64, (int64_t)b * p.idx_sb + (int64_t)m * p.K + k);
-      return (n >= 0 && n < p.N) ? (int32_t)((int64_t)b * p.N + n) : -1;
+      base = (int32_t)(b * (uint32_t)p.N);
+      return load_index(p.idx, p.idx64, (int64_t)b * p.idx_sb + (int64_t)m * p.K + k);
     };
     const float* xq = p.x + q * 4;
     const uint32_t sA_u = smem_u32(sA);
     // raw chunk q (floats 4q..4q+3) of a row lands at bf16 chunk q/2 of the hi (q even) / lo (q odd) image
     const uint32_t part_off = (uint32_t)(q & 1) * kAPartBytes;
-    int32_t src = source_of(0);
+    int32_t base, base_next;
+    int64_t n = index_of(0, base);
     for (uint32_t i = 0; i < n_items; ++i) {
       const uint32_t st = i % NST, use = i / NST;
-      const int32_t src_next = source_of(i + 1);             // index load of the next item: in flight during this one
+      const int64_t n_next = index_of(i + 1, base_next);     // index load of the next item: in flight during this one
       mbar_wait(a_empty(st), (use & 1) ^ 1);
+      // source row (b*N + n; x is batch-contiguous, checked by tc_supported); -1 = no row (tile tail,
+      // masked or out-of-range slot) -> zero-filled
+      const int32_t src = (base >= 0 && n >= 0 && n < p.N) ? base + (int32_t)n : -1;
       const uint32_t stage = sA_u + st * kAStageBytes + part_off;
 #pragma unroll
       for (int it = 0; it < 16; ++it) {
@@ -432,7 +461,8 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
         cp_async16(dst, xq + (int64_t)(row >= 0 ? row : 0) * kC, row >= 0 ? 16u : 0u);
       }
       cp_async_arrive_noinc(raw_full(st));
-      src = src_next;
+      n = n_next;
+      base = base_next;
     }
   } else if (warp < kMmaWarp) {
     // =====================================================================================
@@ -440,27 +470,33 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     // =====================================================================================
     reg_dec<88>();
     const int cr = tid - (kEpiWarps + kGatherWarps) * 32;    // row of the tile this thread converts
-    const uint32_t row_off = (uint32_t)(cr >> 3) * 1024u + (uint32_t)(cr & 7) * 128u;
+    const uint32_t row_u = smem_u32(sA) + (uint32_t)(cr >> 3) * 1024u + (uint32_t)(cr & 7) * 128u;
     for (uint32_t i = 0; i < n_items; ++i) {
       const uint32_t st = i % NST, use = i / NST;
       mbar_wait(raw_full(st), use & 1);
-      uint8_t* hi = sA + st * kAStageBytes + row_off;
-      uint8_t* lo = hi + kAPartBytes;
+      const uint32_t hi = row_u + st * kAStageBytes, lo = hi + kAPartBytes;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t o = (uint32_t)((j ^ (cr & 7)) * 16);
-        const float4 a = *reinterpret_cast<const float4*>(hi + o);      // channels 8j .. 8j+3
-        const float4 c = *reinterpret_cast<const float4*>(lo + o);      // channels 8j+4 .. 8j+7
-        const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
-        const __nv_bfloat162 h2 = __floats2bfloat162_rn(c.x, c.y), h3 = __floats2bfloat162_rn(c.z, c.w);
-        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-        const float2 f2 = __bfloat1622float2(h2), f3 = __bfloat1622float2(h3);
-        const __nv_bfloat162 l0 = __floats2bfloat162_rn(a.x - f0.x, a.y - f0.y), l1 = __floats2bfloat162_rn(a.z - f1.x, a.w - f1.y);
-        const __nv_bfloat162 l2 = __floats2bfloat162_rn(c.x - f2.x, c.y - f2.y), l3 = __floats2bfloat162_rn(c.z - f3.x, c.w - f3.y);
-        *reinterpret_cast<uint4*>(hi + o) = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
-                                                       *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
-        *reinterpret_cast<uint4*>(lo + o) = make_uint4(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1),
-                                                       *reinterpret_cast<const uint32_t*>(&l2), *reinterpret_cast<const uint32_t*>(&l3));
+      for (int half = 0; half < 2; ++half) {                 // 8 loads in flight, then 8 stores
+        float4 a[4], c[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const uint32_t o = (uint32_t)(((half * 4 + jj) ^ (cr & 7)) * 16);
+          a[jj] = lds_f4(hi + o);                            // channels 8j .. 8j+3
+          c[jj] = lds_f4(lo + o);                            // channels 8j+4 .. 8j+7
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const uint32_t o = (uint32_t)(((half * 4 + jj) ^ (cr & 7)) * 16);
+          const __nv_bfloat162 h0 = __floats2bfloat162_rn(a[jj].x, a[jj].y), h1 = __floats2bfloat162_rn(a[jj].z, a[jj].w);
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(c[jj].x, c[jj].y), h3 = __floats2bfloat162_rn(c[jj].z, c[jj].w);
+          const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+          const float2 f2 = __bfloat1622float2(h2), f3 = __bfloat1622float2(h3);
+          sts_u4(hi + o, pack_bf16(h0), pack_bf16(h1), pack_bf16(h2), pack_bf16(h3));
+          sts_u4(lo + o, pack_bf16(__floats2bfloat162_rn(a[jj].x - f0.x, a[jj].y - f0.y)),
+                 pack_bf16(__floats2bfloat162_rn(a[jj].z - f1.x, a[jj].w - f1.y)),
+                 pack_bf16(__floats2bfloat162_rn(c[jj].x - f2.x, c[jj].y - f2.y)),
+                 pack_bf16(__floats2bfloat162_rn(c[jj].z - f3.x, c[jj].w - f3.y)));
+        }
       }
       fence_proxy_async();                                   // generic-proxy stores -> visible to the MMA (async proxy)
       mbar_arrive(a_full(st));
