@@ -6,7 +6,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfgnn_b200.so")
+LIB_PATH = os.environ.get("FGNN_B200_LIB") or os.path.join(HERE, "libfgnn_b200.so")   # override: debug/trace builds
 
 # enums (include/fgnn_b200.h)
 NO_EXTENSION, ORIG_WITH_NEIGHBOR, ORIG_WITH_DIFF = 0, 1, 2

@@ -34,10 +34,18 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    """Compile the CUDA library if it is missing or older than its sources.  Returns its path."""
+def build(force=False, verbose=False, trace=False):
+    """Compile the CUDA library if it is missing or older than its sources.  Returns its path.
+    trace=True builds libfgnn_b200_trace.so with -DFGNN_TC_TRACE (per-item pipeline timestamps,
+    tools/tc_trace.py); the product library never carries that code."""
+    if trace:
+        return _compile(LIB.replace(".so", "_trace.so"), verbose, ["-DFGNN_TC_TRACE"])
     if not force and not _stale():
         return LIB
+    return _compile(LIB, verbose, [])
+
+
+def _compile(out, verbose, extra):
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
            "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false"]
     cmd = [c for c in cmd if c != "--use_fast_math=false"]
@@ -46,14 +54,14 @@ def build(force=False, verbose=False):
     # the image exports CC=/opt/gcc/bin/gcc; nvcc wants the system g++
     if os.path.exists("/usr/bin/g++"):
         cmd += ["-ccbin", "/usr/bin/g++"]
-    cmd += ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += extra + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libfgnn_b200.so:\n" + res.stdout[-4000:])
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, trace="--trace" in sys.argv))

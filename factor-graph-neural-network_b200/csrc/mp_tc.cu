@@ -12,22 +12,28 @@
 // reaches HBM (the reference materialises H, an int64 index expansion and the gathered rows).
 //
 // fp32 parity on bf16 tensor cores: both operands are split x = xh + xl, W = Wh + Wl (bf16 each)
-// and three MMAs xh*Wh + xl*Wh + xh*Wl accumulate in fp32 (error ~2^-16 relative, inside the
+// and three MMAs xl*Wh + xh*Wl + xh*Wh accumulate in fp32 (error ~2^-16 relative, inside the
 // 1e-4 contract; plain TF32/bf16 is not -- SURVEY 7 hard part 2).
+//
+// Shared-memory bandwidth is the scarce resource (measured: with both operands in shared memory the
+// MMA reads 12 KB per 128-cycle instruction and runs at half rate while gather/convert starve), so
+// the A operand lives in TENSOR MEMORY: the converter threads write the split-bf16 rows straight
+// into TMEM with tcgen05.st (thread r == lane r == row r) and the MMA takes A from TMEM; shared
+// memory only carries the raw gather ring and the stationary filter slice.
 //
 // CTA roles (416 threads, 1 CTA / SM, persistent over tiles); an ITEM is one (tile, k):
 //   warps 0-3   epilogue    TMEM -> registers, edge-type contraction, aggregate, bias/BN/act, store;
 //                           the next item's edge-type vector is prefetched during the current one
-//   warps 4-7   gatherers   cp.async (LDGSTS) 16-byte chunks of the 128 source rows straight into the
-//                           A stage: no register staging, every free stage's gather is in flight.
-//                           Raw fp32 chunk 2j of row r lands where bf16 chunk j of A_hi[r] will live,
-//                           chunk 2j+1 where chunk j of A_lo[r] will live
-//   warps 8-11  converters  in place, thread-local: read the two raw chunks (8 floats), write the
-//                           8 bf16 "hi" halves over the first and the 8 "lo" halves over the second
-//                           -> the UMMA K-major SWIZZLE_128B images of A_hi / A_lo
-//   warp  12    MMA         one elected lane issues tcgen05.mma; owns the TMEM allocation; brings the
-//                           stationary filter slice in with TMA bulk copies (cp.async.bulk)
-// Pipelines (all mbarrier): A stages (3-6) a_empty -> raw_full -> a_full; TMEM stages (2) t_full/t_empty.
+//   warps 4-7   converters  thread r: raw fp32 row r from the ring (conflict-free swizzled chunks) ->
+//                           bf16 hi/lo pairs -> tcgen05.st into the A stage in TMEM
+//   warps 8-11  gatherers   cp.async (LDGSTS) 16-byte chunks of the 128 source rows into the raw ring:
+//                           no register staging, every free ring stage's gather is in flight; the
+//                           item's indices are loaded one item ahead
+//   warp  12    MMA         one elected lane issues tcgen05.mma (A: TMEM, B: smem descriptor); owns the
+//                           TMEM allocation; brings the stationary filter slice in with TMA bulk copies
+// TMEM (512 columns): 2 accumulator stages x 128 columns + 4 A stages x 64 columns (32 hi + 32 lo).
+// Pipelines (all mbarrier): raw ring raw_empty -> raw_full; A stages ta_empty -> ta_full;
+// accumulators t_empty -> t_full.
 // The filters are stationary: each CTA keeps the split-bf16 image of its column slice
 // (O*T / S columns, S = column split across CTAs so the slice fits in shared memory) for its
 // whole lifetime; the image is produced once per weight version by w_split_kernel.
@@ -37,6 +43,21 @@
 
 namespace fgnn {
 
+#ifdef FGNN_TC_TRACE
+// Debug builds only (-DFGNN_TC_TRACE): per-item timestamps of CTA 0, read back by tools/tc_trace.py.
+__device__ unsigned long long g_trace[8 * 4096];
+#define TC_TRACE(item, slot)                                                                    \
+  do {                                                                                          \
+    if (blockIdx.x == 0 && (item) < 4096u && (threadIdx.x & 31) == 0) {                         \
+      unsigned long long _t;                                                                    \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                                    \
+      g_trace[(item) * 8 + (slot)] = _t;                                                        \
+    }                                                                                           \
+  } while (0)
+#else
+#define TC_TRACE(item, slot) do { } while (0)
+#endif
+
 namespace tc {
 
 constexpr int kC = 64;                 // input channels (K dimension of the MMA), one 128-byte swizzle atom
@@ -44,11 +65,12 @@ constexpr int kTileM = 128;            // destinations per tile == UMMA M == TME
 constexpr int kEpiWarps = 4, kGatherWarps = 4, kConvWarps = 4;
 constexpr int kMmaWarp = kEpiWarps + kGatherWarps + kConvWarps;
 constexpr int kThreads = (kMmaWarp + 1) * 32;                 // 416
-constexpr int kMaxAStages = 6;
-constexpr int kNumBars = 3 * kMaxAStages + 5;                 // a_full, a_empty, raw_full, t_full[2], t_empty[2], w_full
+constexpr int kMaxAStages = 6;                                // raw ring stages in shared memory
+constexpr int kTA = 4;                                        // A stages in tensor memory
+constexpr int kAccCols = 128, kTACol0 = 2 * kAccCols, kTACols = 64;   // TMEM column map
+constexpr int kNumBars = 2 * kMaxAStages + 2 * kTA + 5;       // raw_full, raw_empty, ta_full, ta_empty, t_full[2], t_empty[2], w_full
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kAPartBytes = kTileM * kC * 2;                  // 16 KB: one bf16 part (hi or lo) of A
-constexpr int kAStageBytes = 2 * kAPartBytes;                 // hi + lo
+constexpr int kAStageBytes = kTileM * kC * 4;                 // 32 KB: 128 raw fp32 rows
 constexpr int kHeaderBytes = 256;                             // workspace header in front of the W image
 constexpr uint32_t kSpinLimit = 1u << 20;                     // watchdog: trap instead of hanging the GPU
 
@@ -157,6 +179,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes x 8 columns (16 bf16 per row, two per column)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_128B, rows of 128 bytes (64 bf16), 8-row groups
@@ -174,12 +218,12 @@ __host__ __device__ constexpr uint32_t umma_idesc(int n) {
 
 // Register re-balancing between warp groups (warps 0-3 epilogue, 4-7 producers): the kernel is
 // compiled for 128 registers/thread (416 threads); setmaxnreg moves registers WITHIN the CTA's
-// launch allocation (416 x 128 = 53248), so 128*232 (epilogue) + 128*56 (gatherers) + 128*88
-// (converters) + 32*128 (MMA warp) = 52224 must fit in it -- an over-subscribed inc never returns.
+// launch allocation (416 x 128 = 53248), so 128*200 (epilogue) + 128*120 (converters) + 128*56
+// (gatherers) + 32*128 (MMA warp) = 52224 must fit in it -- an over-subscribed inc never returns.
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
-// A stages that fit beside a filter slice of `cols` columns (1 KB alignment slack, barriers, epilogue params)
+// raw-ring stages that fit beside a filter slice of `cols` columns (1 KB alignment slack, barriers, epilogue params)
 __host__ __device__ constexpr int a_stages(int cols) {
   int n = (kSmemBudget - 1024 - 2 * cols * 128 - 2048) / kAStageBytes;
   return n > kMaxAStages ? kMaxAStages : n;
@@ -232,24 +276,24 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
   constexpr int COLS = NC * NCH;               // columns of W this CTA owns
   constexpr int CH = COLS / T;                 // output channels this CTA owns
   constexpr int CH_PER_LD = 16 / T;            // channels per 16-column TMEM load
-  constexpr int TMEM_COLS = (2 * NC) < 32 ? 32 : 2 * NC;
-  constexpr int NST = a_stages(COLS);          // A stages that fit beside the filter slice
-  static_assert(NC % 32 == 0 && NC <= 256 && 16 % T == 0 && CH <= 64 && NST >= 2, "unsupported shape");
+  constexpr int NST = a_stages(COLS);          // raw-ring stages that fit beside the filter slice
+  static_assert(NC % 16 == 0 && NC <= kAccCols && 16 % T == 0 && CH <= 64 && NST >= 2, "unsupported shape");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sB = smem;                                        // [2 parts][COLS rows][128 B]
-  uint8_t* sA = sB + 2 * COLS * 128;                         // [NST][2 parts][128 rows][128 B]
+  uint8_t* sB = smem;                                        // [2 parts][COLS rows][128 B]   UMMA K-major SW128
+  uint8_t* sA = sB + 2 * COLS * 128;                         // [NST][128 rows][256 B]        raw fp32 ring
   float* s_epi = reinterpret_cast<float*>(sA + NST * kAStageBytes);   // [3][64]: bias, BN scale, BN shift (16-byte aligned)
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + 3 * 64);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   const uint32_t bar0 = smem_u32(bars);
-  auto a_full = [&](uint32_t s) { return bar0 + 8u * s; };
-  auto a_empty = [&](uint32_t s) { return bar0 + 8u * (kMaxAStages + s); };
-  auto raw_full = [&](uint32_t s) { return bar0 + 8u * (2 * kMaxAStages + s); };
-  auto t_full = [&](uint32_t s) { return bar0 + 8u * (3 * kMaxAStages + s); };
-  auto t_empty = [&](uint32_t s) { return bar0 + 8u * (3 * kMaxAStages + 2 + s); };
-  const uint32_t w_full = bar0 + 8u * (3 * kMaxAStages + 4);
+  auto raw_full = [&](uint32_t s) { return bar0 + 8u * s; };
+  auto raw_empty = [&](uint32_t s) { return bar0 + 8u * (kMaxAStages + s); };
+  auto ta_full = [&](uint32_t s) { return bar0 + 8u * (2 * kMaxAStages + s); };
+  auto ta_empty = [&](uint32_t s) { return bar0 + 8u * (2 * kMaxAStages + kTA + s); };
+  auto t_full = [&](uint32_t s) { return bar0 + 8u * (2 * kMaxAStages + 2 * kTA + s); };
+  auto t_empty = [&](uint32_t s) { return bar0 + 8u * (2 * kMaxAStages + 2 * kTA + 2 + s); };
+  const uint32_t w_full = bar0 + 8u * (2 * kMaxAStages + 2 * kTA + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int split = blockIdx.x % S, worker = blockIdx.x / S;
@@ -267,9 +311,12 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
   // ---- one-time setup ---------------------------------------------------------------------
   if (tid == 0) {
     for (int s = 0; s < kMaxAStages; ++s) {
-      mbar_init(a_full(s), kConvWarps * 32);
-      mbar_init(a_empty(s), 1);
-      mbar_init(raw_full(s), kGatherWarps * 32);
+      mbar_init(raw_full(s), 128);                           // gather threads (cp.async arrive-on)
+      mbar_init(raw_empty(s), 128);                          // converter threads
+    }
+    for (int s = 0; s < kTA; ++s) {
+      mbar_init(ta_full(s), 128);                            // converter threads
+      mbar_init(ta_empty(s), 1);                             // tcgen05.commit
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(t_full(s), 1);
@@ -278,7 +325,7 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     mbar_init(w_full, 1);
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), 512);
   if (tid < CH) {                                             // absent bias / BN: exact identities (+0, *1, +0)
     s_epi[tid] = p.bias ? p.bias[ch0 + tid] : 0.f;
     s_epi[CH + tid] = p.scale ? p.scale[ch0 + tid] : 1.f;
@@ -293,7 +340,7 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     // =====================================================================================
     // EPILOGUE: thread r owns destination row (tile*128 + r) and TMEM lane r
     // =====================================================================================
-    reg_inc<232>();
+    reg_inc<200>();
     const int r = tid;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const int64_t et_st = (int64_t)p.M * p.K;                // stride between edge types
@@ -316,6 +363,9 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     };
     fetch(worker, 0);
     uint32_t ct = 0;
+#ifdef FGNN_TC_TRACE
+    uint32_t ei = 0;
+#endif
     for (int tile = worker; tile < n_tiles; tile += n_workers) {
       const uint32_t g = (uint32_t)tile * kTileM + r;
       const bool valid = g < rows_total;
@@ -338,7 +388,10 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
           const uint32_t st = ct & 1;
           mbar_wait(t_full(st), (ct >> 1) & 1);
           tc_fence_after();
-          const uint32_t taddr = lane_addr + st * NC;
+#ifdef FGNN_TC_TRACE
+          if (chunk == 0 && warp == 0) TC_TRACE(ei, 6);
+#endif
+          const uint32_t taddr = lane_addr + st * kAccCols;
           uint32_t d[2][16];
           tmem_ld16(taddr, d[0]);
 #pragma unroll
@@ -381,6 +434,10 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
           mbar_arrive(t_empty(st));
           ++ct;
         }
+#ifdef FGNN_TC_TRACE
+        if (warp == 0) TC_TRACE(ei, 7);
+        ++ei;
+#endif
         live_count += live ? 1.f : 0.f;
       }
       // finish: aggregate, bias / eval-BN / activation (mp_nn.py:162-173), store this row's channels
@@ -417,12 +474,49 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
         }
       }
     }
-  } else if (warp < kEpiWarps + kGatherWarps) {
+  } else if (warp < kEpiWarps + kConvWarps) {
     // =====================================================================================
-    // GATHERERS: cp.async the 128 source rows of every item into its A stage (raw fp32 chunks)
+    // CONVERTERS: thread cr == TMEM lane cr == row cr of every item.  raw fp32 row (ring) ->
+    // split bf16 -> A stage in tensor memory (32 columns of hi pairs, 32 columns of lo pairs)
+    // =====================================================================================
+    reg_dec<120>();
+    const int cr = tid - kEpiWarps * 32;
+    const uint32_t row_u = smem_u32(sA) + (uint32_t)cr * 256u;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTACol0;
+    for (uint32_t i = 0; i < n_items; ++i) {
+      const uint32_t st = i % NST, use = i / NST;
+      const uint32_t ta = i % kTA, tuse = i / kTA;
+      mbar_wait(raw_full(st), use & 1);
+      if (cr < 32) TC_TRACE(i, 2);
+      float4 v[16];                                          // channels 4c .. 4c+3 in chunk c (stored at c ^ (row & 15))
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] = lds_f4(row_u + st * kAStageBytes + (uint32_t)((c ^ (cr & 15)) * 16));
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[c].x, v[c].y), h1 = __floats2bfloat162_rn(v[c].z, v[c].w);
+        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+        hi[2 * c] = pack_bf16(h0);
+        hi[2 * c + 1] = pack_bf16(h1);
+        lo[2 * c] = pack_bf16(__floats2bfloat162_rn(v[c].x - f0.x, v[c].y - f0.y));
+        lo[2 * c + 1] = pack_bf16(__floats2bfloat162_rn(v[c].z - f1.x, v[c].w - f1.y));
+      }
+      mbar_arrive(raw_empty(st));                            // ring stage is free again: every chunk has been consumed above
+      mbar_wait(ta_empty(ta), (tuse & 1) ^ 1);
+      tc_fence_after();
+      tmem_st32(lane_addr + ta * kTACols, hi);
+      tmem_st32(lane_addr + ta * kTACols + 32, lo);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(ta_full(ta));
+      if (cr < 32) TC_TRACE(i, 3);
+    }
+  } else if (warp < kMmaWarp) {
+    // =====================================================================================
+    // GATHERERS: cp.async the 128 source rows of every item into the raw ring
     // =====================================================================================
     reg_dec<56>();
-    const int pw = warp - kEpiWarps;                         // rows pw*32 .. pw*32+31 of the tile
+    const int pw = warp - (kEpiWarps + kConvWarps);          // rows pw*32 .. pw*32+31 of the tile
     const int sub = lane >> 4, q = lane & 15;                // 16 lanes x 16 B = one 256-byte row
     // index-table entry of the row this lane owns (row pw*32+lane of item i's tile); the load is
     // issued one item ahead and only CONSUMED (range check -> source row) after the stage wait
@@ -439,67 +533,30 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     };
     const float* xq = p.x + q * 4;
     const uint32_t sA_u = smem_u32(sA);
-    // raw chunk q (floats 4q..4q+3) of a row lands at bf16 chunk q/2 of the hi (q even) / lo (q odd) image
-    const uint32_t part_off = (uint32_t)(q & 1) * kAPartBytes;
     int32_t base, base_next;
     int64_t n = index_of(0, base);
     for (uint32_t i = 0; i < n_items; ++i) {
       const uint32_t st = i % NST, use = i / NST;
       const int64_t n_next = index_of(i + 1, base_next);     // index load of the next item: in flight during this one
-      mbar_wait(a_empty(st), (use & 1) ^ 1);
+      mbar_wait(raw_empty(st), (use & 1) ^ 1);
+      if (pw == 0) TC_TRACE(i, 0);
       // source row (b*N + n; x is batch-contiguous, checked by tc_supported); -1 = no row (tile tail,
       // masked or out-of-range slot) -> zero-filled
       const int32_t src = (base >= 0 && n >= 0 && n < p.N) ? base + (int32_t)n : -1;
-      const uint32_t stage = sA_u + st * kAStageBytes + part_off;
+      const uint32_t stage = sA_u + st * kAStageBytes;
 #pragma unroll
       for (int it = 0; it < 16; ++it) {
         const int rw = 2 * it + sub;
         const int32_t row = __shfl_sync(0xffffffffu, src, rw);
         const int rr = pw * 32 + rw;
-        const uint32_t dst = stage + (uint32_t)(rr >> 3) * 1024u + (uint32_t)(rr & 7) * 128u +
-                             (uint32_t)(((q >> 1) ^ (rr & 7)) * 16);
+        // chunk q of row rr at position q ^ (rr & 15): the converter's per-row reads are conflict-free
+        const uint32_t dst = stage + (uint32_t)rr * 256u + (uint32_t)((q ^ (rr & 15)) * 16);
         cp_async16(dst, xq + (int64_t)(row >= 0 ? row : 0) * kC, row >= 0 ? 16u : 0u);
       }
       cp_async_arrive_noinc(raw_full(st));
+      if (pw == 0) TC_TRACE(i, 1);
       n = n_next;
       base = base_next;
-    }
-  } else if (warp < kMmaWarp) {
-    // =====================================================================================
-    // CONVERTERS: raw fp32 -> split bf16, in place (thread-local: two 16-byte chunks in, two out)
-    // =====================================================================================
-    reg_dec<88>();
-    const int cr = tid - (kEpiWarps + kGatherWarps) * 32;    // row of the tile this thread converts
-    const uint32_t row_u = smem_u32(sA) + (uint32_t)(cr >> 3) * 1024u + (uint32_t)(cr & 7) * 128u;
-    for (uint32_t i = 0; i < n_items; ++i) {
-      const uint32_t st = i % NST, use = i / NST;
-      mbar_wait(raw_full(st), use & 1);
-      const uint32_t hi = row_u + st * kAStageBytes, lo = hi + kAPartBytes;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {                 // 8 loads in flight, then 8 stores
-        float4 a[4], c[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const uint32_t o = (uint32_t)(((half * 4 + jj) ^ (cr & 7)) * 16);
-          a[jj] = lds_f4(hi + o);                            // channels 8j .. 8j+3
-          c[jj] = lds_f4(lo + o);                            // channels 8j+4 .. 8j+7
-        }
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const uint32_t o = (uint32_t)(((half * 4 + jj) ^ (cr & 7)) * 16);
-          const __nv_bfloat162 h0 = __floats2bfloat162_rn(a[jj].x, a[jj].y), h1 = __floats2bfloat162_rn(a[jj].z, a[jj].w);
-          const __nv_bfloat162 h2 = __floats2bfloat162_rn(c[jj].x, c[jj].y), h3 = __floats2bfloat162_rn(c[jj].z, c[jj].w);
-          const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-          const float2 f2 = __bfloat1622float2(h2), f3 = __bfloat1622float2(h3);
-          sts_u4(hi + o, pack_bf16(h0), pack_bf16(h1), pack_bf16(h2), pack_bf16(h3));
-          sts_u4(lo + o, pack_bf16(__floats2bfloat162_rn(a[jj].x - f0.x, a[jj].y - f0.y)),
-                 pack_bf16(__floats2bfloat162_rn(a[jj].z - f1.x, a[jj].w - f1.y)),
-                 pack_bf16(__floats2bfloat162_rn(c[jj].x - f2.x, c[jj].y - f2.y)),
-                 pack_bf16(__floats2bfloat162_rn(c[jj].z - f3.x, c[jj].w - f3.y)));
-        }
-      }
-      fence_proxy_async();                                   // generic-proxy stores -> visible to the MMA (async proxy)
-      mbar_arrive(a_full(st));
     }
   } else {
     // =====================================================================================
@@ -507,7 +564,7 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     // descriptors live in uniform registers); one elected lane issues.  First: the stationary
     // B operand (this CTA's column slice of the split-bf16 filter image) by TMA bulk copy.
     // =====================================================================================
-    const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+    const uint32_t sB_u = smem_u32(sB);
     if (elect_one()) {
       const int OT = p.O * p.T;
       constexpr uint32_t part = COLS * 128, piece = part < 32768u ? part : 32768u;
@@ -520,19 +577,20 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     __syncwarp();
     mbar_wait(w_full, 0);
     constexpr uint32_t idesc = umma_idesc(NC);
-    // descriptor of a tile = constant high word + (address >> 4) in the low word
+    // descriptor of a B tile = constant high word + (address >> 4) in the low word
     const uint64_t desc_hi = umma_desc_sw128(0);
     uint32_t ct = 0;
     for (uint32_t i = 0; i < n_items; ++i) {
-      const uint32_t st = i % NST, use = i / NST;
-      mbar_wait(a_full(st), use & 1);
-      const uint32_t a_hi = (sA_u + st * kAStageBytes) >> 4, a_lo = a_hi + (kAPartBytes >> 4);
+      const uint32_t ta = i % kTA, tuse = i / kTA;
+      mbar_wait(ta_full(ta), tuse & 1);
+      TC_TRACE(i, 4);
+      const uint32_t a_hi = tmem_base + kTACol0 + ta * kTACols, a_lo = a_hi + 32;
 #pragma unroll
       for (int chunk = 0; chunk < NCH; ++chunk) {
         const uint32_t ts = ct & 1;
         mbar_wait(t_empty(ts), ((ct >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + ts * NC;
+        const uint32_t d_tmem = tmem_base + ts * kAccCols;
         const uint32_t b_hi = (sB_u + (uint32_t)chunk * NC * 128u) >> 4, b_lo = b_hi + ((uint32_t)COLS * 128u >> 4);
         if (elect_one()) {
 #pragma unroll
@@ -540,16 +598,16 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
             const uint32_t a = term == 0 ? a_lo : a_hi;
             const uint32_t bb = term == 1 ? b_lo : b_hi;
 #pragma unroll
-            for (int ks = 0; ks < kC / 16; ++ks)
-              umma_bf16(d_tmem, desc_hi | (uint64_t)(a + ks * 2), desc_hi | (uint64_t)(bb + ks * 2), idesc,
-                        (term | ks) != 0);
+            for (int ks = 0; ks < kC / 16; ++ks)             // 16 bf16 of K = 8 TMEM columns of A = 32 bytes of a B row
+              umma_bf16_ts(d_tmem, a + ks * 8, desc_hi | (uint64_t)(bb + ks * 2), idesc, (term | ks) != 0);
           }
           umma_commit(t_full(ts));                           // accumulator ready when these MMAs retire
-          if (chunk == NCH - 1) umma_commit(a_empty(st));    // A stage reusable when its readers retire
+          if (chunk == NCH - 1) umma_commit(ta_empty(ta));   // A stage reusable when its readers retire
         }
         __syncwarp();
         ++ct;
       }
+      TC_TRACE(i, 5);
     }
   }
 
@@ -558,7 +616,7 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
   __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -573,14 +631,15 @@ struct TcConfig {
 };
 
 TcConfig pick_config(int T, int agg, int OT) {
+  // accumulator chunks of NC <= 128 columns (TMEM: 2 x 128 accumulator + 4 x 64 A-stage columns);
   // channels per CTA (NC*NCH/T) <= 64 for max/mean, <= 32 for softmax (two registers per channel)
   const bool sm = agg == FGNN_AGG_SOFTMAX;
-  TcConfig c{T, 0, 1, false};
+  TcConfig c{T, 128, 1, false};
   switch (T) {
-    case 16: c.NC = 256; c.NCH = 2; break;
-    case 8: c.NC = 256; c.NCH = 1; break;
-    case 4: c.NC = sm ? 128 : 256; break;
-    case 2: c.NC = sm ? 64 : 128; break;
+    case 16: c.NCH = sm ? 2 : 4; break;          // 16 / 32 channels
+    case 8: c.NCH = 2; break;                    // 32 channels
+    case 4: c.NCH = sm ? 1 : 2; break;           // 32 / 64 channels
+    case 2: c.NCH = 1; c.NC = sm ? 64 : 128; break;
     case 1: c.NC = sm ? 32 : 64; break;
     default: return c;
   }
@@ -594,24 +653,34 @@ size_t smem_bytes(const TcConfig& c) {
          3 * 64 * 4;
 }
 
-template <int T, int NC, int NCH>
+template <int T, int NC, int NCH, int AGG>
+int launch_one(const MpParams& p, const uint8_t* wimg, int S, int workers, int tiles, size_t smem, cudaStream_t st) {
+  auto kern = mp_tc_kernel<T, NC, NCH, AGG>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return FGNN_ERR_CUDA;
+  kern<<<S * workers, tc::kThreads, smem, st>>>(p, wimg, S, workers, tiles);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? (int)FGNN_OK : (int)FGNN_ERR_CUDA;
+}
+
+// NCm/NCHm: max & mean configuration, NCs/NCHs: softmax configuration (must mirror pick_config)
+template <int T, int NCm, int NCHm, int NCs, int NCHs>
 int launch_agg(const MpParams& p, const uint8_t* wimg, int S, int workers, int tiles, size_t smem, cudaStream_t st) {
-  auto go = [&](auto kern) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return (int)FGNN_ERR_CUDA;
-    kern<<<S * workers, tc::kThreads, smem, st>>>(p, wimg, S, workers, tiles);
-    count_launch();
-    return cudaGetLastError() == cudaSuccess ? (int)FGNN_OK : (int)FGNN_ERR_CUDA;
-  };
   switch (p.agg) {
-    case FGNN_AGG_MAX: return go(mp_tc_kernel<T, NC, NCH, FGNN_AGG_MAX>);
-    case FGNN_AGG_SOFTMAX: return go(mp_tc_kernel<T, (NC > 32 ? NC / 2 : NC), NCH, FGNN_AGG_SOFTMAX>);
-    case FGNN_AGG_MEAN: return go(mp_tc_kernel<T, NC, NCH, FGNN_AGG_MEAN>);
+    case FGNN_AGG_MAX: return launch_one<T, NCm, NCHm, FGNN_AGG_MAX>(p, wimg, S, workers, tiles, smem, st);
+    case FGNN_AGG_SOFTMAX: return launch_one<T, NCs, NCHs, FGNN_AGG_SOFTMAX>(p, wimg, S, workers, tiles, smem, st);
+    case FGNN_AGG_MEAN: return launch_one<T, NCm, NCHm, FGNN_AGG_MEAN>(p, wimg, S, workers, tiles, smem, st);
   }
   return FGNN_ERR_UNSUPPORTED;
 }
 
 }  // namespace
+
+#ifdef FGNN_TC_TRACE
+extern "C" int fgnn_debug_trace_read(unsigned long long* host, size_t count) {
+  return cudaMemcpyFromSymbol(host, g_trace, count * sizeof(unsigned long long)) == cudaSuccess ? 0 : -6;
+}
+#endif
 
 bool tc_supported(const fgnn_mp_args* a) {
   if (a->extension != FGNN_NO_EXTENSION || a->dtype != FGNN_F32) return false;
@@ -653,22 +722,17 @@ int launch_mp_tc(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream) 
   }
   const int64_t rows = (int64_t)p.B * p.M;
   const int tiles = (int)((rows + tc::kTileM - 1) / tc::kTileM);
-  // softmax halves NC for T in {16,8} (see launch_agg), so its column split doubles
-  int nc_eff = c.NC;
-  if (p.agg == FGNN_AGG_SOFTMAX && (p.T == 16 || p.T == 8)) nc_eff = c.NC / 2;
-  const int S = OT / (nc_eff * c.NCH);
+  const int S = OT / (c.NC * c.NCH);
   if (S > num_sms) return FGNN_ERR_UNSUPPORTED;
   int workers = num_sms / S;
   if (workers > tiles) workers = tiles;
-  TcConfig ce = c;
-  ce.NC = nc_eff;
-  const size_t smem = smem_bytes(ce);
+  const size_t smem = smem_bytes(c);
   switch (p.T) {
-    case 16: return launch_agg<16, 256, 2>(p, ws, S, workers, tiles, smem, stream);
-    case 8: return launch_agg<8, 256, 1>(p, ws, S, workers, tiles, smem, stream);
-    case 4: return launch_agg<4, 256, 1>(p, ws, S, workers, tiles, smem, stream);
-    case 2: return launch_agg<2, 128, 1>(p, ws, S, workers, tiles, smem, stream);
-    case 1: return launch_agg<1, 64, 1>(p, ws, S, workers, tiles, smem, stream);
+    case 16: return launch_agg<16, 128, 4, 128, 2>(p, ws, S, workers, tiles, smem, stream);
+    case 8: return launch_agg<8, 128, 2, 128, 2>(p, ws, S, workers, tiles, smem, stream);
+    case 4: return launch_agg<4, 128, 2, 128, 1>(p, ws, S, workers, tiles, smem, stream);
+    case 2: return launch_agg<2, 128, 1, 64, 1>(p, ws, S, workers, tiles, smem, stream);
+    case 1: return launch_agg<1, 64, 1, 32, 1>(p, ws, S, workers, tiles, smem, stream);
   }
   return FGNN_ERR_UNSUPPORTED;
 }
