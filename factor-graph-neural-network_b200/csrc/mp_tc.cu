@@ -45,13 +45,13 @@ namespace fgnn {
 
 #ifdef FGNN_TC_TRACE
 // Debug builds only (-DFGNN_TC_TRACE): per-item timestamps of CTA 0, read back by tools/tc_trace.py.
-__device__ unsigned long long g_trace[8 * 4096];
+__device__ unsigned long long g_trace[16 * 4096];
 #define TC_TRACE(item, slot)                                                                    \
   do {                                                                                          \
     if (blockIdx.x == 0 && (item) < 4096u && (threadIdx.x & 31) == 0) {                         \
       unsigned long long _t;                                                                    \
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                                    \
-      g_trace[(item) * 8 + (slot)] = _t;                                                        \
+      g_trace[(item) * 16 + (slot)] = _t;                                                       \
     }                                                                                           \
   } while (0)
 #else
@@ -223,9 +223,10 @@ __host__ __device__ constexpr uint32_t umma_idesc(int n) {
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
-// raw-ring stages that fit beside a filter slice of `cols` columns (1 KB alignment slack, barriers, epilogue params)
-__host__ __device__ constexpr int a_stages(int cols) {
-  int n = (kSmemBudget - 1024 - 2 * cols * 128 - 2048) / kAStageBytes;
+// raw-ring stages that fit beside a filter slice of `cols` columns and the output staging tile of `ch`
+// channels (plus 1 KB alignment slack, barriers, epilogue params)
+__host__ __device__ constexpr int a_stages(int cols, int ch) {
+  int n = (kSmemBudget - 1024 - 2 * cols * 128 - kTileM * ch * 4 - 2048) / kAStageBytes;
   return n > kMaxAStages ? kMaxAStages : n;
 }
 
@@ -276,14 +277,16 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
   constexpr int COLS = NC * NCH;               // columns of W this CTA owns
   constexpr int CH = COLS / T;                 // output channels this CTA owns
   constexpr int CH_PER_LD = 16 / T;            // channels per 16-column TMEM load
-  constexpr int NST = a_stages(COLS);          // raw-ring stages that fit beside the filter slice
+  constexpr int NST = a_stages(COLS, CH);      // raw-ring stages that fit beside the filter slice and the output tile
   static_assert(NC % 16 == 0 && NC <= kAccCols && 16 % T == 0 && CH <= 64 && NST >= 2, "unsupported shape");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by OFFSET (not by integer round-trip) so the compiler keeps the shared state space
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sB = smem;                                        // [2 parts][COLS rows][128 B]   UMMA K-major SW128
   uint8_t* sA = sB + 2 * COLS * 128;                         // [NST][128 rows][256 B]        raw fp32 ring
-  float* s_epi = reinterpret_cast<float*>(sA + NST * kAStageBytes);   // [3][64]: bias, BN scale, BN shift (16-byte aligned)
+  uint8_t* sOut = sA + NST * kAStageBytes;                   // [4 warps][32 rows][CH floats]  output staging (swizzled chunks)
+  float* s_epi = reinterpret_cast<float*>(sOut + kTileM * CH * 4);    // [3][64]: bias, BN scale, BN shift (16-byte aligned)
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + 3 * 64);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   const uint32_t bar0 = smem_u32(bars);
@@ -367,8 +370,6 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     uint32_t ei = 0;
 #endif
     for (int tile = worker; tile < n_tiles; tile += n_workers) {
-      const uint32_t g = (uint32_t)tile * kTileM + r;
-      const bool valid = g < rows_total;
       float acc[CH];                                         // max | running max of gamma*e | sum
       float acc2[AGG == FGNN_AGG_SOFTMAX ? CH : 1];          // softmax: running sum of exp
       float live_count = 0.f;
@@ -440,18 +441,23 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
 #endif
         live_count += live ? 1.f : 0.f;
       }
-      // finish: aggregate, bias / eval-BN / activation (mp_nn.py:162-173), store this row's channels
-      if (valid) {
-        uint32_t b, m;
-        split_row(g, b, m);
-        float* orow = p.out + (int64_t)b * p.o_sb + (int64_t)m * p.o_sm + ch0;
-        const uint32_t epi_u = smem_u32(s_epi);
+      // finish: aggregate, bias / eval-BN / activation (mp_nn.py:162-173) into this warp's staging
+      // rows (16-byte chunk c of row rr at position c ^ (rr & SW): conflict-free both ways) ...
+      {
+        constexpr int CPR = CH / 4;                          // 16-byte chunks per output row
+        constexpr int SW = (CPR < 8 ? CPR : 8) - 1;          // chunk-index bits XOR-ed with the row
+        float4* stage = reinterpret_cast<float4*>(sOut) + warp * (32 * CPR);   // this warp's [32 rows][CPR chunks]
+        const float4* epi4 = reinterpret_cast<const float4*>(s_epi);
         const float inv_gamma = 1.f / p.gamma, inv_live = live_count > 0.f ? 1.f / live_count : 0.f;
         // negative-side slope of the activation: 1 = none, 0 = ReLU, slope = LeakyReLU
         const float neg = p.act == FGNN_ACT_NONE ? 1.f : (p.act == FGNN_ACT_RELU ? 0.f : p.slope);
+        __syncwarp();                                        // previous tile's read-back is complete
+#ifdef FGNN_TC_TRACE
+        if (warp == 0) TC_TRACE(ei - 1, 8);
+#endif
 #pragma unroll
         for (int c4 = 0; c4 < CH; c4 += 4) {
-          const float4 bi = lds_f4(epi_u + c4 * 4), sc = lds_f4(epi_u + (CH + c4) * 4), sh = lds_f4(epi_u + (2 * CH + c4) * 4);
+          const float4 bi = epi4[c4 >> 2], sc = epi4[(CH + c4) >> 2], sh = epi4[(2 * CH + c4) >> 2];
           const float bia[4] = {bi.x, bi.y, bi.z, bi.w}, sca[4] = {sc.x, sc.y, sc.z, sc.w}, shi[4] = {sh.x, sh.y, sh.z, sh.w};
           float v[4];
 #pragma unroll
@@ -465,13 +471,34 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
             y = y >= 0.f ? y : y * neg;
             v[j] = a == -INFINITY ? a : y;                   // no live slot on this shard: stay -inf
           }
-          float4* dst = reinterpret_cast<float4*>(orow + c4);
-          if (p.accumulate) {
-            const float4 old = *dst;
-            v[0] += old.x; v[1] += old.y; v[2] += old.z; v[3] += old.w;
-          }
-          *dst = make_float4(v[0], v[1], v[2], v[3]);
+          stage[lane * CPR + (((c4 >> 2) & ~SW) | (((c4 >> 2) ^ lane) & SW))] = make_float4(v[0], v[1], v[2], v[3]);
         }
+        __syncwarp();
+#ifdef FGNN_TC_TRACE
+        if (warp == 0) TC_TRACE(ei - 1, 9);
+#endif
+        // ... then whole 128-byte lines go out: CPR lanes per row, 32/CPR rows per store instruction
+        // (out is batch-contiguous node-major, so flattened row g lives at out + g * o_sm)
+        constexpr int RPI = 32 / CPR;
+        const int cq = lane % CPR, rsub = lane / CPR;
+        const uint32_t g0 = (uint32_t)tile * kTileM + warp * 32;
+        float* obase = p.out + (int64_t)g0 * p.o_sm + ch0 + cq * 4;
+#pragma unroll
+        for (int it = 0; it < CPR; ++it) {
+          const int rr = it * RPI + rsub;
+          if (g0 + rr < rows_total) {
+            float4 v = stage[rr * CPR + ((cq & ~SW) | ((cq ^ rr) & SW))];
+            float4* dst = reinterpret_cast<float4*>(obase + (int64_t)rr * p.o_sm);
+            if (p.accumulate) {
+              const float4 old = *dst;
+              v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+            }
+            *dst = v;
+          }
+        }
+#ifdef FGNN_TC_TRACE
+        if (warp == 0) TC_TRACE(ei - 1, 10);
+#endif
       }
     }
   } else if (warp < kEpiWarps + kConvWarps) {
@@ -648,9 +675,9 @@ TcConfig pick_config(int T, int agg, int OT) {
 }
 
 size_t smem_bytes(const TcConfig& c) {
-  const int cols = c.NC * c.NCH;
-  return 1024 + (size_t)2 * cols * 128 + (size_t)tc::a_stages(cols) * tc::kAStageBytes + tc::kNumBars * 8 + 16 +
-         3 * 64 * 4;
+  const int cols = c.NC * c.NCH, ch = cols / c.T;
+  return 1024 + (size_t)2 * cols * 128 + (size_t)tc::a_stages(cols, ch) * tc::kAStageBytes +
+         (size_t)tc::kTileM * ch * 4 + tc::kNumBars * 8 + 16 + 3 * 64 * 4;
 }
 
 template <int T, int NC, int NCH, int AGG>
@@ -690,11 +717,12 @@ bool tc_supported(const fgnn_mp_args* a) {
   if (a->B > 1 && a->x_sb != (int64_t)a->N * a->C) return false;                  // batch-contiguous
   if ((int64_t)a->B * a->N >= INT32_MAX) return false;
   if ((reinterpret_cast<uintptr_t>(a->x) & 15) || (reinterpret_cast<uintptr_t>(a->out) & 15)) return false;
-  if (a->out_so != 1 || (a->out_sm & 3) || (a->out_sb & 3)) return false;
+  if (a->out_so != 1 || (a->out_sm & 3)) return false;
+  if (a->B > 1 && a->out_sb != (int64_t)a->M * a->out_sm) return false;             // batch-contiguous rows
   if (a->O % 4) return false;
   const TcConfig c = pick_config(a->T, a->aggregator, a->O * a->T);
   if (!c.ok) return false;
-  if (smem_bytes(c) > (size_t)tc::kSmemBudget || tc::a_stages(c.NC * c.NCH) < 2) return false;
+  if (smem_bytes(c) > (size_t)tc::kSmemBudget || tc::a_stages(c.NC * c.NCH, c.NC * c.NCH / c.T) < 2) return false;
   if ((int64_t)a->B * a->M >= (int64_t)INT32_MAX - 256) return false;
   return true;
 }

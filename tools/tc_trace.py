@@ -33,15 +33,15 @@ for _ in range(3):
                          out=out, workspace=ws, filters_version=7)
 torch.cuda.synchronize()
 lib = ctypes.CDLL(_lib.LIB_PATH)
-n = 8 * 4096
+n = 16 * 4096
 buf = np.zeros(n, dtype=np.uint64)
 assert lib.fgnn_debug_trace_read(buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n)) == 0
-tr = buf.reshape(4096, 8).astype(np.int64)
+tr = buf.reshape(4096, 16).astype(np.int64)[:, :11]
 items = int((tr[:, 4] > 0).sum())
 tr = tr[:items]
 t0 = tr[tr > 0].min()
 tr = np.where(tr > 0, tr - t0, -1)
-names = ["g_free", "g_issued", "c_landed", "c_done", "m_ready", "m_issued", "e_ready", "e_done"]
+names = ["g_free", "g_issued", "c_landed", "c_done", "m_ready", "m_issued", "e_ready", "e_done", "f_start", "f_staged", "f_stored"]
 print(f"T={T} K={K}: {items} items in CTA 0, span {tr.max() / 1e3:.1f} us -> {tr.max() / items:.0f} ns / item")
 print("item " + " ".join(f"{n:>9s}" for n in names))
 for i in list(range(0, min(items, 14))) + list(range(max(14, items - 6), items)):
@@ -52,3 +52,5 @@ print(f"median ns: stage free->copies issued {d(0,1):.0f} | issued->landed {d(1,
       f"epilogue item {d(6,7):.0f}")
 per = np.diff(tr[4:-2], axis=0)
 print("median item-to-item interval per slot (ns):", " ".join(f"{np.median(per[:, s]):.0f}" for s in range(8)))
+fin = tr[(tr[:, 8] >= 0) & (tr[:, 10] >= 0)]
+print(f"finish phase (per tile): stage {np.median(fin[:, 9] - fin[:, 8]):.0f} ns, store {np.median(fin[:, 10] - fin[:, 9]):.0f} ns; e_done->f_start {np.median(fin[:, 8] - fin[:, 7]):.0f} ns")
