@@ -272,12 +272,6 @@ def run_native(args):
     bytes_layer = algorithmic_bytes_per_layer(args, types)
     J, L, C = len(types), args.layers, args.dim
 
-    if world > 1:
-        from fgnn_b200 import parallel
-        plan = parallel.ShardedLayerPlan(types, rank, world, dev)
-    else:
-        plan = None
-
     def to_dev(a, pin=False):
         t = torch.from_numpy(np.ascontiguousarray(a))
         return t.pin_memory() if pin else t.to(dev)
@@ -289,17 +283,29 @@ def run_native(args):
            for d in ("v2f", "f2v")} for j in range(J)] for l in range(L)]
     ws = [[{d: torch.zeros(C * C * args.edge_types * 4 + 4096, dtype=torch.uint8, device=dev) for d in ("v2f", "f2v")}
            for j in range(J)] for l in range(L)]
+    for l in range(L):
+        for j in range(J):
+            ws[l][j]["ver_v2f"], ws[l][j]["ver_f2v"] = 1 + l * 16 + j * 2, 2 + l * 16 + j * 2
     d_in = dict(x_v=to_dev(inp["x_v"]), x_f=[to_dev(a) for a in inp["x_f"]],
                 et_v2f=[to_dev(a) for a in inp["et_v2f"]], et_f2v=[to_dev(a) for a in inp["et_f2v"]],
                 idx_v2f=[to_dev(a) for a in inp["idx_v2f"]], idx_f2v=[to_dev(a) for a in inp["idx_f2v"]])
+    if world > 1:
+        # factor-sharded: this rank keeps its factor ranges, the compacted F->V tables and their edge types
+        from fgnn_b200 import parallel
+        plan = parallel.ShardedLayerPlan(types, rank, world, dev)
+        d_in["x_f"] = plan.local_factor_features(d_in["x_f"])
+        d_in["et_v2f"], d_in["et_f2v"] = plan.local_etypes(d_in["et_v2f"], d_in["et_f2v"])
+        d_in["idx_v2f"] = d_in["idx_f2v"] = None
+    else:
+        plan = None
     # ping-pong feature buffers, node-major
     buf_v = [torch.empty_like(d_in["x_v"]) for _ in range(2)]
     buf_f = [[torch.empty_like(x) for x in d_in["x_f"]] for _ in range(2)]
 
-    def call(x, idx, et, w, out, accumulate, wsb, l, j, d):
+    def call(x, idx, et, w, out, accumulate, wsb, ver):
         fgnn_b200.mp_forward(nm(x), idx, et, w["filters"], w["bias"], w["scale"], w["shift"], extension=0,
                              aggregator=_lib.AGG_MAX, activation=_lib.ACT_RELU, kernel=kernel, out=nm(out),
-                             accumulate=accumulate, workspace=wsb, filters_version=1 + l * 16 + j * 2 + (d == "f2v"))
+                             accumulate=accumulate, workspace=wsb, filters_version=ver)
 
     def step(src):
         """src: dict of device tensors (x_v, x_f, tables).  Returns the final variable features."""
@@ -307,11 +313,11 @@ def run_native(args):
         for l in range(L):
             nv, nf = buf_v[l & 1], buf_f[l & 1]
             if plan is not None:
-                plan.layer(l, x_v, x_f, src, W[l], nv, nf, kernel)
+                plan.layer(x_v, x_f, src["et_v2f"], src["et_f2v"], W[l], nv, nf, kernel, ws[l])
             else:
                 for j in range(J):
-                    call(x_v, src["idx_v2f"][j], src["et_v2f"][j], W[l][j]["v2f"], nf[j], False, ws[l][j]["v2f"], l, j, "v2f")
-                    call(x_f[j], src["idx_f2v"][j], src["et_f2v"][j], W[l][j]["f2v"], nv, j > 0, ws[l][j]["f2v"], l, j, "f2v")
+                    call(x_v, src["idx_v2f"][j], src["et_v2f"][j], W[l][j]["v2f"], nf[j], False, ws[l][j]["v2f"], ws[l][j]["ver_v2f"])
+                    call(x_f[j], src["idx_f2v"][j], src["et_f2v"][j], W[l][j]["f2v"], nv, j > 0, ws[l][j]["f2v"], ws[l][j]["ver_f2v"])
             x_v, x_f = nv, nf
         return x_v
 
@@ -347,7 +353,7 @@ def run_native(args):
 
     # ---- end to end through the module API with host buffers --------------------------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and world == 1:
         mods = []
         for l in range(L):
             row = []

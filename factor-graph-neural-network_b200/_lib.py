@@ -40,6 +40,7 @@ class MpArgs(ctypes.Structure):
         ("dtype", ctypes.c_int32), ("idx_dtype", ctypes.c_int32), ("kernel", ctypes.c_int32),
         ("flags", ctypes.c_uint32), ("gamma", ctypes.c_float), ("act_slope", ctypes.c_float),
         ("filters_version", ctypes.c_int64),
+        ("tile_slots", ctypes.c_void_p), ("out_rows", ctypes.c_void_p),
     ]
 
 

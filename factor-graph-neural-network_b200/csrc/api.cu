@@ -36,6 +36,7 @@ static int validate(const fgnn_mp_args* a) {
   if ((a->bn_scale == nullptr) != (a->bn_shift == nullptr)) return FGNN_ERR_INVALID_ARG;
   if (a->extension != FGNN_NO_EXTENSION && a->M != a->N) return FGNN_ERR_SHAPE;  // mp_nn.py:136-159
   if ((a->flags & FGNN_FLAG_ACCUMULATE) && a->aggregator == FGNN_AGG_NONE) return FGNN_ERR_INVALID_ARG;
+  if ((a->tile_slots || a->out_rows) && a->aggregator == FGNN_AGG_NONE) return FGNN_ERR_INVALID_ARG;
   return FGNN_OK;
 }
 
@@ -49,6 +50,8 @@ static MpParams to_params(const fgnn_mp_args* a) {
   p.scale = a->bn_scale;
   p.shift = a->bn_shift;
   p.out = reinterpret_cast<float*>(a->out);
+  p.tile_k = a->tile_slots;
+  p.out_rows = a->out_rows;
   p.x_sb = a->x_sb; p.x_sc = a->x_sc; p.x_sn = a->x_sn;
   p.idx_sb = a->idx_sb; p.et_sb = a->et_sb;
   p.o_sb = a->out_sb; p.o_so = a->out_so; p.o_sm = a->out_sm; p.o_sk = a->out_sk;
@@ -271,6 +274,7 @@ int fgnn_mp_forward_host(const fgnn_mp_args* h) {
     d.out = dout;
     d.out_sb = (int64_t)h->O * h->M * Kout; d.out_so = (int64_t)h->M * Kout; d.out_sm = Kout; d.out_sk = 1;
     d.filters_version = 0;
+    d.tile_slots = nullptr; d.out_rows = nullptr;
     d.workspace = nullptr; d.workspace_bytes = 0;
     const size_t ws = fgnn_mp_workspace_bytes(&d);
     if (ws) { HCHK(cudaMalloc(&dws, ws)); d.workspace = dws; d.workspace_bytes = ws; }

@@ -17,6 +17,8 @@ struct MpParams {
   const float* scale;  // folded eval-BN or nullptr
   const float* shift;
   float* out;
+  const int32_t* tile_k;    // optional per-128-row-tile slot count
+  const int32_t* out_rows;  // optional destination-row -> output-row map
   int64_t x_sb, x_sc, x_sn;
   int64_t idx_sb, et_sb;
   int64_t o_sb, o_so, o_sm, o_sk;

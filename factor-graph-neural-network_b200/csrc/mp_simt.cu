@@ -43,7 +43,7 @@ mp_simt_kernel(const MpParams p, const int og_count, const int RG) {
     const bool active = dest_ok && o < p.O;
     AggState st;
     st.init(p.agg);
-    for (int k0 = 0; k0 < p.K; k0 += kRB) {
+    for (int k0 = 0; k0 < p.K; k0 += kRB) {                 // (slots beyond tile_k[g/128] are dead, see below)
       __syncthreads();
       // 1) slot -> source row
       if (tid < RG * kRB) {
@@ -55,6 +55,7 @@ mp_simt_kernel(const MpParams p, const int og_count, const int RG) {
           const int bi = (int)(gi / p.M), mi = (int)(gi % p.M);
           n = load_index(p.idx, p.idx64, (int64_t)bi * p.idx_sb + (int64_t)mi * p.K + k);
           if (n < 0 || n >= p.N) n = -1;   // masked (FGNN_FLAG_MASK_NEGATIVE) or invalid: dead slot
+          if (p.tile_k && k >= p.tile_k[gi / 128]) n = -1;   // compacted table: beyond this tile's slot count
         }
         n_s[tid] = n;
       }
@@ -146,7 +147,11 @@ mp_simt_kernel(const MpParams p, const int og_count, const int RG) {
       float v = st.finish(p.agg, p.gamma);
       if (v != -INFINITY) v = apply_epilogue(v, o, p);   // -inf = no live slot (sharded tables): keep
       float* dst = p.out + (int64_t)b * p.o_sb + (int64_t)o * p.o_so + (int64_t)m * p.o_sm;
-      *dst = p.accumulate ? *dst + v : v;
+      if (p.out_rows) {
+        const int32_t row = p.out_rows[g];
+        dst = row >= 0 ? p.out + (int64_t)row * p.o_sm + (int64_t)o * p.o_so : nullptr;
+      }
+      if (dst) *dst = p.accumulate ? *dst + v : v;
     }
   }
 }

@@ -309,7 +309,17 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     if (p.B == 1) { b = 0; m = g; } else { b = g / Mu; m = g - b * Mu; }
   };
   const int my_tiles = worker < n_tiles ? (n_tiles - worker + n_workers - 1) / n_workers : 0;
-  const uint32_t n_items = (uint32_t)my_tiles * (uint32_t)p.K;   // (tile, k) items of this CTA, in order
+  // slots evaluated in a tile: K, or the tile's own count for compacted shard-local tables
+  auto slots_of = [&](int tile) -> int { return p.tile_k ? (tile < n_tiles ? p.tile_k[tile] : 0) : p.K; };
+  // this CTA's items (tile, k) in order: tile = worker + j*n_workers, k < slots_of(tile)
+  struct ItemIter {
+    int tile, k, kt;
+  };
+  auto first_item = [&]() -> ItemIter { return ItemIter{worker, 0, slots_of(worker)}; };
+  auto next_item = [&](ItemIter& it) {
+    if (++it.k >= it.kt) { it.k = 0; it.tile += n_workers; it.kt = slots_of(it.tile); }
+  };
+  (void)my_tiles;
 
   // ---- one-time setup ---------------------------------------------------------------------
   if (tid == 0) {
@@ -377,13 +387,14 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
       for (int c = 0; c < CH; ++c) acc[c] = (AGG == FGNN_AGG_MEAN) ? 0.f : -INFINITY;
 #pragma unroll
       for (int c = 0; c < (AGG == FGNN_AGG_SOFTMAX ? CH : 1); ++c) acc2[c] = 0.f;
-      for (int k = 0; k < p.K; ++k) {
+      const int kt = slots_of(tile);
+      for (int k = 0; k < kt; ++k) {
         float et[T];
 #pragma unroll
         for (int t = 0; t < T; ++t) et[t] = et_nx[t];
         const bool live = live_nx;
         // prefetch the next item's edge types: their latency hides behind this item's math
-        if (k + 1 < p.K) fetch(tile, k + 1); else fetch(tile + n_workers, 0);
+        if (k + 1 < kt) fetch(tile, k + 1); else fetch(tile + n_workers, 0);
 #pragma unroll
         for (int chunk = 0; chunk < NCH; ++chunk) {
           const uint32_t st = ct & 1;
@@ -482,13 +493,15 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
         constexpr int RPI = 32 / CPR;
         const int cq = lane % CPR, rsub = lane / CPR;
         const uint32_t g0 = (uint32_t)tile * kTileM + warp * 32;
-        float* obase = p.out + (int64_t)g0 * p.o_sm + ch0 + cq * 4;
+        float* obase = p.out + ch0 + cq * 4;
 #pragma unroll
         for (int it = 0; it < CPR; ++it) {
           const int rr = it * RPI + rsub;
-          if (g0 + rr < rows_total) {
+          int64_t orow = (int64_t)g0 + rr;                   // flattened output row (out is batch-contiguous)
+          if (g0 + rr < rows_total && p.out_rows) orow = p.out_rows[g0 + rr];
+          if (g0 + rr < rows_total && orow >= 0) {
             float4 v = stage[rr * CPR + ((cq & ~SW) | ((cq ^ rr) & SW))];
-            float4* dst = reinterpret_cast<float4*>(obase + (int64_t)rr * p.o_sm);
+            float4* dst = reinterpret_cast<float4*>(obase + orow * p.o_sm);
             if (p.accumulate) {
               const float4 old = *dst;
               v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
@@ -510,7 +523,8 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     const int cr = tid - kEpiWarps * 32;
     const uint32_t row_u = smem_u32(sA) + (uint32_t)cr * 256u;
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTACol0;
-    for (uint32_t i = 0; i < n_items; ++i) {
+    uint32_t i = 0;
+    for (ItemIter it = first_item(); it.tile < n_tiles; next_item(it), ++i) {
       const uint32_t st = i % NST, use = i / NST;
       const uint32_t ta = i % kTA, tuse = i / kTA;
       mbar_wait(raw_full(st), use & 1);
@@ -547,24 +561,25 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     const int sub = lane >> 4, q = lane & 15;                // 16 lanes x 16 B = one 256-byte row
     // index-table entry of the row this lane owns (row pw*32+lane of item i's tile); the load is
     // issued one item ahead and only CONSUMED (range check -> source row) after the stage wait
-    auto index_of = [&](uint32_t i, int32_t& base) -> int64_t {
+    auto index_of = [&](const ItemIter& it, int32_t& base) -> int64_t {
       base = -1;
-      if (i >= n_items) return -1;
-      const uint32_t j = i / (uint32_t)p.K, k = i - j * (uint32_t)p.K;
-      const uint32_t g = ((uint32_t)worker + j * (uint32_t)n_workers) * kTileM + pw * 32 + lane;
+      if (it.tile >= n_tiles) return -1;
+      const uint32_t g = (uint32_t)it.tile * kTileM + pw * 32 + lane;
       if (g >= rows_total) return -1;
       uint32_t b, m;
       split_row(g, b, m);
       base = (int32_t)(b * (uint32_t)p.N);
-      return load_index(p.idx, p.idx64, (int64_t)b * p.idx_sb + (int64_t)m * p.K + k);
+      return load_index(p.idx, p.idx64, (int64_t)b * p.idx_sb + (int64_t)m * p.K + it.k);
     };
     const float* xq = p.x + q * 4;
     const uint32_t sA_u = smem_u32(sA);
     int32_t base, base_next;
-    int64_t n = index_of(0, base);
-    for (uint32_t i = 0; i < n_items; ++i) {
+    ItemIter it = first_item();
+    int64_t n = index_of(it, base);
+    for (uint32_t i = 0; it.tile < n_tiles; ++i) {
       const uint32_t st = i % NST, use = i / NST;
-      const int64_t n_next = index_of(i + 1, base_next);     // index load of the next item: in flight during this one
+      next_item(it);
+      const int64_t n_next = index_of(it, base_next);        // index load of the next item: in flight during this one
       mbar_wait(raw_empty(st), (use & 1) ^ 1);
       if (pw == 0) TC_TRACE(i, 0);
       // source row (b*N + n; x is batch-contiguous, checked by tc_supported); -1 = no row (tile tail,
@@ -572,8 +587,8 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
       const int32_t src = (base >= 0 && n >= 0 && n < p.N) ? base + (int32_t)n : -1;
       const uint32_t stage = sA_u + st * kAStageBytes;
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int rw = 2 * it + sub;
+      for (int u = 0; u < 16; ++u) {
+        const int rw = 2 * u + sub;
         const int32_t row = __shfl_sync(0xffffffffu, src, rw);
         const int rr = pw * 32 + rw;
         // chunk q of row rr at position q ^ (rr & 15): the converter's per-row reads are conflict-free
@@ -606,8 +621,8 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     constexpr uint32_t idesc = umma_idesc(NC);
     // descriptor of a B tile = constant high word + (address >> 4) in the low word
     const uint64_t desc_hi = umma_desc_sw128(0);
-    uint32_t ct = 0;
-    for (uint32_t i = 0; i < n_items; ++i) {
+    uint32_t ct = 0, i = 0;
+    for (ItemIter it = first_item(); it.tile < n_tiles; next_item(it), ++i) {
       const uint32_t ta = i % kTA, tuse = i / kTA;
       mbar_wait(ta_full(ta), tuse & 1);
       TC_TRACE(i, 4);

@@ -99,12 +99,16 @@ class _Workspace:
 def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=None, *,
                extension=0, aggregator=_lib.AGG_MAX, activation=_lib.ACT_RELU, act_slope=0.01,
                gamma=_SOFTMAX_GAMMA, kernel=_lib.KERNEL_AUTO, mask_negative=False, validate=True,
-               out=None, accumulate=False, workspace=None, filters_version=0):
+               out=None, accumulate=False, workspace=None, filters_version=0, tile_slots=None, out_rows=None):
     """Functional form of the hot path: one `fgnn_mp_forward` call on x's device / current stream.
 
     x [B,C,N,1] or [B,C,N] (any strides; node-major == channels_last is the fast layout),
     nn_idx [B,M,K] int64/int32, etype [B,T,M,K], filters [C or 2C, O*T] fp32.
     Returns [B,O,M,1] ([B,O,M,K] for AGG_NONE) with node-major (channels_last) memory.
+
+    Compacted shard-local tables (factor-sharded F->V, fgnn_b200.parallel): `tile_slots` int32
+    [ceil(B*M/128)] = slots evaluated per 128-row destination tile, `out_rows` int32 [B*M] = output
+    row of every destination row (then `out` [Bo,O,Mo,1] must be given; rows not named keep their value).
     """
     if not x.is_cuda:
         raise RuntimeError("fgnn_b200: mp_conv_v2.forward needs CUDA tensors (there is no CPU "
@@ -160,8 +164,18 @@ def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=Non
     if out is None:
         out = torch.empty((B, O, M, Kout), dtype=x3.dtype, device=dev,
                           memory_format=torch.channels_last)
-    elif tuple(out.shape) != (B, O, M, Kout) or out.dtype != x3.dtype or out.device != dev:
+    elif out_rows is None and (tuple(out.shape) != (B, O, M, Kout) or out.dtype != x3.dtype or out.device != dev):
         raise ValueError("out has the wrong shape, dtype or device")
+    if out_rows is not None:
+        if out_given is None or out.dim() != 4 or out.shape[1] != O or out.shape[3] != 1 or out.dtype != x3.dtype:
+            raise ValueError("out_rows needs a preallocated out [Bo, O, Mo, 1]")
+        if out.stride(1) != 1 or (out.shape[0] > 1 and out.stride(0) != out.shape[2] * out.stride(2)):
+            raise ValueError("out_rows needs a node-major, batch-contiguous out")
+        if out_rows.dtype != torch.int32 or out_rows.numel() != B * M or not out_rows.is_contiguous():
+            raise ValueError("out_rows must be a contiguous int32 tensor of B*M entries")
+    if tile_slots is not None and (tile_slots.dtype != torch.int32 or tile_slots.numel() != (B * M + 127) // 128
+                                   or not tile_slots.is_contiguous()):
+        raise ValueError("tile_slots must be a contiguous int32 tensor of ceil(B*M/128) entries")
     if B * M * K == 0 or N == 0:
         if N == 0 and B * M * K > 0:
             raise IndexError("fgnn_b200: nn_idx entry out of range (no source nodes)")
@@ -198,6 +212,8 @@ def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=Non
     a.gamma, a.act_slope = float(gamma), float(act_slope)
     a.filters_version = int(filters_version)
     a.workspace, a.workspace_bytes = None, 0
+    a.tile_slots = tile_slots.data_ptr() if tile_slots is not None else None
+    a.out_rows = out_rows.data_ptr() if out_rows is not None else None
     with torch.cuda.device(dev):
         need = lib.fgnn_mp_workspace_bytes(ctypes.byref(a))
         if need:

@@ -108,6 +108,12 @@ typedef struct fgnn_mp_args {
   float act_slope;        /* LeakyReLU negative slope                      */
   int64_t filters_version;/* any value that changes when `filters` changes (the tensor-core path caches
                              its bf16 weight image in the workspace keyed on it); 0 = never cache */
+  /* Compacted shard-local tables (factor-sharded F->V direction); both optional (NULL):     */
+  const int32_t* tile_slots; /* [ceil(B*M/128)], each in [1,K]: in the 128-row destination tile i only slots
+                                k < tile_slots[i] are evaluated (rows sorted by live-slot count, the rest
+                                of the row is empty anyway)                                              */
+  const int32_t* out_rows;   /* [B*M]: destination row g = b*M+m is written to out + out_rows[g]*out_sm
+                                (+ o*out_so) instead of its own position; negative = not written       */
 } fgnn_mp_args;
 
 int fgnn_version(void);

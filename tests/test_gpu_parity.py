@@ -256,9 +256,11 @@ def test_masked_slots_and_epilogue_split_equal_fused():
     red = torch.maximum(parts[0], parts[1])               # what ncclAllReduce(max) computes
     rows = red.shape[0] * red.shape[2]
     flat = red.permute(0, 2, 3, 1).contiguous()
+    d_bias, d_scale, d_shift = t(bias), t(scale), t(shift)     # keep the device buffers alive across the call
     _lib.check(_lib.lib().fgnn_epilogue_forward(
-        flat.data_ptr(), flat.data_ptr(), rows, 64, t(bias).data_ptr(), t(scale).data_ptr(), t(shift).data_ptr(),
+        flat.data_ptr(), flat.data_ptr(), rows, 64, d_bias.data_ptr(), d_scale.data_ptr(), d_shift.data_ptr(),
         _lib.ACT_RELU, 0.0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "epilogue")
+    torch.cuda.synchronize()
     got = flat.permute(0, 3, 1, 2)
     assert torch.equal(got, full), "sharded max + epilogue differs from the fused call"
 
@@ -283,3 +285,72 @@ def test_full_size_properties_cfg2():
     scale = bn["weight"] / np.sqrt(bn["running_var"] + 1e-5)
     const = np.maximum(bias * scale + bn["bias"] - bn["running_mean"] * scale, 0).astype(np.float32)
     assert_close(yz.cpu().numpy(), np.broadcast_to(const.reshape(1, O, 1, 1), (1, O, M, 1)), 1e-6, "zero etype")
+
+
+# ---------------------------------------------------------------------------------------------
+# factor-sharded layer: N-GPU result == 1-GPU result, ranks simulated on one device
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("kernel", ["auto", "simt"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_plan_equals_single_gpu(world, kernel):
+    from fgnn_b200 import parallel
+    rng = np.random.default_rng(5)
+    C = O = 64
+    T = 4
+    types = graphs.synthetic_map_graph(3000, 9000, 1500, 3, seed=9)
+    J = len(types)
+    dev = torch.device(DEV)
+    x_v = t(rng.random((1, types[0].n_vars, C), dtype=np.float32))
+    x_f = [t(np.abs(rng.standard_normal((1, ty.n_factors, C))).astype(np.float32)) for ty in types]
+    et_v2f = [t(rng.standard_normal((1, T, ty.n_factors, ty.order)).astype(np.float32)) for ty in types]
+    et_f2v = []
+    for ty in types:
+        e = rng.standard_normal((1, T, ty.n_vars, ty.kv)).astype(np.float32)
+        e[np.broadcast_to(ty.pad_f2v[None, None], e.shape)] = 0.0
+        et_f2v.append(t(e))
+    W = []
+    for _ in range(J):
+        d = {}
+        for direction in ("v2f", "f2v"):
+            d[direction] = dict(filters=t((rng.uniform(-1, 1, (C, O * T)) * 0.1).astype(np.float32)),
+                                bias=t(rng.uniform(-0.2, 0.2, O).astype(np.float32)),
+                                scale=t(rng.uniform(0.8, 1.2, O).astype(np.float32)),
+                                shift=t(rng.uniform(-0.2, 0.2, O).astype(np.float32)))
+        W.append(d)
+    kern = KERNELS[kernel]
+    nm = lambda a: a.permute(0, 2, 1).unsqueeze(-1)
+    # single GPU: the unsharded reference tables
+    ref_v = torch.zeros_like(x_v)
+    ref_f = []
+    for j, ty in enumerate(types):
+        w = W[j]
+        ref_f.append(fgnn_b200.mp_forward(nm(x_v), t(ty.idx_v2f[None]), et_v2f[j], w["v2f"]["filters"], w["v2f"]["bias"],
+                                          w["v2f"]["scale"], w["v2f"]["shift"], extension=0, aggregator=0, kernel=kern))
+        fgnn_b200.mp_forward(nm(x_f[j]), t(ty.idx_f2v[None]), et_f2v[j], w["f2v"]["filters"], w["f2v"]["bias"],
+                             w["f2v"]["scale"], w["f2v"]["shift"], extension=0, aggregator=0, kernel=kern,
+                             out=nm(ref_v), accumulate=j > 0)
+    # `world` ranks, one after the other on this device; the all-reduce(MAX) is the elementwise maximum
+    raws, facs, plans = [], [], []
+    for rank in range(world):
+        plan = parallel.ShardedLayerPlan(types, rank, world, dev)
+        xf_loc = plan.local_factor_features(x_f)
+        ev, ef = plan.local_etypes(et_v2f, et_f2v)
+        out_v = torch.empty_like(x_v)
+        out_f = [torch.empty_like(a) for a in xf_loc]
+        plan.layer(x_v, xf_loc, ev, ef, W, out_v, out_f, kern)      # no process group: reduce is done below
+        raws.append(plan.raw.clone())
+        facs.append(out_f)
+        plans.append(plan)
+    raw = raws[0]
+    for r in raws[1:]:
+        raw = torch.maximum(raw, r)
+    assert torch.isfinite(raw).all()
+    got_v = plans[0].finish(raw, W, torch.empty_like(x_v))
+    assert torch.equal(got_v, ref_v), "sharded F->V differs from the single-GPU result"
+    for j in range(J):
+        cat = torch.cat([f[j] for f in facs], 1)
+        assert torch.equal(nm(cat), ref_f[j]), "sharded V->F differs from the single-GPU result"
+    # work really is sharded: live slots per rank add up to the table size
+    for j, ty in enumerate(types):
+        assert sum(p.f2v[j].live_slots for p in plans) == ty.idx_f2v.size
