@@ -261,6 +261,7 @@ def run_native(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_MAX_CTAS", "16")       # the all-reduce shares the GPU with the V->F kernels
         dist.init_process_group("nccl", device_id=dev)
     kernel = {"auto": _lib.KERNEL_AUTO, "simt": _lib.KERNEL_SIMT, "tcgen05": _lib.KERNEL_TCGEN05}[args.kernel]
 

@@ -41,6 +41,7 @@ class MpArgs(ctypes.Structure):
         ("flags", ctypes.c_uint32), ("gamma", ctypes.c_float), ("act_slope", ctypes.c_float),
         ("filters_version", ctypes.c_int64),
         ("tile_slots", ctypes.c_void_p), ("out_rows", ctypes.c_void_p),
+        ("sm_limit", ctypes.c_int32), ("reserved_", ctypes.c_int32),
     ]
 
 
@@ -59,6 +60,9 @@ EXPORTS = {
                                              ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_int32, ctypes.c_float,
                                              ctypes.c_void_p]),
+    "fgnn_epilogue_sum_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
+                                                 ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.c_int32, ctypes.c_float, ctypes.c_int32, ctypes.c_void_p]),
     "fgnn_to_node_major": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                           ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
                                           ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),

@@ -113,6 +113,41 @@ __global__ void epilogue_kernel(const float* __restrict__ in, float* __restrict_
   }
 }
 
+// out[r, o] (+)= sum_j act(bn_j(in[r, j*O + o] + bias_j[o])); one thread per 4 output channels
+__global__ void epilogue_sum_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t rows, int O, int J,
+                                    const float* __restrict__ bias, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, int act, float slope, int accumulate) {
+  const int O4 = O >> 2;
+  const int64_t total = rows * O4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / O4;
+    const int o = (int)(i % O4) * 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < J; ++j) {
+      const float4 v4 = *reinterpret_cast<const float4*>(in + (r * J + j) * O + o);
+      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float y = v[c];
+        if (y != -INFINITY) {
+          const int col = j * O + o + c;
+          if (bias) y += bias[col];
+          if (scale) y = fmaf(y, scale[col], shift[col]);
+          if (act == FGNN_ACT_RELU) y = fmaxf(y, 0.f);
+          else if (act == FGNN_ACT_LEAKY_RELU) y = y >= 0.f ? y : y * slope;
+        }
+        acc[c] += y;
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(out + r * O + o);
+    if (accumulate) {
+      const float4 old = *dst;
+      acc[0] += old.x; acc[1] += old.y; acc[2] += old.z; acc[3] += old.w;
+    }
+    *dst = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+}
+
 static int device_ok() {
   static int cached = -100;
   if (cached != -100) return cached;
@@ -226,6 +261,23 @@ int fgnn_epilogue_forward(const float* in, float* out, int64_t rows, int32_t O, 
   if (blocks > 148 * 16) blocks = 148 * 16;
   epilogue_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
       in, out, total, O, bias, bn_scale, bn_shift, activation, act_slope);
+  count_launch();
+  FGNN_CUDA(cudaGetLastError());
+  return FGNN_OK;
+}
+
+int fgnn_epilogue_sum_forward(const float* in, float* out, int64_t rows, int32_t O, int32_t J, const float* bias,
+                              const float* bn_scale, const float* bn_shift, int32_t activation, float act_slope,
+                              int32_t accumulate, void* stream_) {
+  if (!in || !out || rows < 0 || O <= 0 || J <= 0 || (O & 3)) return FGNN_ERR_INVALID_ARG;
+  if ((bn_scale == nullptr) != (bn_shift == nullptr)) return FGNN_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return FGNN_ERR_INVALID_ARG;
+  const int64_t total = rows * (O / 4);
+  if (total == 0) return FGNN_OK;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  epilogue_sum_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      in, out, rows, O, J, bias, bn_scale, bn_shift, activation, act_slope, accumulate);
   count_launch();
   FGNN_CUDA(cudaGetLastError());
   return FGNN_OK;

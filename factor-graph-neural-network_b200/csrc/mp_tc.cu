@@ -39,6 +39,9 @@
 // whole lifetime; the image is produced once per weight version by w_split_kernel.
 #include <cuda_bf16.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 
 namespace fgnn {
@@ -388,6 +391,12 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
 #pragma unroll
       for (int c = 0; c < (AGG == FGNN_AGG_SOFTMAX ? CH : 1); ++c) acc2[c] = 0.f;
       const int kt = slots_of(tile);
+      // output row of tile row (warp*32 + lane), fetched now so the finish phase never waits on it
+      int32_t my_orow = -1;
+      {
+        const uint32_t go = (uint32_t)tile * kTileM + warp * 32 + lane;
+        if (go < rows_total) my_orow = p.out_rows ? p.out_rows[go] : (int32_t)go;
+      }
       for (int k = 0; k < kt; ++k) {
         float et[T];
 #pragma unroll
@@ -492,14 +501,12 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
         // (out is batch-contiguous node-major, so flattened row g lives at out + g * o_sm)
         constexpr int RPI = 32 / CPR;
         const int cq = lane % CPR, rsub = lane / CPR;
-        const uint32_t g0 = (uint32_t)tile * kTileM + warp * 32;
         float* obase = p.out + ch0 + cq * 4;
 #pragma unroll
         for (int it = 0; it < CPR; ++it) {
           const int rr = it * RPI + rsub;
-          int64_t orow = (int64_t)g0 + rr;                   // flattened output row (out is batch-contiguous)
-          if (g0 + rr < rows_total && p.out_rows) orow = p.out_rows[g0 + rr];
-          if (g0 + rr < rows_total && orow >= 0) {
+          const int64_t orow = __shfl_sync(0xffffffffu, my_orow, rr);   // flattened output row (out is batch-contiguous)
+          if (orow >= 0) {
             float4 v = stage[rr * CPR + ((cq & ~SW) | ((cq ^ rr) & SW))];
             float4* dst = reinterpret_cast<float4*>(obase + orow * p.o_sm);
             if (p.accumulate) {
@@ -752,9 +759,32 @@ int launch_mp_tc(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream) 
   uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
   if (reinterpret_cast<uintptr_t>(ws) & 255) return FGNN_ERR_WORKSPACE;
   const int OT = p.O * p.T;
-  w_split_kernel<<<(OT * (tc::kC / 8) + 255) / 256, 256, 0, stream>>>(p.W, ws, OT, a->filters_version);
-  count_launch();
-  if (cudaGetLastError() != cudaSuccess) return FGNN_ERR_CUDA;
+  // The image is rebuilt unless this workspace is known to hold the image of exactly these filters
+  // (pointer + caller-supplied version).  Host-side mirror of the device header: a cached image costs
+  // no launch at all.  filters_version == 0 always rebuilds.
+  {
+    static std::mutex mu;
+    static std::unordered_map<const void*, tc::Header> known;
+    bool fresh = false;
+    if (a->filters_version != 0) {
+      std::lock_guard<std::mutex> lock(mu);
+      auto it = known.find(ws);
+      fresh = it != known.end() && it->second.version == a->filters_version && it->second.filters == p.W &&
+              it->second.OT == OT;
+      if (!fresh) {
+        if (known.size() > 4096) known.clear();
+        known[ws] = tc::Header{a->filters_version, p.W, tc::kC, OT};
+      }
+    } else {
+      std::lock_guard<std::mutex> lock(mu);
+      known.erase(ws);
+    }
+    if (!fresh) {
+      w_split_kernel<<<(OT * (tc::kC / 8) + 255) / 256, 256, 0, stream>>>(p.W, ws, OT, 0);
+      count_launch();
+      if (cudaGetLastError() != cudaSuccess) return FGNN_ERR_CUDA;
+    }
+  }
 
   static int num_sms = 0;
   if (num_sms == 0) {
@@ -766,8 +796,10 @@ int launch_mp_tc(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream) 
   const int64_t rows = (int64_t)p.B * p.M;
   const int tiles = (int)((rows + tc::kTileM - 1) / tc::kTileM);
   const int S = OT / (c.NC * c.NCH);
-  if (S > num_sms) return FGNN_ERR_UNSUPPORTED;
-  int workers = num_sms / S;
+  int sms = num_sms;
+  if (a->sm_limit > 0 && a->sm_limit < sms) sms = a->sm_limit;
+  if (S > sms) return FGNN_ERR_UNSUPPORTED;
+  int workers = sms / S;
   if (workers > tiles) workers = tiles;
   const size_t smem = smem_bytes(c);
   switch (p.T) {

@@ -14,6 +14,7 @@ forward under `torch.no_grad()` / `.eval()` is the contract; train-mode BN is se
 the kernel up to the bias add and handing the result to the module's own `bn`.
 """
 import ctypes
+import os
 import weakref
 from enum import Enum
 
@@ -99,7 +100,7 @@ class _Workspace:
 def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=None, *,
                extension=0, aggregator=_lib.AGG_MAX, activation=_lib.ACT_RELU, act_slope=0.01,
                gamma=_SOFTMAX_GAMMA, kernel=_lib.KERNEL_AUTO, mask_negative=False, validate=True,
-               out=None, accumulate=False, workspace=None, filters_version=0, tile_slots=None, out_rows=None):
+               out=None, accumulate=False, workspace=None, filters_version=0, tile_slots=None, out_rows=None, sm_limit=0):
     """Functional form of the hot path: one `fgnn_mp_forward` call on x's device / current stream.
 
     x [B,C,N,1] or [B,C,N] (any strides; node-major == channels_last is the fast layout),
@@ -214,6 +215,7 @@ def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=Non
     a.workspace, a.workspace_bytes = None, 0
     a.tile_slots = tile_slots.data_ptr() if tile_slots is not None else None
     a.out_rows = out_rows.data_ptr() if out_rows is not None else None
+    a.sm_limit = int(sm_limit)
     with torch.cuda.device(dev):
         need = lib.fgnn_mp_workspace_bytes(ctypes.byref(a))
         if need:
@@ -281,6 +283,7 @@ class mp_conv_v2(base_mp_nn):
                 self._agg = _lib.AGG_NONE
         self.kernel = _lib.KERNEL_AUTO
         self._ws = None
+        self._nonce = int.from_bytes(os.urandom(5), "little")      # distinguishes modules that reuse freed addresses
 
     # -- kernel-side description of the epilogue ------------------------------------------------
     def _activation_code(self):
@@ -296,7 +299,7 @@ class mp_conv_v2(base_mp_nn):
     def _filters_version(self):
         # changes whenever `filters` is re-assigned, moved or written in place through autograd-visible ops
         f = self.filters
-        return ((f._version + 1) * 1000003 + (f.data_ptr() >> 4)) & 0x7fffffffffffffff or 1
+        return ((f._version + 1) * 1000003 + (f.data_ptr() >> 4) + (self._nonce << 20)) & 0x7fffffffffffffff or 1
 
     def _workspace_for(self, x):
         """Private scratch so the split-bf16 image of `filters` is cached across calls."""

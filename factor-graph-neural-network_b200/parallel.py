@@ -78,8 +78,11 @@ class ShardedLayerPlan:
     `types` = list of fgnn_b200.graphs.FactorType (full graph, host); tables are built once.
     """
 
-    def __init__(self, types, rank, world, device, group=None):
+    def __init__(self, types, rank, world, device, group=None, comm_sms=16):
         self.rank, self.world, self.device, self.group = rank, world, device, group
+        # SMs left to the collective while V->F runs beside it (the tensor-core kernel owns whole SMs)
+        self.comm_sms = comm_sms
+        self.n_sms = torch.cuda.get_device_properties(device).multi_processor_count if device.type == "cuda" else 0
         self.types = types
         self.n_vars = types[0].n_vars
         self.ranges = [shard_range(t.n_factors, rank, world) for t in types]
@@ -109,46 +112,52 @@ class ShardedLayerPlan:
               workspaces=None):
         """x_v [1,N,C] node-major (replicated), x_f_local[j] [1,F_j_local,C]; weights[j][dir] = dict(filters,
         bias, scale, shift).  Writes the new variable features to out_v [1,N,O] and the new local factor
-        features to out_f_local[j].  Returns out_v."""
+        features to out_f_local[j].  Returns out_v.
+
+        Order: F->V partial maxima of all types, the all-reduce (asynchronous, on NCCL's stream), the
+        V->F calls (no communication; they overlap the reduce), wait, fused epilogue + sum over types."""
         J = len(self.types)
         O = weights[0]["f2v"]["filters"].shape[1] // et_f2v_local[0].shape[1]
         nm = lambda t: t.permute(0, 2, 1).unsqueeze(-1)
         if self._raw is None or self._raw.shape[-1] != J * O:
             self._raw = torch.empty((1, self.n_vars, J * O), dtype=torch.float32, device=self.device)
-        raw = self._raw
-        self.raw = raw
+        raw = self.raw = self._raw
         raw.fill_(float("-inf"))
         for j in range(J):
-            w = weights[j]
-            wsj = workspaces[j] if workspaces is not None else {"v2f": None, "f2v": None}
-            if x_f_local[j].shape[1] > 0:
-                mp_forward(nm(x_v), self.idx_v2f[j], et_v2f_local[j], w["v2f"]["filters"], w["v2f"]["bias"],
-                           w["v2f"]["scale"], w["v2f"]["shift"], extension=0, aggregator=_lib.AGG_MAX,
-                           activation=_lib.ACT_RELU, kernel=kernel, out=nm(out_f_local[j]), workspace=wsj["v2f"],
-                           filters_version=wsj.get("ver_v2f", 0))
             if self.f2v[j].n_rows > 0:
+                w = weights[j]["f2v"]
+                wsj = workspaces[j] if workspaces is not None else {}
                 view = raw[:, :, j * O:(j + 1) * O]                      # [1,N,O] slice of the [1,N,J*O] buffer
-                mp_forward(nm(x_f_local[j]), self.idx_f2v[j], et_f2v_local[j], w["f2v"]["filters"], None, None, None,
+                mp_forward(nm(x_f_local[j]), self.idx_f2v[j], et_f2v_local[j], w["filters"], None, None, None,
                            extension=0, aggregator=_lib.AGG_MAX, activation=_lib.ACT_NONE, kernel=kernel,
                            mask_negative=True, out=nm(view), tile_slots=self.tile_slots[j], out_rows=self.out_rows[j],
-                           workspace=wsj["f2v"], filters_version=wsj.get("ver_f2v", 0))
+                           workspace=wsj.get("f2v"), filters_version=wsj.get("ver_f2v", 0))
+        work = None
         if self.world > 1 and torch.distributed.is_initialized():
-            torch.distributed.all_reduce(raw, op=torch.distributed.ReduceOp.MAX, group=self.group)
+            work = torch.distributed.all_reduce(raw, op=torch.distributed.ReduceOp.MAX, group=self.group, async_op=True)
+        for j in range(J):
+            if x_f_local[j].shape[1] > 0:
+                w = weights[j]["v2f"]
+                wsj = workspaces[j] if workspaces is not None else {}
+                mp_forward(nm(x_v), self.idx_v2f[j], et_v2f_local[j], w["filters"], w["bias"], w["scale"], w["shift"],
+                           extension=0, aggregator=_lib.AGG_MAX, activation=_lib.ACT_RELU, kernel=kernel,
+                           out=nm(out_f_local[j]), workspace=wsj.get("v2f"), filters_version=wsj.get("ver_v2f", 0),
+                           sm_limit=(self.n_sms - self.comm_sms) if work is not None else 0)
+        if work is not None:
+            work.wait()
         return self.finish(raw, weights, out_v)
 
     def finish(self, raw, weights, out_v):
-        """Bias / folded BN / ReLU per type on the (reduced) raw aggregate [1,N,J*O], summed over types."""
+        """out_v = sum_j ReLU(BN_j(raw_j + bias_j)) on the (reduced) raw aggregate [1,N,J*O]: one kernel."""
         J = len(self.types)
         O = raw.shape[-1] // J
-        lib = _lib.lib()
-        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream) if raw.is_cuda else None
-        for j in range(J):
-            w = weights[j]["f2v"]
-            part = raw[:, :, j * O:(j + 1) * O].contiguous() if J > 1 else raw
-            dst = out_v if j == 0 else torch.empty_like(out_v)
-            _lib.check(lib.fgnn_epilogue_forward(part.data_ptr(), dst.data_ptr(), self.n_vars, O, w["bias"].data_ptr(),
-                                                 w["scale"].data_ptr(), w["shift"].data_ptr(), _lib.ACT_RELU, 0.0, stream),
-                       "epilogue_forward")
-            if j > 0:
-                out_v += dst
+        key = tuple(w["f2v"]["bias"].data_ptr() for w in weights)
+        if getattr(self, "_epi_key", None) != key:
+            self._epi = [torch.cat([w["f2v"][k] for w in weights]).contiguous() for k in ("bias", "scale", "shift")]
+            self._epi_key = key
+        bias, scale, shift = self._epi
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(_lib.lib().fgnn_epilogue_sum_forward(raw.data_ptr(), out_v.data_ptr(), self.n_vars, O, J, bias.data_ptr(),
+                                                        scale.data_ptr(), shift.data_ptr(), _lib.ACT_RELU, 0.0, 0, stream),
+                   "epilogue_sum_forward")
         return out_v

@@ -107,13 +107,19 @@ typedef struct fgnn_mp_args {
   float gamma;            /* softmax aggregator temperature (reference: 3)  */
   float act_slope;        /* LeakyReLU negative slope                      */
   int64_t filters_version;/* any value that changes when `filters` changes (the tensor-core path caches
-                             its bf16 weight image in the workspace keyed on it); 0 = never cache */
+                             its bf16 weight image in the workspace keyed on workspace + filters pointer +
+                             this value; the caller then must leave the workspace untouched between
+                             calls); 0 = never cache */
   /* Compacted shard-local tables (factor-sharded F->V direction); both optional (NULL):     */
   const int32_t* tile_slots; /* [ceil(B*M/128)], each in [1,K]: in the 128-row destination tile i only slots
                                 k < tile_slots[i] are evaluated (rows sorted by live-slot count, the rest
                                 of the row is empty anyway)                                              */
   const int32_t* out_rows;   /* [B*M]: destination row g = b*M+m is written to out + out_rows[g]*out_sm
                                 (+ o*out_so) instead of its own position; negative = not written       */
+  int32_t sm_limit;          /* > 0: the persistent tensor-core kernel uses at most this many SMs, leaving the
+                                rest to a concurrent collective (the kernel owns whole SMs: a CTA that cannot
+                                be placed would serialise behind the collective).  0 = all SMs              */
+  int32_t reserved_;
 } fgnn_mp_args;
 
 int fgnn_version(void);
@@ -147,6 +153,14 @@ int fgnn_check_index_range(const void* idx, int idx_dtype, int64_t count, int64_
 int fgnn_epilogue_forward(const float* in, float* out, int64_t rows, int32_t O, const float* bias,
                           const float* bn_scale, const float* bn_shift, int32_t activation,
                           float act_slope, void* stream);
+
+/* The same for J factor types at once: in = [rows, J*O] (type j in columns j*O..j*O+O-1, the layout of
+ * the single max-all-reduce per layer), bias / bn_scale / bn_shift = [J*O] (or NULL),
+ * out[r,o] = sum_j act(bn_j(in[r, j*O+o] + bias_j[o]))  -- FactorNN's `nfeature += nv` over the factor
+ * types (factor_mpnn_sp.py:142-147).  With accumulate != 0 the sum is added to out. */
+int fgnn_epilogue_sum_forward(const float* in, float* out, int64_t rows, int32_t O, int32_t J, const float* bias,
+                              const float* bn_scale, const float* bn_shift, int32_t activation, float act_slope,
+                              int32_t accumulate, void* stream);
 
 /* Layout helper: channel-major [B,C,N] -> node-major [B,N,C] (the reference's
  * x.permute(0,2,3,1).contiguous(), mp_nn.py:125). */
