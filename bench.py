@@ -369,6 +369,7 @@ def run_native(args):
                                        "bn.running_mean": torch.from_numpy(p["rm"]), "bn.running_var": torch.from_numpy(p["rv"]),
                                        "bn.num_batches_tracked": torch.tensor(0)})
                     m.kernel = kernel
+                    m.index_check = "async"          # range scan without a host round trip (reference CUDA semantics)
                     pair[d] = m.to(dev).eval().enable_weight_cache()
                 row.append(pair)
             mods.append(row)
@@ -379,20 +380,51 @@ def run_native(args):
         h2d = sum(t.numel() * t.element_size() for v in pinned.values() for t in (v if isinstance(v, list) else [v]))
         d2h = host_out.numel() * 4
 
+        copy_stream = torch.cuda.Stream(device=dev)
+        order = ["x_v"] + [(k, j) for j in range(J) for k in ("idx_v2f", "et_v2f", "x_f", "idx_f2v", "et_f2v")]
+
         def e2e_step():
-            src = {k: ([t.to(dev, non_blocking=True) for t in v] if isinstance(v, list) else v.to(dev, non_blocking=True))
-                   for k, v in pinned.items()}
-            x_v, x_f = nm(src["x_v"]), [nm(x) for x in src["x_f"]]
+            """Inputs leave pinned host memory on a copy stream in the order the layer consumes them;
+            each module call waits only for the tensors it reads, so the first calls overlap the rest
+            of the upload.  The final variable features come back to pinned host memory."""
+            main = torch.cuda.current_stream(dev)
+            copy_stream.wait_stream(main)                    # previous step's readers are done with the buffers
+            src, ready = {k: ([None] * J if isinstance(v, list) else None) for k, v in pinned.items()}, {}
+            with torch.cuda.stream(copy_stream):
+                for item in order:
+                    if item == "x_v":
+                        src["x_v"] = pinned["x_v"].to(dev, non_blocking=True)
+                    else:
+                        k, j = item
+                        src[k][j] = pinned[k][j].to(dev, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                    ready[item] = ev
+
+            def need(*items):
+                for it in items:
+                    main.wait_event(ready[it])
+
+            need("x_v")
+            x_v, x_f = nm(src["x_v"]), [None] * J
             with torch.no_grad():
                 for l in range(L):
                     nv, nf = None, []
                     for j in range(J):
+                        if l == 0:
+                            need(("idx_v2f", j), ("et_v2f", j))
                         nf.append(mods[l][j]["v2f"](x_v, src["idx_v2f"][j], src["et_v2f"][j]))
+                        if l == 0:
+                            need(("x_f", j), ("idx_f2v", j), ("et_f2v", j))
+                            x_f[j] = nm(src["x_f"][j])
                         y = mods[l][j]["f2v"](x_f[j], src["idx_f2v"][j], src["et_f2v"][j])
                         nv = y if nv is None else nv + y
                     x_v, x_f = nv, nf
             host_out.copy_(x_v[..., 0].permute(0, 2, 1), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            for v in src.values():                           # the copy stream's allocations are used on `main`
+                for t in (v if isinstance(v, list) else [v]):
+                    t.record_stream(main)
+            main.synchronize()
 
         if world == 1:
             for _ in range(2):
@@ -403,10 +435,12 @@ def run_native(args):
             for _ in range(k):
                 e2e_step()
             torch.cuda.synchronize()
+            fgnn_b200.check_async_errors()
             dt = (time.perf_counter() - t0) / k
             e2e = {"value": msgs_layer * L / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                   "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": k,
-                   "api": "fgnn_b200.mp_conv_v2.forward (20 module calls), pinned host tensors in, pinned host tensor out"}
+                   "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": k, "index_check": "async",
+                   "api": "fgnn_b200.mp_conv_v2.forward (20 module calls), pinned host tensors in (uploaded on a copy stream, "
+                          "each call waits only for its own inputs), pinned host tensor out"}
 
     if rank != 0:
         if world > 1:
@@ -414,6 +448,10 @@ def run_native(args):
         return
     peak, peak_src = hbm_peak()
     achieved = bytes_layer * L / (ms_step * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and args.edge_types == 16 and world == 1 and args.vars == 100_000:
+        traffic = json.load(open(tpath))["traffic_bytes_per_launch_avg"]     # ncu --set full of this very workload
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
@@ -423,9 +461,12 @@ def run_native(args):
                    % (bytes_layer // 1_000_000), "parallelism": ("factor-sharded x%d + NCCL max-all-reduce per layer" % world)
                    if world > 1 else "single GPU"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "fgnn mp kernel (avg over the step's launches)",
-                     "algorithmic_bytes_per_launch": bytes_layer * L / max(launches / args.steps, 1),
-                     "avg_launch_us": ms_step * 1e3 / max(launches / args.steps, 1)},
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "mp_tc_kernel (tcgen05; average over the step's %d message-passing launches)" % (4 * L if world == 1 else 0)
+                     if args.kernel != "simt" else "mp_simt_kernel",
+                     "algorithmic_bytes_per_launch": bytes_layer * L / (2 * J * L),
+                     "avg_launch_us": ms_step * 1e3 / (2 * J * L),
+                     "tensor_bound_note": "T=16 fp32 is tensor-bound in this formulation (3-term split-bf16 MMA, 2*E*C*O*T flop): "
+                                          "HBM-roofline ceiling ~0.22, DESIGN.md 3.1" if args.edge_types >= 16 else None},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if e2e is not None:

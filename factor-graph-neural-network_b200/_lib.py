@@ -56,6 +56,8 @@ EXPORTS = {
     "fgnn_check_index_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
                                               ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
                                               ctypes.c_void_p]),
+    "fgnn_check_index_range_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                                    ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     "fgnn_epilogue_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                              ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_int32, ctypes.c_float,

@@ -93,7 +93,7 @@ __global__ void check_index_kernel(const void* idx, int idx64, int64_t count, in
     const int64_t v = load_index(idx, idx64, i);
     bad |= (v < lo) | (v >= n);
   }
-  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
+  if (__syncthreads_or(bad) && threadIdx.x == 0) *reinterpret_cast<volatile int*>(flag) = 1;   // idempotent store: works on mapped host memory too
 }
 
 __global__ void epilogue_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t total, int O,
@@ -248,6 +248,18 @@ int fgnn_check_index_range(const void* idx, int idx_dtype, int64_t count, int64_
   FGNN_CUDA(cudaMemcpyAsync(&host, flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
   FGNN_CUDA(cudaStreamSynchronize(stream));
   return host ? FGNN_ERR_INDEX_RANGE : FGNN_OK;
+}
+
+int fgnn_check_index_range_async(const void* idx, int idx_dtype, int64_t count, int64_t lo, int64_t n,
+                                 int32_t* flag, void* stream_) {
+  if (!idx || !flag || count < 0) return FGNN_ERR_INVALID_ARG;
+  if (count == 0) return FGNN_OK;
+  int blocks = (int)((count + 255) / 256 < 1184 ? (count + 255) / 256 : 1184);
+  check_index_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(idx, idx_dtype == FGNN_I64, count, lo, n,
+                                                                              reinterpret_cast<int*>(flag));
+  count_launch();
+  FGNN_CUDA(cudaGetLastError());
+  return FGNN_OK;
 }
 
 int fgnn_epilogue_forward(const float* in, float* out, int64_t rows, int32_t O, const float* bias,

@@ -31,7 +31,7 @@
 //                           item's indices are loaded one item ahead
 //   warp  12    MMA         one elected lane issues tcgen05.mma (A: TMEM, B: smem descriptor); owns the
 //                           TMEM allocation; brings the stationary filter slice in with TMA bulk copies
-// TMEM (512 columns): 2 accumulator stages x 128 columns + 4 A stages x 64 columns (32 hi + 32 lo).
+// TMEM (512 columns): 3 accumulator stages x 128 columns + 2 A stages x 64 columns (32 hi + 32 lo).
 // Pipelines (all mbarrier): raw ring raw_empty -> raw_full; A stages ta_empty -> ta_full;
 // accumulators t_empty -> t_full.
 // The filters are stationary: each CTA keeps the split-bf16 image of its column slice
@@ -69,9 +69,10 @@ constexpr int kEpiWarps = 4, kGatherWarps = 4, kConvWarps = 4;
 constexpr int kMmaWarp = kEpiWarps + kGatherWarps + kConvWarps;
 constexpr int kThreads = (kMmaWarp + 1) * 32;                 // 416
 constexpr int kMaxAStages = 6;                                // raw ring stages in shared memory
-constexpr int kTA = 4;                                        // A stages in tensor memory
-constexpr int kAccCols = 128, kTACol0 = 2 * kAccCols, kTACols = 64;   // TMEM column map
-constexpr int kNumBars = 2 * kMaxAStages + 2 * kTA + 5;       // raw_full, raw_empty, ta_full, ta_empty, t_full[2], t_empty[2], w_full
+constexpr int kTA = 2;                                        // A stages in tensor memory
+constexpr int kAcc = 3;                                       // accumulator stages in tensor memory
+constexpr int kAccCols = 128, kTACol0 = kAcc * kAccCols, kTACols = 64;   // TMEM column map: 3 x 128 + 2 x 64 = 512
+constexpr int kNumBars = 2 * kMaxAStages + 2 * kTA + 2 * kAcc + 1;    // raw_full, raw_empty, ta_full, ta_empty, t_full, t_empty, w_full
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kAStageBytes = kTileM * kC * 4;                 // 32 KB: 128 raw fp32 rows
 constexpr int kHeaderBytes = 256;                             // workspace header in front of the W image
@@ -298,8 +299,8 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
   auto ta_full = [&](uint32_t s) { return bar0 + 8u * (2 * kMaxAStages + s); };
   auto ta_empty = [&](uint32_t s) { return bar0 + 8u * (2 * kMaxAStages + kTA + s); };
   auto t_full = [&](uint32_t s) { return bar0 + 8u * (2 * kMaxAStages + 2 * kTA + s); };
-  auto t_empty = [&](uint32_t s) { return bar0 + 8u * (2 * kMaxAStages + 2 * kTA + 2 + s); };
-  const uint32_t w_full = bar0 + 8u * (2 * kMaxAStages + 2 * kTA + 4);
+  auto t_empty = [&](uint32_t s) { return bar0 + 8u * (2 * kMaxAStages + 2 * kTA + kAcc + s); };
+  const uint32_t w_full = bar0 + 8u * (2 * kMaxAStages + 2 * kTA + 2 * kAcc);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int split = blockIdx.x % S, worker = blockIdx.x / S;
@@ -334,7 +335,7 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
       mbar_init(ta_full(s), 128);                            // converter threads
       mbar_init(ta_empty(s), 1);                             // tcgen05.commit
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kAcc; ++s) {
       mbar_init(t_full(s), 1);
       mbar_init(t_empty(s), kEpiWarps * 32);
     }
@@ -406,8 +407,8 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
         if (k + 1 < kt) fetch(tile, k + 1); else fetch(tile + n_workers, 0);
 #pragma unroll
         for (int chunk = 0; chunk < NCH; ++chunk) {
-          const uint32_t st = ct & 1;
-          mbar_wait(t_full(st), (ct >> 1) & 1);
+          const uint32_t st = ct % kAcc;
+          mbar_wait(t_full(st), (ct / kAcc) & 1);
           tc_fence_after();
 #ifdef FGNN_TC_TRACE
           if (chunk == 0 && warp == 0) TC_TRACE(ei, 6);
@@ -509,11 +510,12 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
           if (orow >= 0) {
             float4 v = stage[rr * CPR + ((cq & ~SW) | ((cq ^ rr) & SW))];
             float4* dst = reinterpret_cast<float4*>(obase + orow * p.o_sm);
-            if (p.accumulate) {
-              const float4 old = *dst;
-              v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+            if (p.accumulate) {                              // out += v without waiting on a load: one vector reduction
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                           : "memory");
+            } else {
+              *dst = v;
             }
-            *dst = v;
           }
         }
 #ifdef FGNN_TC_TRACE
@@ -636,8 +638,8 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
       const uint32_t a_hi = tmem_base + kTACol0 + ta * kTACols, a_lo = a_hi + 32;
 #pragma unroll
       for (int chunk = 0; chunk < NCH; ++chunk) {
-        const uint32_t ts = ct & 1;
-        mbar_wait(t_empty(ts), ((ct >> 1) & 1) ^ 1);
+        const uint32_t ts = ct % kAcc;
+        mbar_wait(t_empty(ts), ((ct / kAcc) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ts * kAccCols;
         const uint32_t b_hi = (sB_u + (uint32_t)chunk * NC * 128u) >> 4, b_lo = b_hi + ((uint32_t)COLS * 128u >> 4);

@@ -67,6 +67,29 @@ def clear_table_cache():
     _validated_tables.clear()
 
 
+# Asynchronous index checking (validate="async"): the scan kernel stores into pinned host memory that is
+# polled at the next call -- the error surfaces late but loudly, like the reference's CUDA device assert.
+_async_flag = None
+
+
+def _async_flag_tensor():
+    global _async_flag
+    if _async_flag is None:
+        _async_flag = torch.zeros(16, dtype=torch.int32).pin_memory()
+    return _async_flag
+
+
+def check_async_errors(synchronize=False):
+    """Raise IndexError if an asynchronous index check has fired since the last call."""
+    if _async_flag is None:
+        return
+    if synchronize:
+        torch.cuda.synchronize()
+    if int(_async_flag[0]) != 0:
+        _async_flag.zero_()
+        raise IndexError("fgnn_b200: an nn_idx entry was out of range in an earlier call (asynchronous index check)")
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -182,7 +205,18 @@ def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=Non
             raise IndexError("fgnn_b200: nn_idx entry out of range (no source nodes)")
         return out
 
-    if validate and not _table_seen(idx_user, N, mask_negative):
+    if validate == "async":
+        check_async_errors()
+        if not _table_seen(idx_user, N, mask_negative):
+            with torch.cuda.device(dev):
+                rc = lib.fgnn_check_index_range_async(
+                    _ptr(nn_idx), _lib.I64 if nn_idx.dtype == torch.int64 else _lib.I32,
+                    nn_idx.numel() if nn_idx.stride(0) != 0 else M * K, -(2 ** 63) if mask_negative else 0, N,
+                    ctypes.c_void_p(_async_flag_tensor().data_ptr()),
+                    ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            _lib.check(rc, "check_index_range_async")
+            _table_remember(idx_user, N, mask_negative)
+    elif validate and not _table_seen(idx_user, N, mask_negative):
         flag = torch.empty(2, dtype=torch.int32, device=dev)
         lo = -(2 ** 63) if mask_negative else 0
         with torch.cuda.device(dev):
@@ -282,6 +316,10 @@ class mp_conv_v2(base_mp_nn):
             if aggregtor is None:
                 self._agg = _lib.AGG_NONE
         self.kernel = _lib.KERNEL_AUTO
+        # how nn_idx is range-checked (the reference gets it from ATen's gather): True = synchronously the
+        # first time a table object is seen (exact IndexError at the call), "async" = scan without the
+        # round trip, error raised at a later call (the reference's CUDA behaviour), False = trust the caller
+        self.index_check = True
         self._ws = None
         self._nonce = int.from_bytes(os.urandom(5), "little")      # distinguishes modules that reuse freed addresses
 
@@ -329,7 +367,7 @@ class mp_conv_v2(base_mp_nn):
             bias=self.bias if (fuse_tail or not custom_agg) else None,
             bn_scale=scale, bn_shift=shift, extension=ext, aggregator=fused_agg,
             activation=act_code if fuse_tail else _lib.ACT_NONE, act_slope=slope,
-            kernel=self.kernel, workspace=ws,
+            kernel=self.kernel, workspace=ws, validate=self.index_check,
             filters_version=self._filters_version() if ws is not None else 0)
         if fuse_tail:
             return post_act(out) if post_act is not None else out

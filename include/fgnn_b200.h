@@ -146,6 +146,12 @@ int fgnn_mp_forward_host(const fgnn_mp_args* host_args);
 int fgnn_check_index_range(const void* idx, int idx_dtype, int64_t count, int64_t lo, int64_t n,
                            void* scratch, void* stream);
 
+/* The same check without the round trip: only launches the scan on `stream`; on a violation the kernel
+ * stores 1 to *flag (never cleared here).  `flag` may be device memory or pinned (mapped) host memory the
+ * caller polls later -- the reference's own CUDA behaviour is an asynchronous device-side assert. */
+int fgnn_check_index_range_async(const void* idx, int idx_dtype, int64_t count, int64_t lo, int64_t n,
+                                 int32_t* flag, void* stream);
+
 /* Elementwise epilogue out = act(bn(in + bias)) on a node-major [rows, O] buffer, used after the
  * cross-GPU max-all-reduce of the raw aggregate (the epilogue is non-linear, so it runs after the
  * reduce; reference mp_nn.py:165-173).  In-place allowed.  -inf inputs (no live slot on any shard)

@@ -89,6 +89,20 @@ def test_error_behaviour():
         mod(t(case["x"]), t(case["idx"][:1]), t(case["etype"]))
 
 
+def test_async_index_check_raises_late():
+    case = CASES[0]
+    mod = module_for(case)
+    mod.index_check = "async"
+    bad = case["idx"].copy()
+    bad[0, 0, 0] = case["x"].shape[2] + 3
+    with torch.no_grad():
+        mod(t(case["x"]), t(bad), t(case["etype"]))          # no error yet: the scan runs on the stream
+        with pytest.raises(IndexError):
+            fgnn_b200.check_async_errors(synchronize=True)
+        mod(t(case["x"]), t(case["idx"]), t(case["etype"]))  # flag was cleared: good tables pass
+        fgnn_b200.check_async_errors(synchronize=True)
+
+
 def test_custom_aggregator_and_train_mode_bn():
     case = next(c for c in CASES if c["meta"]["name"] == "ext0_max")
     m = case["meta"]
