@@ -28,6 +28,13 @@ def launch_count():
     return int(_lib.lib().fgnn_launch_count())
 
 
+def set_programmatic_launch(enabled=True):
+    """Programmatic dependent launch between consecutive tensor-core launches (default on): launch
+    i+1 overlaps its set-up with the tail of launch i and orders itself behind it before touching
+    x / out, so results do not change.  Returns the previous setting."""
+    return bool(_lib.lib().fgnn_set_programmatic_launch(1 if enabled else 0))
+
+
 def install(reference_mpnn=None):
     """Drop the native core into the reference package: after this call
     `lib.model.mpnn.mp_conv_v2` (and the copies `mp_nn_residual`, `factor_mpnn_sp`, `factor_mpnn`

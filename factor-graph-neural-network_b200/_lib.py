@@ -69,6 +69,7 @@ EXPORTS = {
                                           ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
                                           ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
     "fgnn_launch_count": (ctypes.c_uint64, []),
+    "fgnn_set_programmatic_launch": (ctypes.c_int, [ctypes.c_int]),
 }
 
 _lib = None

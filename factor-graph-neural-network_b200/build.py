@@ -34,12 +34,14 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False, trace=False):
+def build(force=False, verbose=False, trace=False, debug=False):
     """Compile the CUDA library if it is missing or older than its sources.  Returns its path.
     trace=True builds libfgnn_b200_trace.so with -DFGNN_TC_TRACE (per-item pipeline timestamps,
     tools/tc_trace.py); the product library never carries that code."""
     if trace:
         return _compile(LIB.replace(".so", "_trace.so"), verbose, ["-DFGNN_TC_TRACE"])
+    if debug:       # watchdog time-outs print the barrier they were waiting on before trapping
+        return _compile(LIB.replace(".so", "_debug.so"), verbose, ["-DFGNN_TC_DEBUG"])
     if not force and not _stale():
         return LIB
     return _compile(LIB, verbose, [])
@@ -64,4 +66,5 @@ def _compile(out, verbose, extra):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, trace="--trace" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, trace="--trace" in sys.argv,
+                debug="--debug" in sys.argv))

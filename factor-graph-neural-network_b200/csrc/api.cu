@@ -186,6 +186,13 @@ int fgnn_last_cuda_error(void) { return g_last_cuda_error; }
 
 uint64_t fgnn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+int fgnn_set_programmatic_launch(int enabled) {
+  static std::atomic<int> current{1};
+  const int prev = current.exchange(enabled ? 1 : 0);
+  tc_set_pdl(enabled != 0);
+  return prev;
+}
+
 int fgnn_mp_select_kernel(const fgnn_mp_args* a) {
   const int v = validate(a);
   if (v != FGNN_OK) return v;

@@ -76,5 +76,6 @@ int launch_mp_simt(const MpParams& p, cudaStream_t stream);
 bool tc_supported(const fgnn_mp_args* a);
 size_t tc_workspace_bytes(const fgnn_mp_args* a);
 int launch_mp_tc(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream);
+void tc_set_pdl(bool on);
 
 }  // namespace fgnn

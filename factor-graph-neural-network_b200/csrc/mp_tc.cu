@@ -1,4 +1,4 @@
-// tcgen05 / TMEM kernel for the FGNN message-passing call (NO_EXTENSION, C = 64, fp32 I/O).
+// tcgen05 / TMEM kernel for the FGNN message-passing call (NO_EXTENSION, C = 64; fp32 or bf16 I/O).
 //
 //   out[b,o,m] = act(BN(bias[o] + AGG_k sum_t etype[b,t,m,k] * (x[b, idx[b,m,k], :] . W[:, o*T+t])))
 //   reference: lib/model/mpnn/mp_nn.py:115-175 (the VF and the FV module of FGNN)
@@ -6,38 +6,54 @@
 // Formulation.  A destination tile = 128 consecutive (b,m) rows.  For every slot k the 128 source
 // rows x[idx[.,k]] form the A operand [128 x C]; the filters form the B operand [C x O*T]; one
 // UMMA M=128 accumulates H_k = A_k W into TMEM (fp32), NC columns at a time.  TMEM lane r == row r,
-// so epilogue thread r reads its own H_k row, contracts it with its slot's edge-type vector
-// (sum_t et[t] * H[o*T+t]) and folds the result into a running max / logsumexp / mean held in
-// registers: the K-reduction needs no shuffles and no shared memory, and nothing O*T wide ever
+// so an epilogue thread of row r reads its own H_k row, contracts it with its slot's edge-type
+// vector (sum_t et[t] * H[o*T+t]) and folds the result into a running max / logsumexp / mean held
+// in registers: the K-reduction needs no shuffles and no shared memory, and nothing O*T wide ever
 // reaches HBM (the reference materialises H, an int64 index expansion and the gathered rows).
 //
-// fp32 parity on bf16 tensor cores: both operands are split x = xh + xl, W = Wh + Wl (bf16 each)
-// and three MMAs xl*Wh + xh*Wl + xh*Wh accumulate in fp32 (error ~2^-16 relative, inside the
-// 1e-4 contract; plain TF32/bf16 is not -- SURVEY 7 hard part 2).
+// fp32 parity on bf16 tensor cores (fp32 I/O): both operands are split x = xh + xl, W = Wh + Wl
+// (bf16 each) and three MMAs xl*Wh + xh*Wl + xh*Wh accumulate in fp32 (error ~2^-16 relative,
+// inside the 1e-4 contract; plain TF32/bf16 is not -- SURVEY 7 hard part 2).
+// bf16 I/O (SURVEY 8d cfg 4: bf16 features / edge types / weights, fp32 accumulate): x rows are
+// the A operand as they are, W is rounded once to bf16, ONE MMA term; the filter image of all
+// O*T columns then fits one CTA at T = 16 (no column split across CTAs).
 //
 // Shared-memory bandwidth is the scarce resource (measured: with both operands in shared memory the
 // MMA reads 12 KB per 128-cycle instruction and runs at half rate while gather/convert starve), so
-// the A operand lives in TENSOR MEMORY: the converter threads write the split-bf16 rows straight
+// the A operand lives in TENSOR MEMORY: the converter threads write the (split-)bf16 rows straight
 // into TMEM with tcgen05.st (thread r == lane r == row r) and the MMA takes A from TMEM; shared
 // memory only carries the raw gather ring and the stationary filter slice.
 //
-// CTA roles (416 threads, 1 CTA / SM, persistent over tiles); an ITEM is one (tile, k):
-//   warps 0-3   epilogue    TMEM -> registers, edge-type contraction, aggregate, bias/BN/act, store;
-//                           the next item's edge-type vector is prefetched during the current one
-//   warps 4-7   converters  thread r: raw fp32 row r from the ring (conflict-free swizzled chunks) ->
-//                           bf16 hi/lo pairs -> tcgen05.st into the A stage in TMEM
-//   warps 8-11  gatherers   cp.async (LDGSTS) 16-byte chunks of the 128 source rows into the raw ring:
-//                           no register staging, every free ring stage's gather is in flight; the
-//                           item's indices are loaded one item ahead
-//   warp  12    MMA         one elected lane issues tcgen05.mma (A: TMEM, B: smem descriptor); owns the
+// CTA roles (512 threads = 4 warpgroups, 1 CTA / SM, persistent over tiles); an ITEM is one (tile, k):
+//   warps 0-7   epilogue    two groups of four warps; warps w and w+4 share TMEM lanes 32(w%4).. and
+//                           split every accumulator chunk's columns in halves (group 0: low half):
+//                           TMEM -> registers, edge-type contraction, aggregate; bias/BN/act and the
+//                           store go through a shared staging tile (both groups write their channels,
+//                           then share the line-sized stores); the next item's edge-type vector is
+//                           prefetched during the current one
+//   warps 8-11  converters  thread r: raw row r from the ring (conflict-free swizzled chunks) ->
+//                           bf16 hi/lo pairs (fp32 I/O) or as is (bf16 I/O) -> tcgen05.st into the A
+//                           stage in TMEM
+//   warps 12-13 gatherers   cp.async (LDGSTS) 16-byte chunks of the 128 source rows (64 per warp) into the
+//                           raw ring: no register staging, every free ring stage's gather is in flight;
+//                           the item's indices are loaded one item ahead
+//   warp  14    MMA         one elected lane issues tcgen05.mma (A: TMEM, B: smem descriptor); owns the
 //                           TMEM allocation; brings the stationary filter slice in with TMA bulk copies
+//   warp  15    idle        (setmaxnreg is a warpgroup-wide instruction: warps 12-15 release registers together)
 // TMEM (512 columns): 3 accumulator stages x 128 columns + 2 A stages x 64 columns (32 hi + 32 lo).
 // Pipelines (all mbarrier): raw ring raw_empty -> raw_full; A stages ta_empty -> ta_full;
 // accumulators t_empty -> t_full.
-// The filters are stationary: each CTA keeps the split-bf16 image of its column slice
-// (O*T / S columns, S = column split across CTAs so the slice fits in shared memory) for its
-// whole lifetime; the image is produced once per weight version by w_split_kernel.
+// The filters are stationary: each CTA keeps the bf16 image of its column slice (O*T / S columns,
+// S = column split across CTAs so the slice fits in shared memory) for its whole lifetime; the
+// image is produced once per weight version by w_split_kernel.
+//
+// Programmatic dependent launch: the kernel releases its dependents at once
+// (griddepcontrol.launch_dependents) and orders itself behind its predecessor only where it must
+// (griddepcontrol.wait before the first read of x and before the first store to out), so set-up,
+// filter load and index / edge-type prefetch of launch i+1 overlap the tail of launch i.
 #include <cuda_bf16.h>
+
+#include <cstdio>
 
 #include <mutex>
 #include <unordered_map>
@@ -65,24 +81,38 @@ namespace tc {
 
 constexpr int kC = 64;                 // input channels (K dimension of the MMA), one 128-byte swizzle atom
 constexpr int kTileM = 128;            // destinations per tile == UMMA M == TMEM lanes
-constexpr int kEpiWarps = 4, kGatherWarps = 4, kConvWarps = 4;
-constexpr int kMmaWarp = kEpiWarps + kGatherWarps + kConvWarps;
-constexpr int kThreads = (kMmaWarp + 1) * 32;                 // 416
+constexpr int kEpiGroups = 2;          // epilogue warp groups sharing the TMEM lanes, splitting the columns
+constexpr int kEpiWarps = 4 * kEpiGroups, kConvWarps = 4, kGatherWarps = 2;
+constexpr int kConvWarp0 = kEpiWarps, kGatherWarp0 = kConvWarp0 + kConvWarps;
+constexpr int kMmaWarp = kGatherWarp0 + kGatherWarps;
+constexpr int kThreads = 512;                                 // 16 warps: the last one only completes the fourth warpgroup
+static_assert(kMmaWarp == 14, "warps 12-15 must form one warpgroup");
 constexpr int kMaxAStages = 6;                                // raw ring stages in shared memory
 constexpr int kTA = 2;                                        // A stages in tensor memory
 constexpr int kAcc = 3;                                       // accumulator stages in tensor memory
 constexpr int kAccCols = 128, kTACol0 = kAcc * kAccCols, kTACols = 64;   // TMEM column map: 3 x 128 + 2 x 64 = 512
 constexpr int kNumBars = 2 * kMaxAStages + 2 * kTA + 2 * kAcc + 1;    // raw_full, raw_empty, ta_full, ta_empty, t_full, t_empty, w_full
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kAStageBytes = kTileM * kC * 4;                 // 32 KB: 128 raw fp32 rows
 constexpr int kHeaderBytes = 256;                             // workspace header in front of the W image
-constexpr uint32_t kSpinLimit = 1u << 20;                     // watchdog: trap instead of hanging the GPU
+constexpr uint32_t kSpinLimit = 1u << 22;                     // watchdog: trap instead of hanging the GPU
 
 struct Header {                       // first bytes of the workspace
   int64_t version;                    // fgnn_mp_args.filters_version the image was built from
   const float* filters;               // and the pointer it was built from
   int32_t C, OT;
 };
+
+// shared-memory geometry, by I/O type (xb: bf16 I/O)
+__host__ __device__ constexpr int row_bytes(bool xb) { return xb ? kC * 2 : kC * 4; }          // one source row in the ring
+__host__ __device__ constexpr int stage_bytes(bool xb) { return kTileM * row_bytes(xb); }       // 16 / 32 KB
+__host__ __device__ constexpr int w_bytes(int cols, bool xb) { return (xb ? 1 : 2) * cols * 128; }   // hi (+ lo) image rows
+__host__ __device__ constexpr int out_tile_bytes(int ch, bool xb) { return kTileM * ch * (xb ? 2 : 4); }
+// raw-ring stages that fit beside a filter slice of `cols` columns and the output staging tile of `ch`
+// channels (plus 1 KB alignment slack, barriers, epilogue params)
+__host__ __device__ constexpr int a_stages(int cols, int ch, bool xb) {
+  int n = (kSmemBudget - 1024 - w_bytes(cols, xb) - out_tile_bytes(ch, xb) - 2048) / stage_bytes(xb);
+  return n > kMaxAStages ? kMaxAStages : n;
+}
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -107,7 +137,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
-    if (++spins > kSpinLimit) __trap();
+    if (++spins > kSpinLimit) {
+#ifdef FGNN_TC_DEBUG
+      printf("fgnn mbar timeout: block %d thread %d barrier+%u parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
+             bar & 0xfffu, parity);
+#endif
+      __trap();
+    }
   }
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -131,8 +167,10 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
 // one lane of a converged warp (warp-uniform control flow keeps descriptors in uniform registers)
@@ -143,9 +181,6 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -163,16 +198,6 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate, M=128, N from idesc, K=16
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -206,6 +231,13 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// named barrier over `count` threads (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+// programmatic dependent launch (no-ops when the launch carries no programmatic dependency)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_128B, rows of 128 bytes (64 bf16), 8-row groups
 // 1024 bytes apart (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
@@ -220,27 +252,26 @@ __host__ __device__ constexpr uint32_t umma_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
 
-// Register re-balancing between warp groups (warps 0-3 epilogue, 4-7 producers): the kernel is
-// compiled for 128 registers/thread (416 threads); setmaxnreg moves registers WITHIN the CTA's
-// launch allocation (416 x 128 = 53248), so 128*200 (epilogue) + 128*120 (converters) + 128*56
-// (gatherers) + 32*128 (MMA warp) = 52224 must fit in it -- an over-subscribed inc never returns.
+// Register re-balancing between the warp roles.  setmaxnreg is executed by whole WARPGROUPS (four
+// consecutive warps, all with the same value): warpgroups 0-1 = epilogue, 2 = converters, 3 = gatherers +
+// MMA warp + one idle warp.  With setmaxnreg in the code ptxas gives the kernel
+// floor(65536 / threads / 32) * 32 registers per thread at launch (probed: 128 for 416..512 threads, 96 for
+// 544).  The instruction moves registers WITHIN the CTA's launch allocation (512 x 128 = 65536), so
+// 256*160 (epilogue) + 128*120 (converters) + 128*72 (warpgroup 3) = 65536 must fit in it -- an
+// over-subscribed inc never returns; the host checks the launch register count of every instantiation
+// before its first launch.
+constexpr int kRegEpi = 160, kRegConv = 120, kRegAux = 72, kRegLaunch = 128;
+static_assert(kEpiWarps * 32 * kRegEpi + kConvWarps * 32 * kRegConv + 4 * 32 * kRegAux <= kThreads * kRegLaunch,
+              "setmaxnreg budget exceeds the launch allocation");
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-
-// raw-ring stages that fit beside a filter slice of `cols` columns and the output staging tile of `ch`
-// channels (plus 1 KB alignment slack, barriers, epilogue params)
-__host__ __device__ constexpr int a_stages(int cols, int ch) {
-  int n = (kSmemBudget - 1024 - 2 * cols * 128 - kTileM * ch * 4 - 2048) / kAStageBytes;
-  return n > kMaxAStages ? kMaxAStages : n;
-}
-
-__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------
 // filters [C, O*T] fp32 -> split-bf16 image in the UMMA B layout (K-major rows of 64 bf16 = 128 B,
-// 16-byte chunks XOR-swizzled with row % 8): image[part][n][c], n = column o*T+t.
+// 16-byte chunks XOR-swizzled with row % 8): image[part][n][c], n = column o*T+t; part 0 = bf16(W)
+// (all the bf16-I/O kernel uses), part 1 = bf16(W - part 0).
 // ---------------------------------------------------------------------------------------------
 __global__ void w_split_kernel(const float* __restrict__ W, uint8_t* __restrict__ ws, int OT, int64_t version) {
   tc::Header* h = reinterpret_cast<tc::Header*>(ws);
@@ -271,9 +302,9 @@ __global__ void w_split_kernel(const float* __restrict__ W, uint8_t* __restrict_
 // ---------------------------------------------------------------------------------------------
 // main kernel
 //   T   edge types (columns per output channel)        NC  accumulator columns per MMA chunk
-//   NCH chunks per CTA (CTA column slice = NC*NCH)     AGG aggregator
+//   NCH chunks per CTA (CTA column slice = NC*NCH)     AGG aggregator      XB  bf16 x / etype / out
 // ---------------------------------------------------------------------------------------------
-template <int T, int NC, int NCH, int AGG>
+template <int T, int NC, int NCH, int AGG, bool XB>
 __global__ void __launch_bounds__(tc::kThreads, 1)
 mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, const int n_workers,
              const int n_tiles) {
@@ -281,16 +312,23 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
   constexpr int COLS = NC * NCH;               // columns of W this CTA owns
   constexpr int CH = COLS / T;                 // output channels this CTA owns
   constexpr int CH_PER_LD = 16 / T;            // channels per 16-column TMEM load
-  constexpr int NST = a_stages(COLS, CH);      // raw-ring stages that fit beside the filter slice and the output tile
-  static_assert(NC % 16 == 0 && NC <= kAccCols && 16 % T == 0 && CH <= 64 && NST >= 2, "unsupported shape");
+  constexpr int NLD = NC / (16 * kEpiGroups);  // 16-column loads per chunk per epilogue group
+  constexpr int CPG = NC / (T * kEpiGroups);   // channels per chunk per epilogue group
+  constexpr int CHG = CPG * NCH;               // channels (accumulator registers) per epilogue thread
+  constexpr int NST = a_stages(COLS, CH, XB);  // raw-ring stages that fit beside the filter slice and the output tile
+  constexpr int ROWB = row_bytes(XB), STAGEB = stage_bytes(XB);
+  constexpr int OB = XB ? 2 : 4;               // bytes per output element
+  constexpr int NTERMS = XB ? 1 : 3;           // MMA terms per K step
+  static_assert(NC % (16 * kEpiGroups) == 0 && NC <= kAccCols && 16 % T == 0 && CH <= 64 && NST >= 2 && CPG % 4 == 0 &&
+                    (CH * OB) % 32 == 0, "unsupported shape");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1 KB alignment by OFFSET (not by integer round-trip) so the compiler keeps the shared state space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sB = smem;                                        // [2 parts][COLS rows][128 B]   UMMA K-major SW128
-  uint8_t* sA = sB + 2 * COLS * 128;                         // [NST][128 rows][256 B]        raw fp32 ring
-  uint8_t* sOut = sA + NST * kAStageBytes;                   // [4 warps][32 rows][CH floats]  output staging (swizzled chunks)
-  float* s_epi = reinterpret_cast<float*>(sOut + kTileM * CH * 4);    // [3][64]: bias, BN scale, BN shift (16-byte aligned)
+  uint8_t* sB = smem;                                        // [1|2 parts][COLS rows][128 B]  UMMA K-major SW128
+  uint8_t* sA = sB + w_bytes(COLS, XB);                      // [NST][128 rows][ROWB]          raw ring
+  uint8_t* sOut = sA + NST * STAGEB;                         // [4 quarters][32 rows][CH*OB]   output staging (swizzled chunks)
+  float* s_epi = reinterpret_cast<float*>(sOut + out_tile_bytes(CH, XB));   // [3][64]: bias, BN scale, BN shift (16-byte aligned)
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + 3 * 64);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   const uint32_t bar0 = smem_u32(bars);
@@ -312,7 +350,6 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
   auto split_row = [&](uint32_t g, uint32_t& b, uint32_t& m) {
     if (p.B == 1) { b = 0; m = g; } else { b = g / Mu; m = g - b * Mu; }
   };
-  const int my_tiles = worker < n_tiles ? (n_tiles - worker + n_workers - 1) / n_workers : 0;
   // slots evaluated in a tile: K, or the tile's own count for compacted shard-local tables
   auto slots_of = [&](int tile) -> int { return p.tile_k ? (tile < n_tiles ? p.tile_k[tile] : 0) : p.K; };
   // this CTA's items (tile, k) in order: tile = worker + j*n_workers, k < slots_of(tile)
@@ -323,12 +360,12 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
   auto next_item = [&](ItemIter& it) {
     if (++it.k >= it.kt) { it.k = 0; it.tile += n_workers; it.kt = slots_of(it.tile); }
   };
-  (void)my_tiles;
 
   // ---- one-time setup ---------------------------------------------------------------------
+  pdl_launch_dependents();                                   // the next launch may begin its own set-up now
   if (tid == 0) {
     for (int s = 0; s < kMaxAStages; ++s) {
-      mbar_init(raw_full(s), 128);                           // gather threads (cp.async arrive-on)
+      mbar_init(raw_full(s), kGatherWarps * 32);             // gather threads (cp.async arrive-on)
       mbar_init(raw_empty(s), 128);                          // converter threads
     }
     for (int s = 0; s < kTA; ++s) {
@@ -355,11 +392,13 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
 
   if (warp < kEpiWarps) {
     // =====================================================================================
-    // EPILOGUE: thread r owns destination row (tile*128 + r) and TMEM lane r
+    // EPILOGUE: warps w and w+4 own destination rows tile*128 + 32*(w%4) .. +31 == TMEM lanes
+    // 32*(w%4) .. +31; group eg = w/4 takes the columns [eg*NC/2, (eg+1)*NC/2) of every chunk
     // =====================================================================================
-    reg_inc<200>();
-    const int r = tid;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    reg_inc<kRegEpi>();
+    const int eg = warp >> 2, wq = warp & 3;
+    const int r = wq * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(eg * (NC / kEpiGroups));
     const int64_t et_st = (int64_t)p.M * p.K;                // stride between edge types
     // edge-type vector + liveness of item (tile j, slot k) for this thread's row
     float et_nx[T];
@@ -369,33 +408,44 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
       const bool ok = tile < n_tiles && g < rows_total;
       uint32_t b = 0, m = 0;
       if (ok) split_row(g, b, m);
-      const float* pe = p.et + (int64_t)b * p.et_sb + (int64_t)m * p.K + k;
+      const int64_t e0 = (int64_t)b * p.et_sb + (int64_t)m * p.K + k;
+      if (XB) {
+        const unsigned short* pe = reinterpret_cast<const unsigned short*>(p.et) + e0;
 #pragma unroll
-      for (int t = 0; t < T; ++t) {
-        et_nx[t] = ok ? __ldg(pe) : 0.f;
-        pe += et_st;
+        for (int t = 0; t < T; ++t) {
+          et_nx[t] = ok ? __uint_as_float((uint32_t)__ldg(pe) << 16) : 0.f;
+          pe += et_st;
+        }
+      } else {
+        const float* pe = p.et + e0;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          et_nx[t] = ok ? __ldg(pe) : 0.f;
+          pe += et_st;
+        }
       }
       live_nx = ok;
       if (ok && p.mask_neg) live_nx = load_index(p.idx, p.idx64, (int64_t)b * p.idx_sb + (int64_t)m * p.K + k) >= 0;
     };
     fetch(worker, 0);
     uint32_t ct = 0;
+    bool waited = false;
 #ifdef FGNN_TC_TRACE
     uint32_t ei = 0;
 #endif
     for (int tile = worker; tile < n_tiles; tile += n_workers) {
-      float acc[CH];                                         // max | running max of gamma*e | sum
-      float acc2[AGG == FGNN_AGG_SOFTMAX ? CH : 1];          // softmax: running sum of exp
+      float acc[CHG];                                        // max | running max of gamma*e | sum
+      float acc2[AGG == FGNN_AGG_SOFTMAX ? CHG : 1];         // softmax: running sum of exp
       float live_count = 0.f;
 #pragma unroll
-      for (int c = 0; c < CH; ++c) acc[c] = (AGG == FGNN_AGG_MEAN) ? 0.f : -INFINITY;
+      for (int c = 0; c < CHG; ++c) acc[c] = (AGG == FGNN_AGG_MEAN) ? 0.f : -INFINITY;
 #pragma unroll
-      for (int c = 0; c < (AGG == FGNN_AGG_SOFTMAX ? CH : 1); ++c) acc2[c] = 0.f;
+      for (int c = 0; c < (AGG == FGNN_AGG_SOFTMAX ? CHG : 1); ++c) acc2[c] = 0.f;
       const int kt = slots_of(tile);
-      // output row of tile row (warp*32 + lane), fetched now so the finish phase never waits on it
+      // output row of tile row (wq*32 + lane), fetched now so the finish phase never waits on it
       int32_t my_orow = -1;
       {
-        const uint32_t go = (uint32_t)tile * kTileM + warp * 32 + lane;
+        const uint32_t go = (uint32_t)tile * kTileM + r;
         if (go < rows_total) my_orow = p.out_rows ? p.out_rows[go] : (int32_t)go;
       }
       for (int k = 0; k < kt; ++k) {
@@ -417,9 +467,9 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
           uint32_t d[2][16];
           tmem_ld16(taddr, d[0]);
 #pragma unroll
-          for (int gq = 0; gq < NC / 16; ++gq) {
+          for (int gq = 0; gq < NLD; ++gq) {
             tmem_ld_wait();
-            if (gq + 1 < NC / 16) tmem_ld16(taddr + (gq + 1) * 16, d[(gq + 1) & 1]);
+            if (gq + 1 < NLD) tmem_ld16(taddr + (gq + 1) * 16, d[(gq + 1) & 1]);
 #pragma unroll
             for (int q = 0; q < CH_PER_LD; ++q) {
               float e;
@@ -438,7 +488,7 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
 #pragma unroll
                 for (int t = 0; t < T; ++t) e = fmaf(et[t], __uint_as_float(d[gq & 1][q * T + t]), e);
               }
-              const int c = chunk * (NC / T) + gq * CH_PER_LD + q;
+              const int c = chunk * CPG + gq * CH_PER_LD + q;
               if (AGG == FGNN_AGG_MAX) {
                 acc[c] = live ? fmaxf(acc[c], e) : acc[c];
               } else if (AGG == FGNN_AGG_SOFTMAX) {
@@ -462,60 +512,90 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
 #endif
         live_count += live ? 1.f : 0.f;
       }
-      // finish: aggregate, bias / eval-BN / activation (mp_nn.py:162-173) into this warp's staging
+      // finish: aggregate, bias / eval-BN / activation (mp_nn.py:162-173) into this quarter's staging
       // rows (16-byte chunk c of row rr at position c ^ (rr & SW): conflict-free both ways) ...
       {
-        constexpr int CPR = CH / 4;                          // 16-byte chunks per output row
+        constexpr int CPR = CH * OB / 16;                    // 16-byte chunks per output row
         constexpr int SW = (CPR < 8 ? CPR : 8) - 1;          // chunk-index bits XOR-ed with the row
-        float4* stage = reinterpret_cast<float4*>(sOut) + warp * (32 * CPR);   // this warp's [32 rows][CPR chunks]
+        uint8_t* stage = sOut + wq * (32 * CPR * 16);        // this quarter's [32 rows][CPR chunks]
         const float4* epi4 = reinterpret_cast<const float4*>(s_epi);
         const float inv_gamma = 1.f / p.gamma, inv_live = live_count > 0.f ? 1.f / live_count : 0.f;
         // negative-side slope of the activation: 1 = none, 0 = ReLU, slope = LeakyReLU
         const float neg = p.act == FGNN_ACT_NONE ? 1.f : (p.act == FGNN_ACT_RELU ? 0.f : p.slope);
-        __syncwarp();                                        // previous tile's read-back is complete
+        named_bar_sync(1 + wq, 64);                          // both warps of the quarter are done reading the previous tile
 #ifdef FGNN_TC_TRACE
         if (warp == 0) TC_TRACE(ei - 1, 8);
 #endif
 #pragma unroll
-        for (int c4 = 0; c4 < CH; c4 += 4) {
-          const float4 bi = epi4[c4 >> 2], sc = epi4[(CH + c4) >> 2], sh = epi4[(2 * CH + c4) >> 2];
-          const float bia[4] = {bi.x, bi.y, bi.z, bi.w}, sca[4] = {sc.x, sc.y, sc.z, sc.w}, shi[4] = {sh.x, sh.y, sh.z, sh.w};
-          float v[4];
+        for (int chunk = 0; chunk < NCH; ++chunk) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int c = c4 + j;
-            float a;
-            if (AGG == FGNN_AGG_MAX) a = acc[c];
-            else if (AGG == FGNN_AGG_SOFTMAX) a = live_count > 0.f ? (logf(acc2[c]) + acc[c]) * inv_gamma : -INFINITY;
-            else a = acc[c] * inv_live;
-            float y = fmaf(a + bia[j], sca[j], shi[j]);      // bias, then eval BN folded to scale/shift
-            y = y >= 0.f ? y : y * neg;
-            v[j] = a == -INFINITY ? a : y;                   // no live slot on this shard: stay -inf
+          for (int j4 = 0; j4 < CPG; j4 += 4) {
+            const int la = chunk * CPG + j4;                 // first of four accumulators (compile time)
+            const int c4 = chunk * (NC / T) + j4;            // + eg*CPG: first of four CTA-local channels
+            const int cc = c4 + eg * CPG;
+            const float4 bi = epi4[cc >> 2], sc = epi4[(CH + cc) >> 2], sh = epi4[(2 * CH + cc) >> 2];
+            const float bia[4] = {bi.x, bi.y, bi.z, bi.w}, sca[4] = {sc.x, sc.y, sc.z, sc.w}, shi[4] = {sh.x, sh.y, sh.z, sh.w};
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a;
+              if (AGG == FGNN_AGG_MAX) a = acc[la + j];
+              else if (AGG == FGNN_AGG_SOFTMAX) a = live_count > 0.f ? (logf(acc2[la + j]) + acc[la + j]) * inv_gamma : -INFINITY;
+              else a = acc[la + j] * inv_live;
+              float y = fmaf(a + bia[j], sca[j], shi[j]);    // bias, then eval BN folded to scale/shift
+              y = y >= 0.f ? y : y * neg;
+              v[j] = a == -INFINITY ? a : y;                 // no live slot on this shard: stay -inf
+            }
+            const int byte0 = cc * OB, ck = byte0 >> 4, within = byte0 & 15;
+            uint8_t* dst = stage + lane * (CPR * 16) + (((ck & ~SW) | ((ck ^ lane) & SW)) << 4) + within;
+            if (XB) {
+              *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(__floats2bfloat162_rn(v[0], v[1])),
+                                                          pack_bf16(__floats2bfloat162_rn(v[2], v[3])));
+            } else {
+              *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            }
           }
-          stage[lane * CPR + (((c4 >> 2) & ~SW) | (((c4 >> 2) ^ lane) & SW))] = make_float4(v[0], v[1], v[2], v[3]);
         }
-        __syncwarp();
+        named_bar_sync(1 + wq, 64);                          // both groups' channels are staged
 #ifdef FGNN_TC_TRACE
         if (warp == 0) TC_TRACE(ei - 1, 9);
 #endif
-        // ... then whole 128-byte lines go out: CPR lanes per row, 32/CPR rows per store instruction
-        // (out is batch-contiguous node-major, so flattened row g lives at out + g * o_sm)
-        constexpr int RPI = 32 / CPR;
+        if (!waited) { pdl_wait(); waited = true; }          // first store: the preceding launch (a reader of out) is complete
+        // ... then whole lines go out: CPR lanes per row, 32/CPR rows per store instruction, the two
+        // warps of the quarter alternate (out is batch-contiguous node-major: row g at out + g * o_sm)
+        constexpr int RPI = 32 / CPR, NSI = CPR / 2;         // rows per store instruction, store instructions per warp
         const int cq = lane % CPR, rsub = lane / CPR;
-        float* obase = p.out + ch0 + cq * 4;
+        uint8_t* obase = reinterpret_cast<uint8_t*>(p.out) + (size_t)ch0 * OB + cq * 16;
+        const uint32_t ostride = (uint32_t)p.o_sm * OB;      // bytes per output row (< 2^31, tc_supported)
+        int32_t orow[NSI];
+        uint4 ov[NSI];
 #pragma unroll
-        for (int it = 0; it < CPR; ++it) {
-          const int rr = it * RPI + rsub;
-          const int64_t orow = __shfl_sync(0xffffffffu, my_orow, rr);   // flattened output row (out is batch-contiguous)
-          if (orow >= 0) {
-            float4 v = stage[rr * CPR + ((cq & ~SW) | ((cq ^ rr) & SW))];
-            float4* dst = reinterpret_cast<float4*>(obase + orow * p.o_sm);
-            if (p.accumulate) {                              // out += v without waiting on a load: one vector reduction
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                           : "memory");
-            } else {
-              *dst = v;
+        for (int i2 = 0; i2 < NSI; ++i2) {                   // warp eg of the quarter: store instructions 2*i2 + eg
+          const int rr = (2 * i2 + eg) * RPI + rsub;
+          orow[i2] = __shfl_sync(0xffffffffu, my_orow, rr);  // flattened output row (out is batch-contiguous)
+          ov[i2] = *reinterpret_cast<const uint4*>(stage + rr * (CPR * 16) + (((cq & ~SW) | ((cq ^ rr) & SW)) << 4));
+        }
+        if (p.accumulate) {                                  // out += v without waiting on a load: one vector reduction
+#pragma unroll
+          for (int i2 = 0; i2 < NSI; ++i2) {
+            uint8_t* dst = obase + (uint64_t)(uint32_t)orow[i2] * ostride;
+            const uint4 v = ov[i2];
+            if (orow[i2] >= 0) {
+              if (XB) {
+                asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                             : "memory");
+              } else {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(v.x)),
+                             "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                             : "memory");
+              }
             }
+          }
+        } else {
+#pragma unroll
+          for (int i2 = 0; i2 < NSI; ++i2) {
+            uint8_t* dst = obase + (uint64_t)(uint32_t)orow[i2] * ostride;
+            if (orow[i2] >= 0) *reinterpret_cast<uint4*>(dst) = ov[i2];
           }
         }
 #ifdef FGNN_TC_TRACE
@@ -523,14 +603,14 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
 #endif
       }
     }
-  } else if (warp < kEpiWarps + kConvWarps) {
+  } else if (warp < kGatherWarp0) {
     // =====================================================================================
-    // CONVERTERS: thread cr == TMEM lane cr == row cr of every item.  raw fp32 row (ring) ->
-    // split bf16 -> A stage in tensor memory (32 columns of hi pairs, 32 columns of lo pairs)
+    // CONVERTERS: thread cr == TMEM lane cr == row cr of every item.  raw row (ring) -> A stage in
+    // tensor memory: fp32 I/O 32 columns of hi pairs + 32 columns of lo pairs, bf16 I/O 32 columns
     // =====================================================================================
-    reg_dec<120>();
-    const int cr = tid - kEpiWarps * 32;
-    const uint32_t row_u = smem_u32(sA) + (uint32_t)cr * 256u;
+    reg_dec<kRegConv>();
+    const int cr = tid - kConvWarp0 * 32;
+    const uint32_t row_u = smem_u32(sA) + (uint32_t)cr * ROWB;
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTACol0;
     uint32_t i = 0;
     for (ItemIter it = first_item(); it.tile < n_tiles; next_item(it), ++i) {
@@ -538,89 +618,134 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
       const uint32_t ta = i % kTA, tuse = i / kTA;
       mbar_wait(raw_full(st), use & 1);
       if (cr < 32) TC_TRACE(i, 2);
-      float4 v[16];                                          // channels 4c .. 4c+3 in chunk c (stored at c ^ (row & 15))
+      if (XB) {
+        uint32_t a[32];                                      // channels 8c .. 8c+7 in chunk c (stored at c ^ (row & 7))
 #pragma unroll
-      for (int c = 0; c < 16; ++c) v[c] = lds_f4(row_u + st * kAStageBytes + (uint32_t)((c ^ (cr & 15)) * 16));
-      uint32_t hi[32], lo[32];
+        for (int c = 0; c < 8; ++c) {
+          const uint4 v = lds_u4(row_u + st * STAGEB + (uint32_t)((c ^ (cr & 7)) * 16));
+          a[4 * c] = v.x; a[4 * c + 1] = v.y; a[4 * c + 2] = v.z; a[4 * c + 3] = v.w;
+        }
+        mbar_arrive(raw_empty(st));                          // ring stage is free again
+        mbar_wait(ta_empty(ta), (tuse & 1) ^ 1);
+        tc_fence_after();
+        tmem_st32(lane_addr + ta * kTACols, a);
+      } else {
+        float4 v[16];                                        // channels 4c .. 4c+3 in chunk c (stored at c ^ (row & 15))
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[c].x, v[c].y), h1 = __floats2bfloat162_rn(v[c].z, v[c].w);
-        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-        hi[2 * c] = pack_bf16(h0);
-        hi[2 * c + 1] = pack_bf16(h1);
-        lo[2 * c] = pack_bf16(__floats2bfloat162_rn(v[c].x - f0.x, v[c].y - f0.y));
-        lo[2 * c + 1] = pack_bf16(__floats2bfloat162_rn(v[c].z - f1.x, v[c].w - f1.y));
+        for (int c = 0; c < 16; ++c) v[c] = lds_f4(row_u + st * STAGEB + (uint32_t)((c ^ (cr & 15)) * 16));
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[c].x, v[c].y), h1 = __floats2bfloat162_rn(v[c].z, v[c].w);
+          const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+          hi[2 * c] = pack_bf16(h0);
+          hi[2 * c + 1] = pack_bf16(h1);
+          lo[2 * c] = pack_bf16(__floats2bfloat162_rn(v[c].x - f0.x, v[c].y - f0.y));
+          lo[2 * c + 1] = pack_bf16(__floats2bfloat162_rn(v[c].z - f1.x, v[c].w - f1.y));
+        }
+        mbar_arrive(raw_empty(st));                          // ring stage is free again: every chunk has been consumed above
+        mbar_wait(ta_empty(ta), (tuse & 1) ^ 1);
+        tc_fence_after();
+        tmem_st32(lane_addr + ta * kTACols, hi);
+        tmem_st32(lane_addr + ta * kTACols + 32, lo);
       }
-      mbar_arrive(raw_empty(st));                            // ring stage is free again: every chunk has been consumed above
-      mbar_wait(ta_empty(ta), (tuse & 1) ^ 1);
-      tc_fence_after();
-      tmem_st32(lane_addr + ta * kTACols, hi);
-      tmem_st32(lane_addr + ta * kTACols + 32, lo);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(ta_full(ta));
       if (cr < 32) TC_TRACE(i, 3);
     }
-  } else if (warp < kMmaWarp) {
+  } else {
+  reg_dec<kRegAux>();                                        // warps 12-15 together (one warpgroup)
+  if (warp < kMmaWarp) {
     // =====================================================================================
     // GATHERERS: cp.async the 128 source rows of every item into the raw ring
     // =====================================================================================
-    reg_dec<56>();
-    const int pw = warp - (kEpiWarps + kConvWarps);          // rows pw*32 .. pw*32+31 of the tile
-    const int sub = lane >> 4, q = lane & 15;                // 16 lanes x 16 B = one 256-byte row
-    // index-table entry of the row this lane owns (row pw*32+lane of item i's tile); the load is
+    constexpr int LPR = ROWB / 16;                           // lanes per source row (16-byte chunks): 16 | 8
+    constexpr int RPW = 32 / LPR;                            // rows per warp instruction: 2 | 4
+    constexpr int ROWS_W = kTileM / kGatherWarps;            // rows per gather warp: 64
+    constexpr int IPL = ROWS_W / 32;                         // index-table entries per lane: 2
+    const int pw = warp - kGatherWarp0;                      // rows pw*64 .. pw*64+63 of the tile
+    const int sub = lane / LPR, q = lane % LPR;
+    // source rows (b*N + n, -1 = none) of tile rows pw*64 + j*32 + lane of an item; the index loads are
     // issued one item ahead and only CONSUMED (range check -> source row) after the stage wait
-    auto index_of = [&](const ItemIter& it, int32_t& base) -> int64_t {
-      base = -1;
-      if (it.tile >= n_tiles) return -1;
-      const uint32_t g = (uint32_t)it.tile * kTileM + pw * 32 + lane;
-      if (g >= rows_total) return -1;
-      uint32_t b, m;
-      split_row(g, b, m);
-      base = (int32_t)(b * (uint32_t)p.N);
-      return load_index(p.idx, p.idx64, (int64_t)b * p.idx_sb + (int64_t)m * p.K + it.k);
+    struct Idx {
+      int64_t n[IPL];
+      int32_t base[IPL];
     };
-    const float* xq = p.x + q * 4;
+    auto index_of = [&](const ItemIter& it, Idx& v) {
+#pragma unroll
+      for (int j = 0; j < IPL; ++j) {
+        v.base[j] = -1;
+        v.n[j] = -1;
+        if (it.tile >= n_tiles) continue;
+        const uint32_t g = (uint32_t)it.tile * kTileM + pw * ROWS_W + j * 32 + lane;
+        if (g >= rows_total) continue;
+        uint32_t b, m;
+        split_row(g, b, m);
+        v.base[j] = (int32_t)(b * (uint32_t)p.N);
+        v.n[j] = load_index(p.idx, p.idx64, (int64_t)b * p.idx_sb + (int64_t)m * p.K + it.k);
+      }
+    };
+    const uint8_t* xq = reinterpret_cast<const uint8_t*>(p.x) + q * 16;
     const uint32_t sA_u = smem_u32(sA);
-    int32_t base, base_next;
+    // Warp instruction u (of NIT per item) copies chunk q of the RPW rows RPW*u + sub of this warp's 64:
+    // chunk q of tile row rr lands at position q ^ (rr & (LPR-1)) (the converter's per-row reads are then
+    // conflict-free).  The swizzle term repeats every NDO instructions, so the shared-memory offset is one
+    // of NDO lane constants plus a compile-time multiple of LPR rows.
+    constexpr int NIT = ROWS_W / RPW, NDO = LPR / RPW;
+    uint32_t dst_off[NDO];
+#pragma unroll
+    for (int c = 0; c < NDO; ++c)
+      dst_off[c] = (uint32_t)(pw * ROWS_W + RPW * c + sub) * ROWB + (uint32_t)((q ^ ((RPW * c + sub) & (LPR - 1))) * 16);
+    Idx cur, nxt;
     ItemIter it = first_item();
-    int64_t n = index_of(it, base);
+    index_of(it, cur);
+    pdl_wait();                                              // x is the preceding launch's output: order behind it
     for (uint32_t i = 0; it.tile < n_tiles; ++i) {
       const uint32_t st = i % NST, use = i / NST;
       next_item(it);
-      const int64_t n_next = index_of(it, base_next);        // index load of the next item: in flight during this one
+      index_of(it, nxt);                                     // index loads of the next item: in flight during this one
       mbar_wait(raw_empty(st), (use & 1) ^ 1);
       if (pw == 0) TC_TRACE(i, 0);
-      // source row (b*N + n; x is batch-contiguous, checked by tc_supported); -1 = no row (tile tail,
-      // masked or out-of-range slot) -> zero-filled
-      const int32_t src = (base >= 0 && n >= 0 && n < p.N) ? base + (int32_t)n : -1;
-      const uint32_t stage = sA_u + st * kAStageBytes;
+      // byte offset of the source row in x ((b*N + n) * ROWB < 2^32, checked by tc_supported); ~0 = no row
+      // (tile tail, masked or out-of-range slot) -> zero-filled
+      uint32_t off[IPL];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const int rw = 2 * u + sub;
-        const int32_t row = __shfl_sync(0xffffffffu, src, rw);
-        const int rr = pw * 32 + rw;
-        // chunk q of row rr at position q ^ (rr & 15): the converter's per-row reads are conflict-free
-        const uint32_t dst = stage + (uint32_t)rr * 256u + (uint32_t)((q ^ (rr & 15)) * 16);
-        cp_async16(dst, xq + (int64_t)(row >= 0 ? row : 0) * kC, row >= 0 ? 16u : 0u);
+      for (int j = 0; j < IPL; ++j)
+        off[j] = (cur.base[j] >= 0 && cur.n[j] >= 0 && cur.n[j] < p.N) ? (uint32_t)(cur.base[j] + (int32_t)cur.n[j]) * ROWB
+                                                                       : 0xffffffffu;
+      const uint32_t stage = sA_u + st * STAGEB;
+#pragma unroll
+      for (int u0 = 0; u0 < NIT; u0 += 8) {                  // batches of 8: all shuffles first, then the copies
+        uint32_t o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = __shfl_sync(0xffffffffu, off[(RPW * (u0 + j)) / 32], (RPW * (u0 + j) + sub) & 31);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int u = u0 + j;
+          const uint32_t dst = stage + dst_off[u % NDO] + (uint32_t)((u / NDO) * LPR * ROWB);
+          const bool ok = o[j] != 0xffffffffu;
+          cp_async16(dst, xq + (ok ? o[j] : 0u), ok ? 16u : 0u);
+        }
       }
       cp_async_arrive_noinc(raw_full(st));
       if (pw == 0) TC_TRACE(i, 1);
-      n = n_next;
-      base = base_next;
+      cur = nxt;
     }
-  } else {
+  } else if (warp == kMmaWarp) {
     // =====================================================================================
     // MMA ISSUER: the whole warp runs the loop (warp-uniform control flow, so addresses and
     // descriptors live in uniform registers); one elected lane issues.  First: the stationary
-    // B operand (this CTA's column slice of the split-bf16 filter image) by TMA bulk copy.
+    // B operand (this CTA's column slice of the bf16 filter image) by TMA bulk copy.
     // =====================================================================================
     const uint32_t sB_u = smem_u32(sB);
     if (elect_one()) {
       const int OT = p.O * p.T;
       constexpr uint32_t part = COLS * 128, piece = part < 32768u ? part : 32768u;
-      mbar_expect_tx(w_full, 2 * part);
-      for (int h = 0; h < 2; ++h) {
+      constexpr int parts = XB ? 1 : 2;
+      mbar_expect_tx(w_full, parts * part);
+      for (int h = 0; h < parts; ++h) {
         const uint8_t* src = wimg + kHeaderBytes + (size_t)h * OT * 128 + (size_t)col0 * 128;
         for (uint32_t o = 0; o < part; o += piece) bulk_g2s(sB_u + h * part + o, src + o, piece, w_full);
       }
@@ -645,9 +770,9 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
         const uint32_t b_hi = (sB_u + (uint32_t)chunk * NC * 128u) >> 4, b_lo = b_hi + ((uint32_t)COLS * 128u >> 4);
         if (elect_one()) {
 #pragma unroll
-          for (int term = 0; term < 3; ++term) {             // xl*Wh + xh*Wl + xh*Wh
-            const uint32_t a = term == 0 ? a_lo : a_hi;
-            const uint32_t bb = term == 1 ? b_lo : b_hi;
+          for (int term = 0; term < NTERMS; ++term) {        // fp32 I/O: xl*Wh + xh*Wl + xh*Wh; bf16 I/O: x*Wh
+            const uint32_t a = (!XB && term == 0) ? a_lo : a_hi;
+            const uint32_t bb = (!XB && term == 1) ? b_lo : b_hi;
 #pragma unroll
             for (int ks = 0; ks < kC / 16; ++ks)             // 16 bf16 of K = 8 TMEM columns of A = 32 bytes of a B row
               umma_bf16_ts(d_tmem, a + ks * 8, desc_hi | (uint64_t)(bb + ks * 2), idesc, (term | ks) != 0);
@@ -660,6 +785,7 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
       }
       TC_TRACE(i, 5);
     }
+  }
   }
 
   // ---- teardown -----------------------------------------------------------------------------
@@ -681,15 +807,16 @@ struct TcConfig {
   bool ok;
 };
 
-TcConfig pick_config(int T, int agg, int OT) {
-  // accumulator chunks of NC <= 128 columns (TMEM: 2 x 128 accumulator + 4 x 64 A-stage columns);
-  // channels per CTA (NC*NCH/T) <= 64 for max/mean, <= 32 for softmax (two registers per channel)
+TcConfig pick_config(int T, int agg, int OT, bool xb) {
+  // accumulator chunks of NC <= 128 columns (TMEM: 3 x 128 accumulator + 2 x 64 A-stage columns);
+  // channels per CTA (NC*NCH/T) <= 64; accumulator registers per epilogue thread = half of that
+  // (twice for softmax).  bf16 I/O: the image has one part, so twice the columns fit a CTA.
   const bool sm = agg == FGNN_AGG_SOFTMAX;
   TcConfig c{T, 128, 1, false};
   switch (T) {
-    case 16: c.NCH = sm ? 2 : 4; break;          // 16 / 32 channels
-    case 8: c.NCH = 2; break;                    // 32 channels
-    case 4: c.NCH = sm ? 1 : 2; break;           // 32 / 64 channels
+    case 16: c.NCH = xb ? (sm ? 4 : 8) : (sm ? 2 : 4); break;   // bf16: 32 / 64 channels, fp32: 16 / 32
+    case 8: c.NCH = xb ? (sm ? 2 : 4) : 2; break;               // bf16: 32 / 64 channels, fp32: 32
+    case 4: c.NCH = sm ? 1 : 2; break;                          // 32 / 64 channels
     case 2: c.NCH = 1; c.NC = sm ? 64 : 128; break;
     case 1: c.NC = sm ? 32 : 64; break;
     default: return c;
@@ -698,34 +825,57 @@ TcConfig pick_config(int T, int agg, int OT) {
   return c;
 }
 
-size_t smem_bytes(const TcConfig& c) {
+size_t smem_bytes(const TcConfig& c, bool xb) {
   const int cols = c.NC * c.NCH, ch = cols / c.T;
-  return 1024 + (size_t)2 * cols * 128 + (size_t)tc::a_stages(cols, ch) * tc::kAStageBytes +
-         (size_t)tc::kTileM * ch * 4 + tc::kNumBars * 8 + 16 + 3 * 64 * 4;
+  return 1024 + (size_t)tc::w_bytes(cols, xb) + (size_t)tc::a_stages(cols, ch, xb) * tc::stage_bytes(xb) +
+         (size_t)tc::out_tile_bytes(ch, xb) + tc::kNumBars * 8 + 16 + 3 * 64 * 4;
 }
 
-template <int T, int NC, int NCH, int AGG>
+bool g_pdl = true;      // programmatic dependent launch between consecutive tensor-core launches
+
+template <int T, int NC, int NCH, int AGG, bool XB>
 int launch_one(const MpParams& p, const uint8_t* wimg, int S, int workers, int tiles, size_t smem, cudaStream_t st) {
-  auto kern = mp_tc_kernel<T, NC, NCH, AGG>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return FGNN_ERR_CUDA;
-  kern<<<S * workers, tc::kThreads, smem, st>>>(p, wimg, S, workers, tiles);
+  auto kern = mp_tc_kernel<T, NC, NCH, AGG, XB>;
+  static bool attr_set = false;                              // per instantiation; the value never changes
+  if (!attr_set) {
+    // the in-kernel setmaxnreg budget assumes the launch register count ptxas chose (see tc::kRegLaunch):
+    // refuse to launch a build that breaks it instead of hanging in setmaxnreg.inc
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) return FGNN_ERR_CUDA;
+    if (fa.numRegs != tc::kRegLaunch) return FGNN_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return FGNN_ERR_CUDA;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(S * workers));
+  cfg.blockDim = dim3(tc::kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p, wimg, S, workers, tiles);
   count_launch();
-  return cudaGetLastError() == cudaSuccess ? (int)FGNN_OK : (int)FGNN_ERR_CUDA;
+  return e == cudaSuccess ? (int)FGNN_OK : (int)FGNN_ERR_CUDA;
 }
 
-// NCm/NCHm: max & mean configuration, NCs/NCHs: softmax configuration (must mirror pick_config)
-template <int T, int NCm, int NCHm, int NCs, int NCHs>
+// NCHm: chunks per CTA for max & mean, NCHs: for softmax (must mirror pick_config)
+template <int T, int NCm, int NCHm, int NCs, int NCHs, bool XB>
 int launch_agg(const MpParams& p, const uint8_t* wimg, int S, int workers, int tiles, size_t smem, cudaStream_t st) {
   switch (p.agg) {
-    case FGNN_AGG_MAX: return launch_one<T, NCm, NCHm, FGNN_AGG_MAX>(p, wimg, S, workers, tiles, smem, st);
-    case FGNN_AGG_SOFTMAX: return launch_one<T, NCs, NCHs, FGNN_AGG_SOFTMAX>(p, wimg, S, workers, tiles, smem, st);
-    case FGNN_AGG_MEAN: return launch_one<T, NCm, NCHm, FGNN_AGG_MEAN>(p, wimg, S, workers, tiles, smem, st);
+    case FGNN_AGG_MAX: return launch_one<T, NCm, NCHm, FGNN_AGG_MAX, XB>(p, wimg, S, workers, tiles, smem, st);
+    case FGNN_AGG_SOFTMAX: return launch_one<T, NCs, NCHs, FGNN_AGG_SOFTMAX, XB>(p, wimg, S, workers, tiles, smem, st);
+    case FGNN_AGG_MEAN: return launch_one<T, NCm, NCHm, FGNN_AGG_MEAN, XB>(p, wimg, S, workers, tiles, smem, st);
   }
   return FGNN_ERR_UNSUPPORTED;
 }
 
 }  // namespace
+
+void tc_set_pdl(bool on) { g_pdl = on; }
 
 #ifdef FGNN_TC_TRACE
 extern "C" int fgnn_debug_trace_read(unsigned long long* host, size_t count) {
@@ -734,19 +884,22 @@ extern "C" int fgnn_debug_trace_read(unsigned long long* host, size_t count) {
 #endif
 
 bool tc_supported(const fgnn_mp_args* a) {
-  if (a->extension != FGNN_NO_EXTENSION || a->dtype != FGNN_F32) return false;
+  if (a->extension != FGNN_NO_EXTENSION) return false;
+  if (a->dtype != FGNN_F32 && a->dtype != FGNN_BF16) return false;
+  const bool xb = a->dtype == FGNN_BF16;
   if (a->C != tc::kC) return false;
   if (a->aggregator == FGNN_AGG_NONE) return false;
   if (a->x_sc != 1 || a->x_sn != a->C) return false;                              // node-major rows
   if (a->B > 1 && a->x_sb != (int64_t)a->N * a->C) return false;                  // batch-contiguous
-  if ((int64_t)a->B * a->N >= INT32_MAX) return false;
+  if ((int64_t)a->B * a->N * tc::row_bytes(xb) >= (int64_t)UINT32_MAX) return false;   // 32-bit source byte offsets
+  if (a->out_sm * (xb ? 2 : 4) >= (int64_t)INT32_MAX) return false;
   if ((reinterpret_cast<uintptr_t>(a->x) & 15) || (reinterpret_cast<uintptr_t>(a->out) & 15)) return false;
-  if (a->out_so != 1 || (a->out_sm & 3)) return false;
+  if (a->out_so != 1 || (a->out_sm & (xb ? 7 : 3))) return false;                   // 16-byte aligned output rows
   if (a->B > 1 && a->out_sb != (int64_t)a->M * a->out_sm) return false;             // batch-contiguous rows
-  if (a->O % 4) return false;
-  const TcConfig c = pick_config(a->T, a->aggregator, a->O * a->T);
+  if (a->O % (xb ? 8 : 4)) return false;
+  const TcConfig c = pick_config(a->T, a->aggregator, a->O * a->T, xb);
   if (!c.ok) return false;
-  if (smem_bytes(c) > (size_t)tc::kSmemBudget || tc::a_stages(c.NC * c.NCH, c.NC * c.NCH / c.T) < 2) return false;
+  if (smem_bytes(c, xb) > (size_t)tc::kSmemBudget || tc::a_stages(c.NC * c.NCH, c.NC * c.NCH / c.T, xb) < 2) return false;
   if ((int64_t)a->B * a->M >= (int64_t)INT32_MAX - 256) return false;
   return true;
 }
@@ -756,7 +909,8 @@ size_t tc_workspace_bytes(const fgnn_mp_args* a) {
 }
 
 int launch_mp_tc(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream) {
-  TcConfig c = pick_config(p.T, p.agg, p.O * p.T);
+  const bool xb = a->dtype == FGNN_BF16;
+  TcConfig c = pick_config(p.T, p.agg, p.O * p.T, xb);
   if (!c.ok) return FGNN_ERR_UNSUPPORTED;
   uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
   if (reinterpret_cast<uintptr_t>(ws) & 255) return FGNN_ERR_WORKSPACE;
@@ -803,13 +957,23 @@ int launch_mp_tc(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream) 
   if (S > sms) return FGNN_ERR_UNSUPPORTED;
   int workers = sms / S;
   if (workers > tiles) workers = tiles;
-  const size_t smem = smem_bytes(c);
-  switch (p.T) {
-    case 16: return launch_agg<16, 128, 4, 128, 2>(p, ws, S, workers, tiles, smem, stream);
-    case 8: return launch_agg<8, 128, 2, 128, 2>(p, ws, S, workers, tiles, smem, stream);
-    case 4: return launch_agg<4, 128, 2, 128, 1>(p, ws, S, workers, tiles, smem, stream);
-    case 2: return launch_agg<2, 128, 1, 64, 1>(p, ws, S, workers, tiles, smem, stream);
-    case 1: return launch_agg<1, 64, 1, 32, 1>(p, ws, S, workers, tiles, smem, stream);
+  const size_t smem = smem_bytes(c, xb);
+  if (xb) {
+    switch (p.T) {
+      case 16: return launch_agg<16, 128, 8, 128, 4, true>(p, ws, S, workers, tiles, smem, stream);
+      case 8: return launch_agg<8, 128, 4, 128, 2, true>(p, ws, S, workers, tiles, smem, stream);
+      case 4: return launch_agg<4, 128, 2, 128, 1, true>(p, ws, S, workers, tiles, smem, stream);
+      case 2: return launch_agg<2, 128, 1, 64, 1, true>(p, ws, S, workers, tiles, smem, stream);
+      case 1: return launch_agg<1, 64, 1, 32, 1, true>(p, ws, S, workers, tiles, smem, stream);
+    }
+  } else {
+    switch (p.T) {
+      case 16: return launch_agg<16, 128, 4, 128, 2, false>(p, ws, S, workers, tiles, smem, stream);
+      case 8: return launch_agg<8, 128, 2, 128, 2, false>(p, ws, S, workers, tiles, smem, stream);
+      case 4: return launch_agg<4, 128, 2, 128, 1, false>(p, ws, S, workers, tiles, smem, stream);
+      case 2: return launch_agg<2, 128, 1, 64, 1, false>(p, ws, S, workers, tiles, smem, stream);
+      case 1: return launch_agg<1, 64, 1, 32, 1, false>(p, ws, S, workers, tiles, smem, stream);
+    }
   }
   return FGNN_ERR_UNSUPPORTED;
 }

@@ -173,6 +173,12 @@ int fgnn_epilogue_sum_forward(const float* in, float* out, int64_t rows, int32_t
 int fgnn_to_node_major(const float* x, float* out, int32_t B, int32_t C, int32_t N, int64_t x_sb,
                        int64_t x_sc, int64_t x_sn, void* stream);
 
+/* Programmatic dependent launch between consecutive tensor-core launches on a stream (default on):
+ * launch i+1 may start its set-up, filter load and index / edge-type prefetch while launch i drains;
+ * it orders itself behind launch i before its first read of x and its first store to out, so results
+ * do not change.  Returns the previous setting.  Process-wide; not a per-call option. */
+int fgnn_set_programmatic_launch(int enabled);
+
 /* Number of kernels this library has launched since load (all threads). */
 uint64_t fgnn_launch_count(void);
 

@@ -251,6 +251,113 @@ def test_seeded_vs_oracle(shape, agg):
     assert_close(y.cpu().numpy(), ref, RTOL, f"{shape} {agg}")
 
 
+def _bf16_round(a):
+    """fp32 array rounded to the nearest bf16 value (still fp32), as torch does it."""
+    return torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).float().numpy()
+
+
+BF16_RTOL = 8e-3      # bf16 output: half an ulp is 2^-9 = 2e-3 of the value; the rest is the epilogue's scale/shift
+
+
+@pytest.mark.parametrize("shape", [
+    dict(B=1, N=5000, M=15000, K=2, C=64, O=64, T=16),     # cfg-4 V2F pairwise shape (scaled)
+    dict(B=1, N=15000, M=5000, K=6, C=64, O=64, T=16),     # cfg-4 F2V pairwise
+    dict(B=1, N=5000, M=2500, K=4, C=64, O=64, T=16),      # cfg-4 V2F order-4
+    dict(B=1, N=5000, M=15000, K=2, C=64, O=64, T=4),
+    dict(B=1, N=900, M=1001, K=3, C=64, O=64, T=8),
+    dict(B=3, N=130, M=257, K=5, C=64, O=64, T=1),
+    dict(B=2, N=130, M=300, K=2, C=64, O=64, T=2),
+    dict(B=1, N=300, M=500, K=2, C=64, O=128, T=16),
+], ids=lambda s: "B{B}_N{N}_M{M}_K{K}_C{C}_O{O}_T{T}".format(**s))
+@pytest.mark.parametrize("agg", ["max", "softmax", "mean"])
+def test_bf16_io_vs_oracle(shape, agg):
+    """bf16 features / edge types / output (SURVEY 8d cfg 4): the oracle runs in fp32 on the bf16-rounded
+    inputs and bf16-rounded filters (the kernel rounds the filters once, accumulates in fp32); the
+    result differs by the bf16 rounding of the output and summation order only."""
+    rng = np.random.default_rng(hash((shape["M"], shape["K"], shape["T"], 7)) & 0xffff)
+    x, idx, et, W, bias, bn = _random_call(rng, **shape)
+    x, et = _bf16_round(x), _bf16_round(et)
+    ref = orc.mp_conv_forward_c(x, idx, et, _bf16_round(W), bias, bn, extension=0, aggregator=agg)
+    scale = (bn["weight"] / np.sqrt(bn["running_var"] + 1e-5)).astype(np.float32)
+    shift = (bn["bias"] - bn["running_mean"] * scale).astype(np.float32)
+    xt = t(x).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    before = fgnn_b200.launch_count()
+    y = fgnn_b200.mp_forward(xt, t(idx), t(et).to(torch.bfloat16), t(W), t(bias), t(scale), t(shift), extension=0,
+                             aggregator={"max": 0, "softmax": 1, "mean": 2}[agg], kernel=_lib.KERNEL_TCGEN05)
+    assert fgnn_b200.launch_count() > before
+    assert y.dtype == torch.bfloat16 and y.stride(1) == 1
+    assert_close(y.float().cpu().numpy(), ref, BF16_RTOL, f"bf16 {shape} {agg}")
+
+
+def test_bf16_accumulate_and_masked():
+    rng = np.random.default_rng(3)
+    x, idx, et, W, bias, bn = _random_call(rng, B=1, N=700, M=900, K=4, C=64, O=64, T=16, pad_frac=0.0)
+    x, et = _bf16_round(x), _bf16_round(et)
+    idx[rng.random(idx.shape) < 0.3] = -1
+    idx[:, :, 0] = np.abs(idx[:, :, 0])                  # every destination keeps one live slot
+    scale = (bn["weight"] / np.sqrt(bn["running_var"] + 1e-5)).astype(np.float32)
+    shift = (bn["bias"] - bn["running_mean"] * scale).astype(np.float32)
+    args = (t(x).to(torch.bfloat16).contiguous(memory_format=torch.channels_last), t(idx), t(et).to(torch.bfloat16),
+            t(W), t(bias), t(scale), t(shift))
+    y = fgnn_b200.mp_forward(*args, extension=0, aggregator=0, mask_negative=True)
+    # reference: masked slots never win the max -- give them an edge type that makes them lose
+    et_m = et.copy()
+    live = idx >= 0
+    ref_rows = []
+    refs = orc.mp_conv_forward_c(x, np.where(live, idx, 0), et_m, _bf16_round(W), None, None, extension=0,
+                                 aggregator=None, activation=None)          # [B,O,M,K] raw messages
+    raw = np.where(live[:, None], refs, -np.inf).max(3, keepdims=True)
+    ref = np.maximum((raw + bias.reshape(1, -1, 1, 1)) * scale.reshape(1, -1, 1, 1) + shift.reshape(1, -1, 1, 1), 0)
+    assert_close(y.float().cpu().numpy(), ref, BF16_RTOL, "bf16 masked")
+    base = torch.full_like(y, 0.5)
+    acc = base.clone()
+    fgnn_b200.mp_forward(*args, extension=0, aggregator=0, mask_negative=True, out=acc, accumulate=True)
+    assert_close(acc.float().cpu().numpy(), (y.float() + 0.5).cpu().numpy(), BF16_RTOL, "bf16 accumulate")
+
+
+def test_programmatic_launch_chain_bit_identical():
+    """Back-to-back dependent launches (layer l+1 gathers what layer l stored, ping-pong buffers, the
+    F->V call accumulating into what the previous call wrote) give bit-identical results with
+    programmatic dependent launch on and off."""
+    rng = np.random.default_rng(21)
+    N, F, K, Kv, C, T = 6000, 18000, 2, 6, 64, 16
+    g = graphs.synthetic_map_graph(N, F, 0, 3, seed=4)[0]
+    x_v = t(rng.random((1, N, C), dtype=np.float32))
+    x_f = t(np.abs(rng.standard_normal((1, F, C))).astype(np.float32))
+    et_v2f = t(rng.standard_normal((1, T, F, K)).astype(np.float32))
+    et_f2v = t(rng.standard_normal((1, T, N, g.kv)).astype(np.float32))
+    idx_v2f, idx_f2v = t(g.idx_v2f[None]), t(g.idx_f2v[None])
+    Ws = [t((rng.uniform(-1, 1, (C, C * T)) * 0.1).astype(np.float32)) for _ in range(2)]
+    bias = t(rng.uniform(0, 0.05, C).astype(np.float32))
+    nm = lambda a: a.permute(0, 2, 1).unsqueeze(-1)
+    wsb = [torch.zeros(C * C * T * 4 + 4096, dtype=torch.uint8, device=DEV) for _ in range(2)]
+
+    def chain():
+        bv = [x_v.clone(), torch.empty_like(x_v)]
+        bf = [x_f.clone(), torch.empty_like(x_f)]
+        for l in range(4):
+            s, d = l & 1, (l + 1) & 1
+            fgnn_b200.mp_forward(nm(bv[s]), idx_v2f, et_v2f, Ws[0], bias, None, None, extension=0, aggregator=0,
+                                 out=nm(bf[d]), workspace=wsb[0], filters_version=1)
+            fgnn_b200.mp_forward(nm(bf[s]), idx_f2v, et_f2v, Ws[1], bias, None, None, extension=0, aggregator=0,
+                                 out=nm(bv[d]), workspace=wsb[1], filters_version=2)
+            fgnn_b200.mp_forward(nm(bf[s]), idx_f2v, et_f2v, Ws[1], bias, None, None, extension=0, aggregator=0,
+                                 out=nm(bv[d]), accumulate=True, workspace=wsb[1], filters_version=2)
+        torch.cuda.synchronize()
+        return bv[0].clone(), bf[0].clone()
+
+    prev = fgnn_b200.set_programmatic_launch(False)
+    try:
+        ref_v, ref_f = chain()
+        fgnn_b200.set_programmatic_launch(True)
+        for _ in range(3):
+            got_v, got_f = chain()
+            assert torch.equal(got_v, ref_v) and torch.equal(got_f, ref_f)
+    finally:
+        fgnn_b200.set_programmatic_launch(prev)
+    assert torch.isfinite(ref_v).all() and float(ref_v.abs().max()) > 0
+
+
 def test_masked_slots_and_epilogue_split_equal_fused():
     """Shard-local tables: negative indices are empty slots excluded from the max; the
     raw aggregate of two half-tables, max-combined and passed through fgnn_epilogue_forward,

@@ -64,14 +64,45 @@ def run(B, N, M, K, T, agg=0, O=64, C=64, seed=0, oracle=True, mask=False):
     return err <= 1e-4
 
 
-def timeit(B, N, M, K, T, kernel, reps=10):
+def run_bf16(B, N, M, K, T, agg=0, O=64, seed=0):
+    """bf16 I/O kernel against the C oracle on the bf16-rounded inputs / filters."""
+    rng = np.random.default_rng(seed)
+    r16 = lambda a: torch.from_numpy(a).to(torch.bfloat16).float().numpy()
+    x = r16(rng.standard_normal((B, N, 64)).astype(np.float32))
+    idx = rng.integers(0, N, (B, M, K))
+    et = r16(rng.standard_normal((B, T, M, K)).astype(np.float32))
+    W = (rng.uniform(-1, 1, (64, O * T)) * 0.1).astype(np.float32)
+    bias = rng.uniform(-0.2, 0.2, O).astype(np.float32)
+    xt = torch.from_numpy(x).to(dev).to(torch.bfloat16).permute(0, 2, 1).unsqueeze(-1)
+    try:
+        y = fgnn_b200.mp_forward(xt, torch.from_numpy(idx).to(dev), torch.from_numpy(et).to(dev).to(torch.bfloat16),
+                                 torch.from_numpy(W).to(dev), torch.from_numpy(bias).to(dev), None, None, extension=0,
+                                 aggregator=agg, kernel=_lib.KERNEL_TCGEN05)
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        print(f"bf16 B{B} N{N} M{M} K{K} T{T} agg{agg}: FAILED: {e}")
+        return False
+    ref = orc.mp_conv_forward_c(np.ascontiguousarray(x.transpose(0, 2, 1))[..., None], idx, et, r16(W), bias, None,
+                                extension=0, aggregator={0: "max", 1: "softmax", 2: "mean"}[agg])
+    a = y.float().cpu().numpy()
+    scale_ = max(np.abs(ref).max(), 1e-30)
+    err = np.abs(a - ref).max() / scale_
+    print(f"bf16 B{B} N{N} M{M} K{K} T{T} O{O} agg{agg}: tc-vs-oracle rel err {err:.3e} (scale {scale_:.3f})", flush=True)
+    if not err <= 8e-3:
+        bad = np.argwhere(~(np.abs(a - ref) <= 8e-3 * scale_))
+        print(f"   BAD elements {len(bad)} of {a.size}; first {bad[:5].tolist()}; rows {np.unique(bad[:, 2])[:10]} "
+              f"channels {np.unique(bad[:, 1])[:16]}")
+    return err <= 8e-3
+
+
+def timeit(B, N, M, K, T, kernel, reps=10, dtype=torch.float32):
     rng = np.random.default_rng(0)
-    x = torch.randn(B, N, 64, device=dev).permute(0, 2, 1).unsqueeze(-1)
+    x = torch.randn(B, N, 64, device=dev).to(dtype).permute(0, 2, 1).unsqueeze(-1)
     idx = torch.from_numpy(rng.integers(0, N, (B, M, K))).to(dev)
-    et = torch.randn(B, T, M, K, device=dev)
+    et = torch.randn(B, T, M, K, device=dev).to(dtype)
     W = torch.randn(64, 64 * T, device=dev) * 0.1
     bias = torch.zeros(64, device=dev)
-    out = torch.empty(B, 64, M, 1, device=dev, memory_format=torch.channels_last)
+    out = torch.empty(B, 64, M, 1, device=dev, dtype=dtype, memory_format=torch.channels_last)
     ws = torch.zeros(64 * 64 * T * 4 + 4096, dtype=torch.uint8, device=dev)
     f = lambda: fgnn_b200.mp_forward(x, idx, et, W, bias, None, None, extension=0, aggregator=0, kernel=kernel, out=out,
                                      workspace=ws, filters_version=7)
@@ -85,8 +116,9 @@ def timeit(B, N, M, K, T, kernel, reps=10):
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / reps * 1e3
-    byt = 4 * M * K * B + 4 * T * M * K * B + 4 * 64 * N * B + 4 * 64 * M * B
-    print(f"time B{B} N{N} M{M} K{K} T{T} kernel{kernel}: {us:9.1f} us  {B * M * K / us:8.1f} Mslots/s  "
+    sz = 2 if dtype == torch.bfloat16 else 4
+    byt = 4 * M * K * B + sz * T * M * K * B + sz * 64 * N * B + sz * 64 * M * B
+    print(f"time {'bf16' if sz == 2 else 'fp32'} B{B} N{N} M{M} K{K} T{T} kernel{kernel}: {us:9.1f} us  {B * M * K / us:8.1f} Mslots/s  "
           f"{byt / us / 1e3:7.1f} GB/s algorithmic", flush=True)
 
 
@@ -110,9 +142,25 @@ if __name__ == "__main__":
     ok &= run(1, 5000, 20000, 3, 16, agg=2)
     ok &= run(1, 500, 3000, 4, 16, mask=True)
     ok &= run(1, 500, 3000, 4, 4, O=128)
+    ok &= run_bf16(1, 200, 128, 1, 16)
+    ok &= run_bf16(1, 300, 1000, 3, 16)
+    ok &= run_bf16(1, 300, 1000, 3, 4)
+    ok &= run_bf16(1, 300, 1000, 3, 8)
+    ok &= run_bf16(2, 300, 1000, 3, 1)
+    ok &= run_bf16(1, 300, 1000, 3, 2, agg=2)
+    ok &= run_bf16(1, 5000, 20000, 6, 16, agg=1)
+    ok &= run_bf16(1, 500, 3000, 4, 16, O=128)
     print("ALL OK" if ok else "SOME FAILED")
     if "--big" in sys.argv or ok:
+        for pdl in (True, False):
+            fgnn_b200.set_programmatic_launch(pdl)
+            print(f"programmatic launch {'on' if pdl else 'off'}")
+            for T in (16, 4):
+                for (N, M, K) in ((100_000, 300_000, 2), (300_000, 100_000, 6), (100_000, 50_000, 3), (50_000, 100_000, 2)):
+                    timeit(1, N, M, K, T, _lib.KERNEL_TCGEN05)
+        fgnn_b200.set_programmatic_launch(True)
         for T in (16, 4):
-            for (N, M, K) in ((100_000, 300_000, 2), (300_000, 100_000, 6)):
-                timeit(1, N, M, K, T, _lib.KERNEL_TCGEN05)
-        timeit(1, 100_000, 300_000, 2, 16, _lib.KERNEL_SIMT, reps=3)
+            for (N, M, K) in ((100_000, 300_000, 2), (300_000, 100_000, 6), (1_000_000, 3_000_000, 2)):
+                timeit(1, N, M, K, T, _lib.KERNEL_TCGEN05, dtype=torch.bfloat16)
+        timeit(4096, 96, 48, 6, 4, _lib.KERNEL_TCGEN05)
+        timeit(4096, 48, 96, 3, 4, _lib.KERNEL_TCGEN05)
