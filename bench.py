@@ -55,6 +55,9 @@ def parse_args():
     ap.add_argument("--dim", type=int, default=64)
     ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--local-band", type=int, default=0, help="0 = uniform-random incidence (primary)")
+    ap.add_argument("--src-calls", default="auto",
+                    help="which core calls run source-stationary (one row-product per source row, csrc/mp_src.cu): "
+                         "'auto' (fan-out rule of mp_conv_v2), 'none', or a comma list of v2f<j>/f2v<j> (j = factor type)")
     ap.add_argument("--cpu-sample-scale", type=int, default=2, help="cpu_baseline runs on 1/scale of the graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -303,10 +306,23 @@ def run_native(args):
     buf_v = [torch.empty_like(d_in["x_v"]) for _ in range(2)]
     buf_f = [[torch.empty_like(x) for x in d_in["x_f"]] for _ in range(2)]
 
-    def call(x, idx, et, w, out, accumulate, wsb, ver):
+    # source-stationary plans of the index tables (static across layers and steps: built once, outside the
+    # timed region, like the reference's own table construction)
+    plans = {}
+    if plan is None and args.src_calls != "none" and kernel != _lib.KERNEL_SIMT and C == 64 and args.edge_types in (4, 8, 16):
+        rule = fgnn_b200.mp_conv_v2.AUTO_FAN_OUT[args.edge_types]
+        for j, ty in enumerate(types):
+            for name, idx, n_src in (("v2f%d" % j, d_in["idx_v2f"][j], ty.n_vars), ("f2v%d" % j, d_in["idx_f2v"][j], ty.n_factors)):
+                fan = idx.numel() / n_src
+                if (args.src_calls == "auto" and fan >= rule) or name in args.src_calls.split(","):
+                    sp = fgnn_b200.SourcePlan(idx, n_src)
+                    if args.src_calls != "auto" or sp.max_fan_out <= fgnn_b200.mp_conv_v2.AUTO_MAX_FAN_OUT:
+                        plans[name] = sp        # auto: not for tables with hub sources (the reference's pad target)
+
+    def call(x, idx, et, w, out, accumulate, wsb, ver, name=None):
         fgnn_b200.mp_forward(nm(x), idx, et, w["filters"], w["bias"], w["scale"], w["shift"], extension=0,
                              aggregator=_lib.AGG_MAX, activation=_lib.ACT_RELU, kernel=kernel, out=nm(out),
-                             accumulate=accumulate, workspace=wsb, filters_version=ver)
+                             accumulate=accumulate, workspace=wsb, filters_version=ver, plan=plans.get(name))
 
     def step(src):
         """src: dict of device tensors (x_v, x_f, tables).  Returns the final variable features."""
@@ -317,8 +333,8 @@ def run_native(args):
                 plan.layer(x_v, x_f, src["et_v2f"], src["et_f2v"], W[l], nv, nf, kernel, ws[l])
             else:
                 for j in range(J):
-                    call(x_v, src["idx_v2f"][j], src["et_v2f"][j], W[l][j]["v2f"], nf[j], False, ws[l][j]["v2f"], ws[l][j]["ver_v2f"])
-                    call(x_f[j], src["idx_f2v"][j], src["et_f2v"][j], W[l][j]["f2v"], nv, j > 0, ws[l][j]["f2v"], ws[l][j]["ver_f2v"])
+                    call(x_v, src["idx_v2f"][j], src["et_v2f"][j], W[l][j]["v2f"], nf[j], False, ws[l][j]["v2f"], ws[l][j]["ver_v2f"], "v2f%d" % j)
+                    call(x_f[j], src["idx_f2v"][j], src["et_f2v"][j], W[l][j]["f2v"], nv, j > 0, ws[l][j]["f2v"], ws[l][j]["ver_f2v"], "f2v%d" % j)
             x_v, x_f = nv, nf
         return x_v
 
@@ -457,7 +473,7 @@ def run_native(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "messages_per_layer": msgs_layer, "layers": L,
-                   "kernel": args.kernel, "l2": "per-step working set (~%d MB/layer) exceeds the 126 MB L2; no explicit flush"
+                   "kernel": args.kernel, "source_stationary_calls": sorted(plans), "l2": "per-step working set (~%d MB/layer) exceeds the 126 MB L2; no explicit flush"
                    % (bytes_layer // 1_000_000), "parallelism": ("factor-sharded x%d + NCCL max-all-reduce per layer" % world)
                    if world > 1 else "single GPU"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -42,6 +42,8 @@ class MpArgs(ctypes.Structure):
         ("filters_version", ctypes.c_int64),
         ("tile_slots", ctypes.c_void_p), ("out_rows", ctypes.c_void_p),
         ("sm_limit", ctypes.c_int32), ("reserved_", ctypes.c_int32),
+        ("src_ptr", ctypes.c_void_p), ("slot_edge", ctypes.c_void_p), ("etype_edges", ctypes.c_void_p),
+        ("messages", ctypes.c_void_p), ("n_edges", ctypes.c_int64),
     ]
 
 
@@ -68,6 +70,10 @@ EXPORTS = {
     "fgnn_to_node_major": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                           ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
                                           ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
+    "fgnn_mp_src_supported": (ctypes.c_int, [ctypes.POINTER(MpArgs)]),
+    "fgnn_src_permute_etype": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
+                                              ctypes.c_void_p]),
     "fgnn_launch_count": (ctypes.c_uint64, []),
     "fgnn_set_programmatic_launch": (ctypes.c_int, [ctypes.c_int]),
 }

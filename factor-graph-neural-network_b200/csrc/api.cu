@@ -203,6 +203,7 @@ int fgnn_mp_select_kernel(const fgnn_mp_args* a) {
 }
 
 size_t fgnn_mp_workspace_bytes(const fgnn_mp_args* a) {
+  if (a && a->src_ptr && validate(a) == FGNN_OK && src_supported(a)) return tc_workspace_bytes(a);
   const int k = fgnn_mp_select_kernel(a);
   if (k == FGNN_KERNEL_TCGEN05) return tc_workspace_bytes(a);
   return 0;
@@ -216,6 +217,13 @@ int fgnn_mp_forward(const fgnn_mp_args* a, void* stream_) {
   if (d != FGNN_OK) return d;
   MpParams p = to_params(a);
   int rc;
+  if (a->src_ptr) {                      // the caller asked for the source-stationary evaluation
+    if (!src_supported(a)) return FGNN_ERR_UNSUPPORTED;
+    if (a->workspace_bytes < tc_workspace_bytes(a) || !a->workspace) return FGNN_ERR_WORKSPACE;
+    rc = launch_mp_src(p, a, stream);
+    if (rc == FGNN_ERR_CUDA) g_last_cuda_error = (int)cudaGetLastError();
+    return rc;
+  }
   if (k == FGNN_KERNEL_TCGEN05) {
     if (a->workspace_bytes < tc_workspace_bytes(a) || (tc_workspace_bytes(a) && !a->workspace))
       return FGNN_ERR_WORKSPACE;
@@ -224,6 +232,20 @@ int fgnn_mp_forward(const fgnn_mp_args* a, void* stream_) {
     if (a->dtype != FGNN_F32) return FGNN_ERR_UNSUPPORTED;
     rc = launch_mp_simt(p, stream);
   }
+  if (rc == FGNN_ERR_CUDA) g_last_cuda_error = (int)cudaGetLastError();
+  return rc;
+}
+
+int fgnn_mp_src_supported(const fgnn_mp_args* a) {
+  if (validate(a) != FGNN_OK) return 0;
+  return src_supported(a) ? 1 : 0;
+}
+
+int fgnn_src_permute_etype(const float* etype, int64_t et_sb, const int32_t* edge_slot, float* out, int32_t T,
+                           int32_t M, int32_t K, int64_t n_edges, void* stream_) {
+  if (!etype || !edge_slot || !out || T <= 0 || M <= 0 || K <= 0 || n_edges < 0) return FGNN_ERR_INVALID_ARG;
+  const int rc = launch_et_permute(etype, et_sb, edge_slot, out, T, (int64_t)M * K, n_edges,
+                                   reinterpret_cast<cudaStream_t>(stream_));
   if (rc == FGNN_ERR_CUDA) g_last_cuda_error = (int)cudaGetLastError();
   return rc;
 }

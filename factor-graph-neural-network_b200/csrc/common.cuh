@@ -77,5 +77,14 @@ bool tc_supported(const fgnn_mp_args* a);
 size_t tc_workspace_bytes(const fgnn_mp_args* a);
 int launch_mp_tc(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream);
 void tc_set_pdl(bool on);
+bool tc_pdl_enabled();
+int tc_prepare_weights(const float* W, uint8_t* ws, int OT, int64_t version, cudaStream_t stream);
+int tc_num_sms();
+
+// source-stationary path (mp_src.cu)
+bool src_supported(const fgnn_mp_args* a);
+int launch_mp_src(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream);
+int launch_et_permute(const float* et, int64_t et_sb, const int32_t* edge_slot, float* out, int T, int64_t MK,
+                      int64_t n_edges, cudaStream_t stream);
 
 }  // namespace fgnn

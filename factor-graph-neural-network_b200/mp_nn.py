@@ -120,10 +120,79 @@ class _Workspace:
         return buf
 
 
+class SourcePlan:
+    """Source-stationary plan of one index table (include/fgnn_b200.h, `src_ptr` ...): the live slots
+    (b,m,k) -- the EDGES -- numbered in order of their flattened source row b*N + nn_idx[b,m,k].
+
+    The reference computes H = x W once per source node and gathers rows of H (mp_nn.py:124-134); the
+    destination-stationary kernel recomputes the row-product once per slot.  With this plan the call
+    computes it once per source row, stores one message per edge and aggregates per destination in a
+    second pass (csrc/mp_src.cu) -- bit-identical output.  Built once per table with torch sorting ops
+    on the table's device (tables are static across layers and steps) and cached on the table object
+    by `SourcePlan.for_table`.
+    """
+    _cache = {}
+
+    def __init__(self, nn_idx, n_src, mask_negative=False):
+        B, M, K = nn_idx.shape
+        dev = nn_idx.device
+        flat = nn_idx.reshape(B, M * K).long()
+        valid = (flat >= 0) & (flat < n_src)          # anything else is an empty slot here; range errors are the validator's job
+        key = flat + torch.arange(B, device=dev, dtype=torch.long)[:, None] * n_src
+        key = torch.where(valid, key, torch.full_like(key, B * n_src)).reshape(-1)
+        order = torch.argsort(key, stable=True)
+        E = int(valid.sum().item())
+        self.B, self.M, self.K, self.n_src, self.n_edges = B, M, K, n_src, E
+        self.edge_slot = order[:E].to(torch.int32).contiguous()                 # [E] slot of every edge
+        self.slot_edge = torch.full((B * M * K,), -1, dtype=torch.int32, device=dev)
+        self.slot_edge[order[:E]] = torch.arange(E, dtype=torch.int32, device=dev)
+        counts = torch.bincount(key[order[:E]], minlength=B * n_src)[:B * n_src]
+        self.src_ptr = torch.zeros(B * n_src + 1, dtype=torch.int32, device=dev)
+        self.src_ptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+        self.fan_out = E / max(1, B * n_src)
+        # a source row is one thread of the first pass: a hub (the reference pads with a VALID index and a zero
+        # edge type, so the pad target collects every padded slot) would serialise its whole edge list there
+        self.max_fan_out = int(counts.max().item()) if counts.numel() else 0
+        self._msg = None
+        self._et = None                    # (weakref(etype), version, data_ptr, permuted)
+
+    @classmethod
+    def for_table(cls, nn_idx, n_src, mask_negative=False):
+        ent = cls._cache.get(id(nn_idx))
+        if ent is not None and ent[0]() is nn_idx and ent[1:4] == (nn_idx._version, nn_idx.data_ptr(), n_src):
+            return ent[4]
+        plan = cls(nn_idx, n_src, mask_negative)
+        key = id(nn_idx)
+        ref = weakref.ref(nn_idx, lambda _r, key=key: cls._cache.pop(key, None))
+        cls._cache[key] = (ref, nn_idx._version, nn_idx.data_ptr(), n_src, plan)
+        return plan
+
+    def messages(self, O):
+        if self._msg is None or self._msg.numel() < self.n_edges * O:
+            self._msg = torch.empty(max(1, self.n_edges * O), dtype=torch.float32, device=self.src_ptr.device)
+        return self._msg
+
+    def etype_edges(self, etype, et_sb):
+        """etype [B,T,M,K] -> edge-major [E,T]; cached per etype object (FactorNN hands every layer the same one)."""
+        ent = self._et
+        if ent is not None and ent[0]() is etype and ent[1:3] == (etype._version, etype.data_ptr()):
+            return ent[3]
+        T = etype.shape[1]
+        out = torch.empty((max(1, self.n_edges), T), dtype=torch.float32, device=etype.device)
+        with torch.cuda.device(etype.device):
+            rc = _lib.lib().fgnn_src_permute_etype(
+                _ptr(etype), et_sb, _ptr(self.edge_slot), _ptr(out), T, self.M, self.K, self.n_edges,
+                ctypes.c_void_p(torch.cuda.current_stream(etype.device).cuda_stream))
+        _lib.check(rc, "src_permute_etype")
+        self._et = (weakref.ref(etype), etype._version, etype.data_ptr(), out)
+        return out
+
+
 def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=None, *,
                extension=0, aggregator=_lib.AGG_MAX, activation=_lib.ACT_RELU, act_slope=0.01,
                gamma=_SOFTMAX_GAMMA, kernel=_lib.KERNEL_AUTO, mask_negative=False, validate=True,
-               out=None, accumulate=False, workspace=None, filters_version=0, tile_slots=None, out_rows=None, sm_limit=0):
+               out=None, accumulate=False, workspace=None, filters_version=0, tile_slots=None, out_rows=None, sm_limit=0,
+               plan=None):
     """Functional form of the hot path: one `fgnn_mp_forward` call on x's device / current stream.
 
     x [B,C,N,1] or [B,C,N] (any strides; node-major == channels_last is the fast layout),
@@ -133,6 +202,9 @@ def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=Non
     Compacted shard-local tables (factor-sharded F->V, fgnn_b200.parallel): `tile_slots` int32
     [ceil(B*M/128)] = slots evaluated per 128-row destination tile, `out_rows` int32 [B*M] = output
     row of every destination row (then `out` [Bo,O,Mo,1] must be given; rows not named keep their value).
+
+    `plan` (a SourcePlan of nn_idx): source-stationary evaluation -- one row-product per source row instead
+    of one per slot; same result bit for bit.  Raises if the shape does not qualify (fp32, C = 64, T in {4,8,16}).
     """
     if not x.is_cuda:
         raise RuntimeError("fgnn_b200: mp_conv_v2.forward needs CUDA tensors (there is no CPU "
@@ -250,6 +322,15 @@ def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=Non
     a.tile_slots = tile_slots.data_ptr() if tile_slots is not None else None
     a.out_rows = out_rows.data_ptr() if out_rows is not None else None
     a.sm_limit = int(sm_limit)
+    keep = None
+    if plan is not None:
+        if (plan.B, plan.M, plan.K, plan.n_src) != (B, M, K, N):
+            raise ValueError("plan was built for another index table")
+        if x3.dtype != torch.float32:
+            raise TypeError("the source-stationary path is fp32")
+        keep = (plan.etype_edges(etype, et_sb), plan.messages(O))
+        a.src_ptr, a.slot_edge = plan.src_ptr.data_ptr(), plan.slot_edge.data_ptr()
+        a.etype_edges, a.messages, a.n_edges = keep[0].data_ptr(), keep[1].data_ptr(), plan.n_edges
     with torch.cuda.device(dev):
         need = lib.fgnn_mp_workspace_bytes(ctypes.byref(a))
         if need:
@@ -320,6 +401,9 @@ class mp_conv_v2(base_mp_nn):
         # first time a table object is seen (exact IndexError at the call), "async" = scan without the
         # round trip, error raised at a later call (the reference's CUDA behaviour), False = trust the caller
         self.index_check = True
+        # source-stationary evaluation (SourcePlan): True / False / "auto" = when the table's sources feed
+        # enough slots for the saved tensor work to pay for the message round trip (measured)
+        self.source_stationary = "auto"
         self._ws = None
         self._nonce = int.from_bytes(os.urandom(5), "little")      # distinguishes modules that reuse freed addresses
 
@@ -362,13 +446,14 @@ class mp_conv_v2(base_mp_nn):
         if fuse_tail and self.bn is not None:
             scale, shift = _fold_bn(self.bn)
         ws = self._workspace_for(x)
+        plan = self._plan_for(x, nn_idx, etype, ext, fused_agg)
         out = mp_forward(
             x, nn_idx, etype, self.filters,
             bias=self.bias if (fuse_tail or not custom_agg) else None,
             bn_scale=scale, bn_shift=shift, extension=ext, aggregator=fused_agg,
             activation=act_code if fuse_tail else _lib.ACT_NONE, act_slope=slope,
             kernel=self.kernel, workspace=ws, validate=self.index_check,
-            filters_version=self._filters_version() if ws is not None else 0)
+            filters_version=self._filters_version() if ws is not None else 0, plan=plan)
         if fuse_tail:
             return post_act(out) if post_act is not None else out
         # tail in PyTorch: user aggregator and/or train-mode batch statistics (mp_nn.py:162-173)
@@ -381,6 +466,38 @@ class mp_conv_v2(base_mp_nn):
         if self.activation_fn is not None:
             out = self.activation_fn(out)
         return out
+
+    # fan-out (edges per source row) from which the source-stationary path is chosen automatically, by
+    # edge-type count (measured on B200, DESIGN.md 6: it pays at T = 16, where the destination-stationary
+    # kernel is tensor-bound; at T <= 8 the message round trip costs more than the saved row-products), and
+    # the largest single fan-out tolerated (hub rows serialise in one thread)
+    AUTO_FAN_OUT = {16: 2.0, 8: float("inf"), 4: float("inf")}
+    AUTO_MAX_FAN_OUT = 64
+    AUTO_MIN_SLOTS = 200_000
+
+    def _plan_for(self, x, nn_idx, etype, ext, agg):
+        mode = self.source_stationary
+        if not mode or self.kernel == _lib.KERNEL_SIMT:
+            return None
+        T = self.nedge_types
+        ok = (ext == 0 and agg != _lib.AGG_NONE and x.is_cuda and x.dtype == torch.float32 and self.nin == 64
+              and T in (4, 8, 16) and (self.nou * T) % 256 == 0 and self.nou % 4 == 0 and self.nou <= 128
+              and nn_idx.dim() == 3 and x.dim() in (3, 4) and x.stride(1) == 1)
+        if not ok:
+            if mode is True:
+                raise RuntimeError("fgnn_b200: this call does not qualify for the source-stationary path")
+            return None
+        n_src = x.shape[2]
+        if mode == "auto":
+            B, M, K = nn_idx.shape
+            if B * M * K < self.AUTO_MIN_SLOTS or B * M * K < self.AUTO_FAN_OUT[T] * B * n_src:
+                return None
+            if self.index_check is not True and not _table_seen(nn_idx, n_src, False):
+                return None                 # the plan builder trusts validated tables only
+        plan = SourcePlan.for_table(nn_idx, n_src)
+        if mode == "auto" and (plan.fan_out < self.AUTO_FAN_OUT[T] or plan.max_fan_out > self.AUTO_MAX_FAN_OUT):
+            return None
+        return plan
 
     def enable_weight_cache(self, device=None):
         """Give this module a private workspace so the tensor-core kernel converts `filters`

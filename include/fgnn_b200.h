@@ -120,6 +120,18 @@ typedef struct fgnn_mp_args {
                                 rest to a concurrent collective (the kernel owns whole SMs: a CTA that cannot
                                 be placed would serialise behind the collective).  0 = all SMs              */
   int32_t reserved_;
+  /* Source-stationary evaluation (optional; src_ptr == NULL = destination-stationary).  The reference computes
+     H = x W once per SOURCE node and gathers rows of H per slot (mp_nn.py:124-134); the default kernel instead
+     recomputes x[n] W once per slot.  With a plan of the index table (built by the caller from nn_idx, layout
+     below) the call computes H once per source row on the tensor cores, stores one O-wide message per edge and
+     aggregates every destination's messages in a second streaming pass -- bit-identical results, fewer
+     row-products when sources feed several slots.  fp32, NO_EXTENSION, C = 64, T in {4,8,16}, O*T % 256 == 0.
+     An EDGE is a live slot (b,m,k); edges are numbered in order of their flattened source row b*N + idx[b,m,k]. */
+  const int32_t* src_ptr;    /* [B*N + 1]: the edges of source row g are src_ptr[g] .. src_ptr[g+1]-1            */
+  const int32_t* slot_edge;  /* [B*M*K]: edge number of slot (b*M + m)*K + k, -1 = empty slot                    */
+  const void* etype_edges;   /* [E, T]: edge-type vector of every edge, edge-major (fgnn_src_permute_etype)      */
+  void* messages;            /* [E, O] scratch for the per-edge messages                                        */
+  int64_t n_edges;           /* E                                                                                */
 } fgnn_mp_args;
 
 int fgnn_version(void);
@@ -139,6 +151,14 @@ int fgnn_mp_forward(const fgnn_mp_args* args, void* stream);
  * host too).  Allocates device buffers, copies in, runs, copies out, frees, synchronises.  This is
  * the end-to-end entry a non-PyTorch caller binds. */
 int fgnn_mp_forward_host(const fgnn_mp_args* host_args);
+
+/* 1 if `args` (with its source-stationary plan fields set) qualifies for the source-stationary path, else 0. */
+int fgnn_mp_src_supported(const fgnn_mp_args* args);
+
+/* etype [B,T,M,K] (reference layout, batch stride et_sb elements) -> edge-major [E,T] in the plan's edge order:
+ * out[e, t] = etype[b, t, m, k] for edge e = slot (b*M + m)*K + k = edge_slot[e].  Asynchronous on `stream`. */
+int fgnn_src_permute_etype(const float* etype, int64_t et_sb, const int32_t* edge_slot, float* out, int32_t T,
+                           int32_t M, int32_t K, int64_t n_edges, void* stream);
 
 /* Index validation the reference gets for free from ATen's gather (mp_nn.py:111): returns
  * FGNN_ERR_INDEX_RANGE if any entry of idx[count] is outside [lo, N).  Synchronises `stream`.

@@ -358,6 +358,69 @@ def test_programmatic_launch_chain_bit_identical():
     assert torch.isfinite(ref_v).all() and float(ref_v.abs().max()) > 0
 
 
+@pytest.mark.parametrize("shape", [
+    dict(B=1, N=5000, M=15000, K=2, C=64, O=64, T=16),     # cfg-2 V2F pairwise at 1/20 scale: fan-out 6
+    dict(B=1, N=15000, M=5000, K=6, C=64, O=64, T=16),     # cfg-2 F2V pairwise: fan-out 2
+    dict(B=1, N=2500, M=5000, K=2, C=64, O=64, T=16),      # cfg-2 F2V order-3 shape
+    dict(B=1, N=5000, M=15000, K=2, C=64, O=64, T=4),
+    dict(B=1, N=900, M=1001, K=3, C=64, O=64, T=8),
+    dict(B=1, N=37, M=3000, K=5, C=64, O=64, T=16),        # fan-out ~400: many passes over each chunk
+    dict(B=3, N=130, M=257, K=4, C=64, O=64, T=16),        # batched, ragged tiles
+    dict(B=1, N=300, M=500, K=2, C=64, O=128, T=16),
+], ids=lambda s: "B{B}_N{N}_M{M}_K{K}_C{C}_O{O}_T{T}".format(**s))
+@pytest.mark.parametrize("agg", ["max", "softmax", "mean"])
+def test_source_stationary_equals_destination_stationary(shape, agg):
+    """The source-stationary evaluation (one row-product per source row, per-edge messages, second pass)
+    is bit-identical to the destination-stationary kernel and within 1e-4 of the oracle."""
+    rng = np.random.default_rng(hash((shape["M"], shape["K"], shape["T"], 3)) & 0xffff)
+    x, idx, et, W, bias, bn = _random_call(rng, **shape)
+    code = {"max": 0, "softmax": 1, "mean": 2}[agg]
+    d_idx = t(idx)
+    plan = fgnn_b200.SourcePlan(d_idx, shape["N"])
+    assert plan.n_edges == idx.size and int(plan.src_ptr[-1]) == idx.size
+    y_dst = _native(x, idx, et, W, bias, bn, agg=code, kernel=_lib.KERNEL_TCGEN05)
+    before = fgnn_b200.launch_count()
+    scale = bn["weight"] / np.sqrt(bn["running_var"] + 1e-5)
+    shift = bn["bias"] - bn["running_mean"] * scale
+    y_src = fgnn_b200.mp_forward(t(x).contiguous(memory_format=torch.channels_last), d_idx, t(et), t(W), t(bias),
+                                 t(scale.astype(np.float32)), t(shift.astype(np.float32)), extension=0, aggregator=code,
+                                 plan=plan)
+    assert fgnn_b200.launch_count() >= before + 2
+    assert torch.equal(y_src, y_dst), f"max |diff| = {float((y_src - y_dst).abs().max())}"
+    ref = orc.mp_conv_forward_c(x, idx, et, W, bias, bn, extension=0, aggregator=agg)
+    assert_close(y_src.cpu().numpy(), ref, RTOL, f"source-stationary {shape} {agg}")
+
+
+def test_source_stationary_masked_accumulate_and_module_auto():
+    rng = np.random.default_rng(17)
+    x, idx, et, W, bias, bn = _random_call(rng, B=1, N=700, M=4000, K=4, C=64, O=64, T=16, pad_frac=0.0)
+    idx[rng.random(idx.shape) < 0.3] = -1
+    d_idx = t(idx)
+    plan = fgnn_b200.SourcePlan(d_idx, 700, mask_negative=True)
+    assert plan.n_edges == int((idx >= 0).sum())
+    args = (t(x).contiguous(memory_format=torch.channels_last), d_idx, t(et), t(W), t(bias), None, None)
+    y_dst = fgnn_b200.mp_forward(*args, extension=0, aggregator=0, mask_negative=True, kernel=_lib.KERNEL_TCGEN05)
+    y_src = fgnn_b200.mp_forward(*args, extension=0, aggregator=0, mask_negative=True, plan=plan)
+    assert torch.equal(y_src, y_dst)                       # including the -inf rows of destinations with no live slot
+    acc_d, acc_s = torch.full_like(y_dst, 0.25), torch.full_like(y_dst, 0.25)
+    ok = torch.isfinite(y_dst)
+    fgnn_b200.mp_forward(*args, extension=0, aggregator=0, mask_negative=True, kernel=_lib.KERNEL_TCGEN05, out=acc_d,
+                         accumulate=True)
+    fgnn_b200.mp_forward(*args, extension=0, aggregator=0, mask_negative=True, plan=plan, out=acc_s, accumulate=True)
+    assert torch.equal(acc_s[ok], acc_d[ok])
+    # the module picks the plan by itself for a table whose sources feed many slots, and says so
+    mod = fgnn_b200.mp_conv_v2(64, 64, 16, extension=fgnn_b200.mp_conv_type.NO_EXTENSION, aggregtor="max").to(DEV).eval()
+    mod.AUTO_MIN_SLOTS = 1000
+    big = t(rng.integers(0, 700, (1, 6000, 2)))
+    xe, ete = t(x).contiguous(memory_format=torch.channels_last), t(rng.standard_normal((1, 16, 6000, 2)).astype(np.float32))
+    with torch.no_grad():
+        y_auto = mod(xe, big, ete)
+        assert mod._plan_for(xe, big, ete, 0, _lib.AGG_MAX) is not None
+        mod.source_stationary = False
+        y_off = mod(xe, big, ete)
+    assert torch.equal(y_auto, y_off)
+
+
 def test_masked_slots_and_epilogue_split_equal_fused():
     """Shard-local tables: negative indices are empty slots excluded from the max; the
     raw aggregate of two half-tables, max-combined and passed through fgnn_epilogue_forward,

@@ -149,3 +149,27 @@ def test_install_drops_into_reference_package():
         mpnn.mp_conv_v2 = orig
         for n, v in saved.items():
             mods[n].mp_conv_v2 = v
+
+
+def test_source_plan_layout():
+    """SourcePlan (host side of the source-stationary path): edges = live slots in source order."""
+    import torch
+    import fgnn_b200
+    rng = np.random.default_rng(0)
+    B, N, M, K = 2, 7, 11, 3
+    idx = rng.integers(-1, N, (B, M, K))
+    plan = fgnn_b200.SourcePlan(torch.from_numpy(idx), N, mask_negative=True)
+    live = idx >= 0
+    assert plan.n_edges == int(live.sum())
+    ptr, slot_edge, edge_slot = plan.src_ptr.numpy(), plan.slot_edge.numpy(), plan.edge_slot.numpy()
+    assert ptr[0] == 0 and ptr[-1] == plan.n_edges and np.all(np.diff(ptr) >= 0)
+    flat_src = (idx + np.arange(B)[:, None, None] * N).reshape(-1)
+    for g in range(B * N):
+        slots = edge_slot[ptr[g]:ptr[g + 1]]
+        assert np.all(flat_src[slots] == g) and np.all(live.reshape(-1)[slots])
+        assert np.all(np.diff(slots) > 0)                       # stable: slot order within a source
+    assert np.array_equal(slot_edge[edge_slot], np.arange(plan.n_edges))
+    assert np.all(slot_edge[~live.reshape(-1)] == -1)
+    # cached per table object
+    tbl = torch.from_numpy(idx)
+    assert fgnn_b200.SourcePlan.for_table(tbl, N, True) is fgnn_b200.SourcePlan.for_table(tbl, N, True)

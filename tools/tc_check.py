@@ -95,6 +95,57 @@ def run_bf16(B, N, M, K, T, agg=0, O=64, seed=0):
     return err <= 8e-3
 
 
+def run_src(B, N, M, K, T, agg=0, O=64, seed=0):
+    """source-stationary path against the destination-stationary kernel (bit-identical by construction)."""
+    rng = np.random.default_rng(seed)
+    x = torch.from_numpy(rng.standard_normal((B, N, 64)).astype(np.float32)).to(dev).permute(0, 2, 1).unsqueeze(-1)
+    idx = torch.from_numpy(rng.integers(0, N, (B, M, K))).to(dev)
+    et = torch.from_numpy(rng.standard_normal((B, T, M, K)).astype(np.float32)).to(dev)
+    W = torch.from_numpy((rng.uniform(-1, 1, (64, O * T)) * 0.1).astype(np.float32)).to(dev)
+    bias = torch.from_numpy(rng.uniform(-0.2, 0.2, O).astype(np.float32)).to(dev)
+    try:
+        plan = fgnn_b200.SourcePlan(idx, N)
+        y0 = fgnn_b200.mp_forward(x, idx, et, W, bias, None, None, extension=0, aggregator=agg, kernel=_lib.KERNEL_TCGEN05)
+        y1 = fgnn_b200.mp_forward(x, idx, et, W, bias, None, None, extension=0, aggregator=agg, plan=plan)
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        print(f"src B{B} N{N} M{M} K{K} T{T} agg{agg}: FAILED: {e}")
+        return False
+    same = torch.equal(y0, y1)
+    diff = float((y0 - y1).abs().max())
+    msg = f"src B{B} N{N} M{M} K{K} T{T} O{O} agg{agg}: fan-out {plan.fan_out:.2f} bit-identical {same} max|diff| {diff:.3e}"
+    if not same:
+        bad = torch.nonzero((y0 != y1)[0, :, :, 0])
+        msg += f" | {len(bad)} bad of {y0.numel()}; channels {sorted(set(bad[:, 0].tolist()))[:20]} rows {sorted(set(bad[:, 1].tolist()))[:10]}"
+    print(msg, flush=True)
+    return same
+
+
+def timeit_src(N, M, K, T, reps=10):
+    rng = np.random.default_rng(0)
+    x = torch.randn(1, N, 64, device=dev).permute(0, 2, 1).unsqueeze(-1)
+    idx = torch.from_numpy(rng.integers(0, N, (1, M, K))).to(dev)
+    et = torch.randn(1, T, M, K, device=dev)
+    W = torch.randn(64, 64 * T, device=dev) * 0.1
+    bias = torch.zeros(64, device=dev)
+    out = torch.empty(1, 64, M, 1, device=dev, memory_format=torch.channels_last)
+    ws = torch.zeros(64 * 64 * T * 4 + 4096, dtype=torch.uint8, device=dev)
+    plan = fgnn_b200.SourcePlan(idx, N)
+    f = lambda: fgnn_b200.mp_forward(x, idx, et, W, bias, None, None, extension=0, aggregator=0, out=out, workspace=ws,
+                                     filters_version=7, plan=plan)
+    for _ in range(3):
+        f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        f()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / reps * 1e3
+    print(f"time src  N{N} M{M} K{K} T{T}: {us:9.1f} us  {M * K / us:8.1f} Mslots/s (fan-out {plan.fan_out:.1f})", flush=True)
+
+
 def timeit(B, N, M, K, T, kernel, reps=10, dtype=torch.float32):
     rng = np.random.default_rng(0)
     x = torch.randn(B, N, 64, device=dev).to(dtype).permute(0, 2, 1).unsqueeze(-1)
@@ -123,6 +174,10 @@ def timeit(B, N, M, K, T, kernel, reps=10, dtype=torch.float32):
 
 
 if __name__ == "__main__":
+    if "--profile-src" in sys.argv:       # source-stationary launches for ncu: the four cfg-2 calls at T=16
+        for (N, M, K) in ((100_000, 300_000, 2), (300_000, 100_000, 6), (100_000, 50_000, 3), (50_000, 100_000, 2)):
+            timeit_src(N, M, K, 16, reps=1)
+        sys.exit(0)
     if "--profile" in sys.argv:           # two launches for ncu: V2F-pairwise shaped, T=16 and T=4
         timeit(1, 100_000, 300_000, 2, 16, _lib.KERNEL_TCGEN05, reps=1)
         timeit(1, 100_000, 300_000, 2, 4, _lib.KERNEL_TCGEN05, reps=1)
@@ -150,6 +205,14 @@ if __name__ == "__main__":
     ok &= run_bf16(1, 300, 1000, 3, 2, agg=2)
     ok &= run_bf16(1, 5000, 20000, 6, 16, agg=1)
     ok &= run_bf16(1, 500, 3000, 4, 16, O=128)
+    ok &= run_src(1, 200, 128, 1, 16)
+    ok &= run_src(1, 200, 1000, 2, 16)
+    ok &= run_src(1, 3000, 9000, 2, 16)
+    ok &= run_src(1, 3000, 9000, 2, 4)
+    ok &= run_src(1, 3000, 9000, 2, 8, agg=2)
+    ok &= run_src(1, 50, 3000, 3, 16, agg=1)
+    ok &= run_src(2, 300, 1000, 3, 16)
+    ok &= run_src(1, 300, 1000, 3, 16, O=128)
     print("ALL OK" if ok else "SOME FAILED")
     if "--big" in sys.argv or ok:
         for pdl in (True, False):
@@ -159,6 +222,9 @@ if __name__ == "__main__":
                 for (N, M, K) in ((100_000, 300_000, 2), (300_000, 100_000, 6), (100_000, 50_000, 3), (50_000, 100_000, 2)):
                     timeit(1, N, M, K, T, _lib.KERNEL_TCGEN05)
         fgnn_b200.set_programmatic_launch(True)
+        for T in (16, 4):
+            for (N, M, K) in ((100_000, 300_000, 2), (300_000, 100_000, 6), (100_000, 50_000, 3), (50_000, 100_000, 2)):
+                timeit_src(N, M, K, T)
         for T in (16, 4):
             for (N, M, K) in ((100_000, 300_000, 2), (300_000, 100_000, 6), (1_000_000, 3_000_000, 2)):
                 timeit(1, N, M, K, T, _lib.KERNEL_TCGEN05, dtype=torch.bfloat16)
