@@ -249,6 +249,27 @@ def hbm_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def tensor_peak():
+    """Sustained dense bf16 TFLOP/s (the kernels run inside a long step)."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 0.0))), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1360.0, "fallback"
+
+
+def executed_mma_flops_per_layer(args, types, plans):
+    """bf16 MMA flops the step really issues per layer: 3 split terms x 2*C*O*T per row-product; one
+    row-product per SLOT in a destination-stationary call, per SOURCE ROW in a source-stationary call."""
+    C = O = args.dim
+    T = args.edge_types
+    rows = 0
+    for j, t in enumerate(types):
+        rows += t.n_vars if ("v2f%d" % j) in plans else t.n_factors * t.order
+        rows += t.n_factors if ("f2v%d" % j) in plans else t.n_vars * t.kv
+    return 3 * 2 * C * O * T * rows
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -396,30 +417,37 @@ def run_native(args):
         h2d = sum(t.numel() * t.element_size() for v in pinned.values() for t in (v if isinstance(v, list) else [v]))
         d2h = host_out.numel() * 4
 
-        copy_stream = torch.cuda.Stream(device=dev)
+        copy_stream, out_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         order = ["x_v"] + [(k, j) for j in range(J) for k in ("idx_v2f", "et_v2f", "x_f", "idx_f2v", "et_f2v")]
+        # two sets of device input buffers: step i+1 is uploaded while step i computes
+        dsets = [{k: ([torch.empty_like(t, device=dev) for t in v] if isinstance(v, list) else torch.empty_like(v, device=dev))
+                  for k, v in pinned.items()} for _ in range(2)]
+        ready, free_ev = [{}, {}], [None, None]
 
-        def e2e_step():
-            """Inputs leave pinned host memory on a copy stream in the order the layer consumes them;
-            each module call waits only for the tensors it reads, so the first calls overlap the rest
-            of the upload.  The final variable features come back to pinned host memory."""
-            main = torch.cuda.current_stream(dev)
-            copy_stream.wait_stream(main)                    # previous step's readers are done with the buffers
-            src, ready = {k: ([None] * J if isinstance(v, list) else None) for k, v in pinned.items()}, {}
+        def upload(s):
+            """Inputs leave pinned host memory on the copy stream in the order the layer consumes them."""
+            if free_ev[s] is not None:
+                copy_stream.wait_event(free_ev[s])           # the step that last read this buffer set is done
             with torch.cuda.stream(copy_stream):
                 for item in order:
                     if item == "x_v":
-                        src["x_v"] = pinned["x_v"].to(dev, non_blocking=True)
+                        dsets[s]["x_v"].copy_(pinned["x_v"], non_blocking=True)
                     else:
                         k, j = item
-                        src[k][j] = pinned[k][j].to(dev, non_blocking=True)
+                        dsets[s][k][j].copy_(pinned[k][j], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(copy_stream)
-                    ready[item] = ev
+                    ready[s][item] = ev
+
+        def compute(s):
+            """20 module calls on the main stream; each waits only for the tensors it reads, so the first calls
+            overlap the rest of the upload.  The final variable features go back to pinned host memory."""
+            main = torch.cuda.current_stream(dev)
+            src = dsets[s]
 
             def need(*items):
                 for it in items:
-                    main.wait_event(ready[it])
+                    main.wait_event(ready[s][it])
 
             need("x_v")
             x_v, x_f = nm(src["x_v"]), [None] * J
@@ -436,27 +464,43 @@ def run_native(args):
                         y = mods[l][j]["f2v"](x_f[j], src["idx_f2v"][j], src["et_f2v"][j])
                         nv = y if nv is None else nv + y
                     x_v, x_f = nv, nf
-            host_out.copy_(x_v[..., 0].permute(0, 2, 1), non_blocking=True)
-            for v in src.values():                           # the copy stream's allocations are used on `main`
-                for t in (v if isinstance(v, list) else [v]):
-                    t.record_stream(main)
-            main.synchronize()
+            done = torch.cuda.Event()
+            done.record(main)
+            free_ev[s] = done
+            out_stream.wait_event(done)
+            with torch.cuda.stream(out_stream):
+                host_out.copy_(x_v[..., 0].permute(0, 2, 1), non_blocking=True)
+            x_v.record_stream(out_stream)
+
+        def e2e_run(n):
+            upload(0)
+            for i in range(n):
+                if i + 1 < n:
+                    upload((i + 1) & 1)
+                compute(i & 1)
+            torch.cuda.synchronize()
 
         if world == 1:
-            for _ in range(2):
-                e2e_step()
+            e2e_run(2)
             k = max(3, min(args.steps, 10))
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            for _ in range(k):
-                e2e_step()
-            torch.cuda.synchronize()
+            e2e_run(k)
             fgnn_b200.check_async_errors()
             dt = (time.perf_counter() - t0) / k
+            # the link itself: the same uploads with nothing else running
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            for _ in range(3):
+                upload(0)
+            torch.cuda.synchronize()
+            h2d_gbs = 3 * h2d / (time.perf_counter() - t1) / 1e9
             e2e = {"value": msgs_layer * L / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                    "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": k, "index_check": "async",
-                   "api": "fgnn_b200.mp_conv_v2.forward (20 module calls), pinned host tensors in (uploaded on a copy stream, "
-                          "each call waits only for its own inputs), pinned host tensor out"}
+                   "h2d_link_gbs": h2d_gbs,
+                   "api": "fgnn_b200.mp_conv_v2.forward (20 module calls per step) on pinned host tensors: every step's inputs "
+                          "are uploaded (copy stream, double-buffered: step i+1 uploads while step i computes; each call waits "
+                          "only for its own inputs) and every step's variable features are read back to pinned host memory"}
 
     if rank != 0:
         if world > 1:
@@ -466,8 +510,10 @@ def run_native(args):
     achieved = bytes_layer * L / (ms_step * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath) and args.edge_types == 16 and world == 1 and args.vars == 100_000:
+    if os.path.exists(tpath) and args.edge_types == 16 and world == 1 and args.vars == 100_000 and args.src_calls == "auto":
         traffic = json.load(open(tpath))["traffic_bytes_per_launch_avg"]     # ncu --set full of this very workload
+    tpeak, tpeak_src = tensor_peak()
+    mma_flops = executed_mma_flops_per_layer(args, types, plans) if args.kernel != "simt" else 0
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
@@ -477,12 +523,16 @@ def run_native(args):
                    % (bytes_layer // 1_000_000), "parallelism": ("factor-sharded x%d + NCCL max-all-reduce per layer" % world)
                    if world > 1 else "single GPU"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "mp_tc_kernel (tcgen05; average over the step's %d message-passing launches)" % (4 * L if world == 1 else 0)
+                     "traffic": traffic, "peak_source": peak_src,
+                     "kernel": ("mp_tc_kernel / mp_src_kernel + mp_reduce_kernel (tcgen05; average over the step's %d core calls, "
+                                "a source-stationary call being two launches)" % (2 * J * L))
                      if args.kernel != "simt" else "mp_simt_kernel",
                      "algorithmic_bytes_per_launch": bytes_layer * L / (2 * J * L),
                      "avg_launch_us": ms_step * 1e3 / (2 * J * L),
-                     "tensor_bound_note": "T=16 fp32 is tensor-bound in this formulation (3-term split-bf16 MMA, 2*E*C*O*T flop): "
-                                          "HBM-roofline ceiling ~0.22, DESIGN.md 3.1" if args.edge_types >= 16 else None},
+                     "tensor": {"executed_tflops": mma_flops * L / (ms_step * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                                "frac": mma_flops * L / (ms_step * 1e-3) / 1e12 / tpeak if tpeak else None, "peak_source": tpeak_src,
+                                "note": "bf16 MMA flops actually issued (3 split-bf16 terms for fp32 parity) against the sustained "
+                                        "cuBLAS bf16 rate: at T=16 the tensor pipe, not HBM, bounds this path (DESIGN.md 3)"}},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if e2e is not None:

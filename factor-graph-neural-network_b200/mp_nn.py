@@ -65,6 +65,25 @@ def _table_remember(nn_idx, n_src, mask_negative):
 
 def clear_table_cache():
     _validated_tables.clear()
+    _table_uses.clear()
+
+
+# How often an index-table object has been used unchanged (identity + version + address): building a
+# source-stationary plan costs a sort and a host round trip, which only a table that is demonstrably static
+# (FGNN tables are shared by all layers and steps) pays back.
+_table_uses = {}
+
+
+def _table_use_count(nn_idx):
+    key = id(nn_idx)
+    ent = _table_uses.get(key)
+    if ent is not None and ent[0]() is nn_idx and ent[1:3] == (nn_idx._version, nn_idx.data_ptr()):
+        n = ent[3] + 1
+    else:
+        n = 1
+    ref = ent[0] if (ent is not None and ent[0]() is nn_idx) else weakref.ref(nn_idx, lambda _r, key=key: _table_uses.pop(key, None))
+    _table_uses[key] = (ref, nn_idx._version, nn_idx.data_ptr(), n)
+    return n
 
 
 # Asynchronous index checking (validate="async"): the scan kernel stores into pinned host memory that is
@@ -231,6 +250,19 @@ def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=Non
         raise ValueError(f"etype shape {tuple(etype.shape)} does not match [B={B},T,M={M},K={K}]")
     if nn_idx.device != dev or etype.device != dev or filters.device != dev:
         raise RuntimeError("fgnn_b200: x, nn_idx, etype and the module must be on the same device")
+    # The tensor-core kernels gather whole node rows.  A channels-first x (what a Conv2d on a contiguous
+    # tensor returns; the reference permutes it itself, mp_nn.py:125) is brought to node-major memory with one
+    # pass of the library's own transpose when the call otherwise qualifies for them -- that pass costs 8 bytes
+    # per element, the fp32 CUDA-core kernel it avoids is 10-60x slower.  Results do not depend on the layout.
+    if (extension == 0 and C == 64 and kernel != _lib.KERNEL_SIMT and x3.dtype == torch.float32
+            and aggregator != _lib.AGG_NONE and N > 0 and B * M * K > 0
+            and not (x3.stride(1) == 1 and x3.stride(2) == C and (B == 1 or x3.stride(0) == N * C))):
+        xt = torch.empty((B, N, C), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.fgnn_to_node_major(_ptr(x3), _ptr(xt), B, C, N, x3.stride(0), x3.stride(1), x3.stride(2),
+                                        ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check(rc, "to_node_major")
+        x3 = xt.permute(0, 2, 1)
     idx_user = nn_idx                                 # the caller's object: identity for the validation cache
     if nn_idx.dtype not in (torch.int64, torch.int32):
         nn_idx = nn_idx.long()
@@ -474,6 +506,7 @@ class mp_conv_v2(base_mp_nn):
     AUTO_FAN_OUT = {16: 2.0, 8: float("inf"), 4: float("inf")}
     AUTO_MAX_FAN_OUT = 64
     AUTO_MIN_SLOTS = 200_000
+    AUTO_MIN_USES = 8                  # uses of the unchanged table object before a plan is built (a plan costs ~50 calls' worth of its gain)
 
     def _plan_for(self, x, nn_idx, etype, ext, agg):
         mode = self.source_stationary
@@ -482,7 +515,7 @@ class mp_conv_v2(base_mp_nn):
         T = self.nedge_types
         ok = (ext == 0 and agg != _lib.AGG_NONE and x.is_cuda and x.dtype == torch.float32 and self.nin == 64
               and T in (4, 8, 16) and (self.nou * T) % 256 == 0 and self.nou % 4 == 0 and self.nou <= 128
-              and nn_idx.dim() == 3 and x.dim() in (3, 4) and x.stride(1) == 1)
+              and nn_idx.dim() == 3 and x.dim() in (3, 4))
         if not ok:
             if mode is True:
                 raise RuntimeError("fgnn_b200: this call does not qualify for the source-stationary path")
@@ -494,6 +527,8 @@ class mp_conv_v2(base_mp_nn):
                 return None
             if self.index_check is not True and not _table_seen(nn_idx, n_src, False):
                 return None                 # the plan builder trusts validated tables only
+            if _table_use_count(nn_idx) < self.AUTO_MIN_USES:
+                return None                 # not (yet) known to be static: a plan would cost more than it saves
         plan = SourcePlan.for_table(nn_idx, n_src)
         if mode == "auto" and (plan.fan_out < self.AUTO_FAN_OUT[T] or plan.max_fan_out > self.AUTO_MAX_FAN_OUT):
             return None

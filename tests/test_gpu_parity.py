@@ -410,7 +410,7 @@ def test_source_stationary_masked_accumulate_and_module_auto():
     assert torch.equal(acc_s[ok], acc_d[ok])
     # the module picks the plan by itself for a table whose sources feed many slots, and says so
     mod = fgnn_b200.mp_conv_v2(64, 64, 16, extension=fgnn_b200.mp_conv_type.NO_EXTENSION, aggregtor="max").to(DEV).eval()
-    mod.AUTO_MIN_SLOTS = 1000
+    mod.AUTO_MIN_SLOTS, mod.AUTO_MIN_USES = 1000, 1
     big = t(rng.integers(0, 700, (1, 6000, 2)))
     xe, ete = t(x).contiguous(memory_format=torch.channels_last), t(rng.standard_normal((1, 16, 6000, 2)).astype(np.float32))
     with torch.no_grad():
