@@ -59,6 +59,10 @@ def parse_args():
                     help="which core calls run source-stationary (one row-product per source row, csrc/mp_src.cu): "
                          "'auto' (fan-out rule of mp_conv_v2), 'none', or a comma list of v2f<j>/f2v<j> (j = factor type)")
     ap.add_argument("--cpu-sample-scale", type=int, default=2, help="cpu_baseline runs on 1/scale of the graph")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU: the cross-GPU step as one kernel over NVLink peer memory (csrc/exchange.cu), or "
+                         "NCCL all_reduce(MAX) + epilogue kernel")
+    ap.add_argument("--exchange-ctas", type=int, default=32, help="grid of the peer exchange kernel (512-thread CTAs, two per SM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
@@ -317,7 +321,7 @@ def run_native(args):
     if world > 1:
         # factor-sharded: this rank keeps its factor ranges, the compacted F->V tables and their edge types
         from fgnn_b200 import parallel
-        plan = parallel.ShardedLayerPlan(types, rank, world, dev)
+        plan = parallel.ShardedLayerPlan(types, rank, world, dev, exchange=args.exchange, exchange_ctas=args.exchange_ctas)
         d_in["x_f"] = plan.local_factor_features(d_in["x_f"])
         d_in["et_v2f"], d_in["et_f2v"] = plan.local_etypes(d_in["et_v2f"], d_in["et_f2v"])
         d_in["idx_v2f"] = d_in["idx_f2v"] = None
@@ -345,9 +349,21 @@ def run_native(args):
                              aggregator=_lib.AGG_MAX, activation=_lib.ACT_RELU, kernel=kernel, out=nm(out),
                              accumulate=accumulate, workspace=wsb, filters_version=ver, plan=plans.get(name))
 
+    peer_xv = plan.peer_buffers(J, C) if (plan is not None and args.exchange == "peer") else None
+
     def step(src):
         """src: dict of device tensors (x_v, x_f, tables).  Returns the final variable features."""
         x_v, x_f = src["x_v"], src["x_f"]
+        if peer_xv is not None:
+            # the variable features live in the peer-mapped arena: layer l reads buffer l & 1 and the fused
+            # exchange kernel leaves the new features in buffer (l + 1) & 1 on every rank
+            peer_xv[0].copy_(src["x_v"])
+            for l in range(L):
+                nf = buf_f[l & 1]
+                x_v = plan.layer_peer(l & 1, x_f, src["et_v2f"], src["et_f2v"], W[l], nf, kernel, ws[l], last=(l == L - 1))
+                x_f = nf
+            plan.peer_wait()
+            return x_v
         for l in range(L):
             nv, nf = buf_v[l & 1], buf_f[l & 1]
             if plan is not None:
@@ -520,7 +536,8 @@ def run_native(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "messages_per_layer": msgs_layer, "layers": L,
                    "kernel": args.kernel, "source_stationary_calls": sorted(plans), "l2": "per-step working set (~%d MB/layer) exceeds the 126 MB L2; no explicit flush"
-                   % (bytes_layer // 1_000_000), "parallelism": ("factor-sharded x%d + NCCL max-all-reduce per layer" % world)
+                   % (bytes_layer // 1_000_000), "parallelism": ("factor-sharded x%d + %s per layer" % (world, "fused max-reduce/epilogue/broadcast kernel over NVLink peer memory"
+                                                                         if args.exchange == "peer" else "NCCL max-all-reduce"))
                    if world > 1 else "single GPU"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,

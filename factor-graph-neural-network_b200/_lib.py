@@ -47,6 +47,19 @@ class MpArgs(ctypes.Structure):
     ]
 
 
+class ExchangeArgs(ctypes.Structure):
+    """struct fgnn_exchange_args"""
+    _fields_ = [
+        ("raw", ctypes.c_void_p * 8), ("out", ctypes.c_void_p * 8), ("flags", ctypes.c_void_p * 8),
+        ("counter", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("bn_scale", ctypes.c_void_p),
+        ("bn_shift", ctypes.c_void_p),
+        ("rows", ctypes.c_int64), ("row0", ctypes.c_int64), ("row1", ctypes.c_int64),
+        ("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("J", ctypes.c_int32), ("O", ctypes.c_int32),
+        ("activation", ctypes.c_int32), ("act_slope", ctypes.c_float), ("epoch", ctypes.c_uint32),
+        ("ctas", ctypes.c_int32), ("raw_mask", ctypes.c_void_p), ("out_mask", ctypes.c_void_p),
+    ]
+
+
 EXPORTS = {
     "fgnn_version": (ctypes.c_int, []),
     "fgnn_strerror": (ctypes.c_char_p, [ctypes.c_int]),
@@ -74,6 +87,11 @@ EXPORTS = {
     "fgnn_src_permute_etype": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                               ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
                                               ctypes.c_void_p]),
+    "fgnn_comm_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
+    "fgnn_comm_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "fgnn_comm_close": (ctypes.c_int, [ctypes.c_void_p]),
+    "fgnn_comm_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "fgnn_exchange_forward": (ctypes.c_int, [ctypes.POINTER(ExchangeArgs), ctypes.c_void_p]),
     "fgnn_launch_count": (ctypes.c_uint64, []),
     "fgnn_set_programmatic_launch": (ctypes.c_int, [ctypes.c_int]),
 }

@@ -72,14 +72,126 @@ class LocalF2V:
         return (out * torch.from_numpy(self.slot_live).to(dev)[None, None]).contiguous()
 
 
+class _DevMem:
+    """Raw device memory exposed through __cuda_array_interface__ (zero-copy torch view)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerExchange:
+    """The cross-GPU step of the factor-sharded layer as ONE kernel over NVLink peer memory
+    (csrc/exchange.cu, `fgnn_exchange_forward`): the owner of a row range reads the peers' raw per-type maxima
+    straight out of their memory, reduces, applies bias / BN / activation per type, sums the types and stores the
+    finished rows into every rank's next-layer feature buffer.  Replaces all_reduce(MAX) + epilogue kernel.
+
+    Each rank's ARENA (library-allocated, IPC-exported) holds: 16 epoch flags + block counter (256 B header), TWO raw
+    aggregates [rows, J*O] (layer l fills raws[l & 1], so the exchange of layer l can still be reading while the F->V
+    calls of layer l+1 write the other one) and two next-layer feature buffers [rows, O] (ping-pong: layer l reads
+    xv[l & 1], the exchange of layer l fills xv[(l + 1) & 1] on every rank).
+    """
+    HEADER = 256
+
+    def __init__(self, rows, J, O, rank, world, device, group=None, ctas=64, peers=None):
+        self.rows, self.J, self.O, self.rank, self.world, self.device, self.ctas = rows, J, O, rank, world, device, ctas
+        self.raw_offs = [self.HEADER, self._align(self.HEADER + rows * J * O * 4)]
+        self.raw_off = self.raw_offs[0]
+        self.xv_off = [self._align(self.raw_offs[1] + rows * J * O * 4)]
+        self.xv_off.append(self._align(self.xv_off[0] + rows * O * 4))
+        self.nbytes = self._align(self.xv_off[1] + rows * O * 4)
+        lib = _lib.lib()
+        ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        with torch.cuda.device(device):
+            _lib.check(lib.fgnn_comm_alloc(self.nbytes, ctypes.byref(ptr), handle), "comm_alloc")
+        self.base = ptr.value
+        self._opened = []
+        if peers is not None:                     # same-process ranks (tests): arena base pointers given directly
+            self.peer_base = list(peers)
+            self.peer_base[rank] = self.base
+        elif world == 1:
+            self.peer_base = [self.base]
+        else:
+            handles = [None] * world
+            torch.distributed.all_gather_object(handles, bytes(handle.raw), group=group)
+            self.peer_base = []
+            for q, h in enumerate(handles):
+                if q == rank:
+                    self.peer_base.append(self.base)
+                    continue
+                pp = ctypes.c_void_p()
+                with torch.cuda.device(device):
+                    _lib.check(lib.fgnn_comm_open(h, ctypes.byref(pp)), "comm_open")
+                self.peer_base.append(pp.value)
+                self._opened.append(pp.value)
+        mem = torch.as_tensor(_DevMem(self.base, self.nbytes), device=device)
+        self._mem = mem
+        self.raws = [mem[o:o + rows * J * O * 4].view(torch.float32).view(1, rows, J * O) for o in self.raw_offs]
+        self.raw = self.raws[0]
+        self.xv = [mem[o:o + rows * O * 4].view(torch.float32).view(1, rows, O) for o in self.xv_off]
+        self.row0, self.row1 = shard_range(rows, rank, world)
+        self.epoch = 0
+
+    @staticmethod
+    def _align(n):
+        return (n + 255) // 256 * 256
+
+    def set_peers(self, bases):
+        self.peer_base = list(bases)
+
+    def forward(self, dst, bias, scale, shift, activation=_lib.ACT_RELU, slope=0.0, stream=None, raw_index=0,
+                raw_mask=None, out_mask=None):
+        """Launch the exchange of raw buffer `raw_index` into xv[dst] of every rank (asynchronous).
+        raw_mask / out_mask: uint32-as-int32 [rows] device tensors (fgnn_exchange_args), or None = dense."""
+        self.epoch += 1
+        a = _lib.ExchangeArgs()
+        for q in range(self.world):
+            a.raw[q] = self.peer_base[q] + self.raw_offs[raw_index]
+            a.out[q] = self.peer_base[q] + self.xv_off[dst]
+            a.flags[q] = self.peer_base[q]
+        a.counter = self.base + 128
+        a.bias = bias.data_ptr() if bias is not None else None
+        a.bn_scale = scale.data_ptr() if scale is not None else None
+        a.bn_shift = shift.data_ptr() if shift is not None else None
+        a.rows, a.row0, a.row1 = self.rows, self.row0, self.row1
+        a.world, a.rank, a.J, a.O = self.world, self.rank, self.J, self.O
+        a.activation, a.act_slope, a.epoch, a.ctas = int(activation), float(slope), self.epoch, self.ctas
+        a.raw_mask = raw_mask.data_ptr() if raw_mask is not None else None
+        a.out_mask = out_mask.data_ptr() if out_mask is not None else None
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().fgnn_exchange_forward(ctypes.byref(a), ctypes.c_void_p(st.cuda_stream)), "exchange_forward")
+        return self.xv[dst]
+
+    def close(self):
+        lib = _lib.lib()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for pp in self._opened:
+                lib.fgnn_comm_close(ctypes.c_void_p(pp))
+            self._opened = []
+            if self.base:
+                self.raw = self.raws = self.xv = self._mem = None
+                lib.fgnn_comm_free(ctypes.c_void_p(self.base))
+                self.base = 0
+
+
 class ShardedLayerPlan:
     """Everything rank `rank` of `world` needs to run FGNN layers on its factor shard.
 
     `types` = list of fgnn_b200.graphs.FactorType (full graph, host); tables are built once.
     """
 
-    def __init__(self, types, rank, world, device, group=None, comm_sms=16):
+    def __init__(self, types, rank, world, device, group=None, comm_sms=16, exchange="nccl", exchange_ctas=32):
         self.rank, self.world, self.device, self.group = rank, world, device, group
+        # "nccl": all_reduce(MAX) + epilogue kernel; "peer": one fused kernel over NVLink peer memory (PeerExchange)
+        self.exchange = exchange
+        self.exchange_ctas = exchange_ctas        # 512-thread CTAs of the exchange kernel, two per SM
+        # The V->F calls of layer l always run beside the exchange of layer l and leave it its SMs.  By the time the
+        # F->V calls of layer l+1 start, that exchange has normally finished (it is shorter than the V->F calls), so
+        # they take the whole GPU unless told otherwise; CTAs that find an SM still taken simply start a little later.
+        self.limit_f2v = False
+        self.px = None
+        self._comm_stream = None
         # SMs left to the collective while V->F runs beside it (the tensor-core kernel owns whole SMs)
         self.comm_sms = comm_sms
         self.n_sms = torch.cuda.get_device_properties(device).multi_processor_count if device.type == "cuda" else 0
@@ -95,6 +207,25 @@ class ShardedLayerPlan:
         self.out_rows = [torch.from_numpy(l.var).to(device) for l in self.f2v]
         self._raw = None
         self._et_cache = {}
+        # static sparsity of the shards for the peer exchange: which (rank, type) touches which variable.  Every rank
+        # holds the whole (host) graph, so the masks need no communication.
+        self.raw_mask = self.out_mask = None
+        if exchange == "peer" and world > 1 and world * len(types) <= 32:
+            raw_bits = np.zeros(self.n_vars, dtype=np.uint32)
+            out_bits = np.zeros(self.n_vars, dtype=np.uint32)
+            for q in range(world):
+                for j, t in enumerate(types):
+                    lo, hi = shard_range(t.n_factors, q, world)
+                    touched = ((np.asarray(t.idx_f2v) >= lo) & (np.asarray(t.idx_f2v) < hi)).any(1)
+                    raw_bits[touched] |= np.uint32(1 << (q * len(types) + j))
+                    # variables the rank gathers in its V->F calls: those named by its factors
+                    named = np.zeros(self.n_vars, dtype=bool)
+                    named[np.asarray(t.idx_v2f[lo:hi]).reshape(-1)] = True
+                    out_bits[named] |= np.uint32(1 << q)
+            self.raw_mask = torch.from_numpy(raw_bits.view(np.int32)).to(device)
+            self.out_mask = torch.from_numpy(out_bits.view(np.int32)).to(device)
+            self.link_fraction = (float(np.mean([bin(int(b)).count("1") for b in raw_bits[::97]])) / (world * len(types)),
+                                  float(np.mean([bin(int(b)).count("1") for b in out_bits[::97]])) / world)
 
     # -- inputs ------------------------------------------------------------------------------
     def local_factor_features(self, x_f_full):
@@ -106,6 +237,77 @@ class ShardedLayerPlan:
         ev = [e[:, :, lo:hi].contiguous() for e, (lo, hi) in zip(et_v2f_full, self.ranges)]
         ef = [l.gather_etype(e) for l, e in zip(self.f2v, et_f2v_full)]
         return ev, ef
+
+    # -- peer-memory exchange ----------------------------------------------------------------
+    def peer_buffers(self, J, O):
+        """The two arena-backed variable-feature buffers [1,N,O] (layer l reads [l & 1], writes [(l + 1) & 1])."""
+        if self.px is None:
+            self.px = PeerExchange(self.n_vars, J, O, self.rank, self.world, self.device, self.group, ctas=self.exchange_ctas)
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        return self.px.xv
+
+    def layer_peer(self, src, x_f_local, et_v2f_local, et_f2v_local, weights, out_f_local, kernel=_lib.KERNEL_AUTO,
+                   workspaces=None, last=False):
+        """One layer with the fused peer-memory exchange: reads the variable features from peer_buffers()[src],
+        leaves the new ones in peer_buffers()[src ^ 1] on every rank -- valid after peer_wait() or the next call.
+
+        Order on the main stream: the F->V partial maxima (they need only the factor features, so they do NOT wait
+        for the previous layer's exchange) into raw buffer `src`; the exchange kernel is launched on a side stream;
+        then, once the PREVIOUS layer's exchange has landed, the V->F calls.  The exchange of layer l therefore runs
+        beside V->F of layer l and F->V of layer l+1, all of which leave it `ctas / 2` SMs (sm_limit)."""
+        J = len(self.types)
+        O = weights[0]["f2v"]["filters"].shape[1] // et_f2v_local[0].shape[1]
+        xv = self.peer_buffers(J, O)
+        px = self.px
+        x_v = xv[src]
+        nm = lambda t: t.permute(0, 2, 1).unsqueeze(-1)
+        main = torch.cuda.current_stream(self.device)
+        sms = self.n_sms - (px.ctas + 1) // 2               # two exchange CTAs share an SM
+        raw = self.raw = px.raws[src]
+        if self.raw_mask is None:
+            raw.fill_(float("-inf"))      # with the masks nobody reads a (row, type) this rank's calls do not write
+        for j in range(J):
+            if self.f2v[j].n_rows > 0:
+                w = weights[j]["f2v"]
+                wsj = workspaces[j] if workspaces is not None else {}
+                view = raw[:, :, j * O:(j + 1) * O]
+                mp_forward(nm(x_f_local[j]), self.idx_f2v[j], et_f2v_local[j], w["filters"], None, None, None,
+                           extension=0, aggregator=_lib.AGG_MAX, activation=_lib.ACT_NONE, kernel=kernel,
+                           mask_negative=True, out=nm(view), tile_slots=self.tile_slots[j], out_rows=self.out_rows[j],
+                           workspace=wsj.get("f2v"), filters_version=wsj.get("ver_f2v", 0),
+                           sm_limit=sms if self.limit_f2v else 0)
+        key = tuple(w["f2v"]["bias"].data_ptr() for w in weights)
+        if getattr(self, "_epi_key", None) != key:
+            self._epi = [torch.cat([w["f2v"][k] for w in weights]).contiguous() for k in ("bias", "scale", "shift")]
+            self._epi_key = key
+        bias, scale, shift = self._epi
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self._comm_stream.wait_event(ready)
+        # intermediate layers: a rank receives only the rows its own V->F calls will gather; the last layer's
+        # features go to everyone in full (they are the result)
+        px.forward(src ^ 1, bias, scale, shift, _lib.ACT_RELU, 0.0, stream=self._comm_stream, raw_index=src,
+                   raw_mask=self.raw_mask, out_mask=None if last else self.out_mask)
+        done = torch.cuda.Event()
+        done.record(self._comm_stream)
+        self.peer_wait()                                    # x_v (the previous layer's exchange) must have landed
+        self._peer_done = done
+        for j in range(J):
+            if x_f_local[j].shape[1] > 0:
+                w = weights[j]["v2f"]
+                wsj = workspaces[j] if workspaces is not None else {}
+                mp_forward(nm(x_v), self.idx_v2f[j], et_v2f_local[j], w["filters"], w["bias"], w["scale"], w["shift"],
+                           extension=0, aggregator=_lib.AGG_MAX, activation=_lib.ACT_RELU, kernel=kernel,
+                           out=nm(out_f_local[j]), workspace=wsj.get("v2f"), filters_version=wsj.get("ver_v2f", 0),
+                           sm_limit=sms)
+        return xv[src ^ 1]
+
+    def peer_wait(self):
+        """Make the current stream wait for the last launched exchange (its output buffer is then complete)."""
+        done = getattr(self, "_peer_done", None)
+        if done is not None:
+            torch.cuda.current_stream(self.device).wait_event(done)
+            self._peer_done = None
 
     # -- one layer ---------------------------------------------------------------------------
     def layer(self, x_v, x_f_local, et_v2f_local, et_f2v_local, weights, out_v, out_f_local, kernel=_lib.KERNEL_AUTO,

@@ -188,6 +188,42 @@ int fgnn_epilogue_sum_forward(const float* in, float* out, int64_t rows, int32_t
                               const float* bn_scale, const float* bn_shift, int32_t activation, float act_slope,
                               int32_t accumulate, void* stream);
 
+/* ---- factor-sharded layer: the cross-GPU step as one kernel over NVLink peer memory -------------
+ * Every rank owns an ARENA allocated by this library (cudaMalloc, zero-filled) whose IPC handle the host code
+ * passes to the other ranks (one process per GPU); `fgnn_comm_open` maps a peer's arena.  The caller lays the
+ * arena out: 2*8 uint32 epoch flags + one uint64 block counter, the raw aggregate [rows, J*O] and the next-layer
+ * feature buffers [rows, O] (factor-graph-neural-network_b200/parallel.py: PeerExchange). */
+int fgnn_comm_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64);
+int fgnn_comm_open(const unsigned char* handle64, void** dev_ptr);
+int fgnn_comm_close(void* dev_ptr);
+int fgnn_comm_free(void* dev_ptr);
+
+typedef struct fgnn_exchange_args {
+  const float* raw[8];   /* per rank: raw per-type maxima [rows, J*O] of that rank's factor shard (-inf = none)        */
+  float* out[8];         /* per rank: next-layer variable features [rows, O]; this rank writes rows row0..row1-1 of ALL */
+  uint32_t* flags[8];    /* per rank: 16 uint32 epoch flags (A[8] then B[8]) in that rank's arena                        */
+  uint64_t* counter;     /* this rank's block counter (in its own arena); every launch must use the same `ctas`          */
+  const float* bias;     /* [J*O] or NULL; bn_scale / bn_shift likewise (both or neither)                                 */
+  const float* bn_scale;
+  const float* bn_shift;
+  int64_t rows, row0, row1;
+  int32_t world, rank, J, O;
+  int32_t activation;    /* fgnn_activation */
+  float act_slope;
+  uint32_t epoch;        /* > 0, the same on every rank, growing by one per call                                          */
+  int32_t ctas;          /* grid of 512-thread CTAs, two per SM (<= 128; 0 = 64): small, so the kernel is co-resident beside
+                            sm_limit-ed launches                                                                          */
+  /* Static sparsity of the shards (both optional, device, [rows] uint32): a rank's factors touch only some variables,
+     so its raw row is -inf elsewhere and it never gathers the others' features.                                       */
+  const uint32_t* raw_mask; /* bit q*J+j set: rank q's raw row holds data of type j (unset: never read, taken as -inf) */
+  const uint32_t* out_mask; /* bit q set: rank q needs the finished row (unset: not written to it; own rank always)   */
+} fgnn_exchange_args;
+
+/* out_q[n, o] = sum_j act(bn_j(max_r raw_r[n, j*O+o] + bias_j[o])) for n in [row0,row1), written into every rank's
+ * `out`; returns when launched.  When the kernel completes on a rank, all rows of its own `out` are in place and no
+ * peer still reads its `raw` (epoch flags, system-scope release/acquire).  All ranks launch it with the same epoch. */
+int fgnn_exchange_forward(const fgnn_exchange_args* args, void* stream);
+
 /* Layout helper: channel-major [B,C,N] -> node-major [B,N,C] (the reference's
  * x.permute(0,2,3,1).contiguous(), mp_nn.py:125). */
 int fgnn_to_node_major(const float* x, float* out, int32_t B, int32_t C, int32_t N, int64_t x_sb,

@@ -538,3 +538,67 @@ def test_sharded_plan_equals_single_gpu(world, kernel):
     # work really is sharded: live slots per rank add up to the table size
     for j, ty in enumerate(types):
         assert sum(p.f2v[j].live_slots for p in plans) == ty.idx_f2v.size
+
+
+def test_peer_exchange_two_ranks_on_one_device():
+    """fgnn_exchange_forward (max over ranks + per-type epilogue + sum over types + broadcast, one kernel over peer
+    memory): two ranks' arenas on this device, their kernels running concurrently on two streams, against
+    torch.maximum + fgnn_epilogue_sum_forward.  Three epochs exercise the flag protocol and the ping-pong buffers."""
+    from fgnn_b200.parallel import PeerExchange
+    dev = torch.device(DEV)
+    N, J, O = 5003, 2, 64
+    rng = np.random.default_rng(31)
+    px = [PeerExchange(N, J, O, r, 2, dev, peers=[0, 0]) for r in range(2)]
+    try:
+        bases = [px[0].base, px[1].base]
+        for q in px:
+            q.set_peers(bases)
+        bias, scale, shift = (t(rng.uniform(-0.2, 0.2, J * O).astype(np.float32)), t(rng.uniform(0.8, 1.2, J * O).astype(np.float32)),
+                              t(rng.uniform(-0.2, 0.2, J * O).astype(np.float32)))
+        streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        for epoch in range(3):
+            dst = epoch & 1
+            raws = []
+            for r in range(2):
+                a = rng.standard_normal((1, N, J * O)).astype(np.float32)
+                a[:, rng.random(N) < 0.4] = -np.inf                      # rows this rank's shard does not touch
+                a[:, :7] = -np.inf                                        # rows nobody touches
+                px[r].raw.copy_(t(a))
+                raws.append(t(a))
+            torch.cuda.synchronize()
+            raw_mask = out_mask = None
+            if epoch == 2:            # static shard sparsity: untouched rows are not read, unneeded rows not written
+                bits = np.zeros(N, dtype=np.uint32)
+                for r in range(2):
+                    fin = np.isfinite(raws[r].cpu().numpy()[0, :, 0])
+                    for j in range(J):
+                        bits[fin] |= np.uint32(1 << (r * J + j))
+                raw_mask = t(bits.view(np.int32))
+                want = rng.integers(0, 4, N).astype(np.uint32)
+                out_mask = t(want.view(np.int32))
+                for r in range(2):
+                    px[r].xv[dst].fill_(-7.0)
+                torch.cuda.synchronize()
+            for r in range(2):
+                px[r].forward(dst, bias, scale, shift, _lib.ACT_RELU, 0.0, stream=streams[r], raw_mask=raw_mask, out_mask=out_mask)
+            torch.cuda.synchronize()
+            red = torch.maximum(raws[0], raws[1]).contiguous()
+            ref = torch.empty((1, N, O), dtype=torch.float32, device=dev)
+            _lib.check(_lib.lib().fgnn_epilogue_sum_forward(red.data_ptr(), ref.data_ptr(), N, O, J, bias.data_ptr(), scale.data_ptr(),
+                                                            shift.data_ptr(), _lib.ACT_RELU, 0.0, 0,
+                                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "epilogue_sum")
+            torch.cuda.synchronize()
+            for r in range(2):
+                if out_mask is None:
+                    assert torch.equal(px[r].xv[dst], ref), f"epoch {epoch} rank {r}"
+                else:                 # a rank holds the rows it asked for and the rows it owns; the rest was left alone
+                    rows = np.arange(N)
+                    owned = (rows >= px[r].row0) & (rows < px[r].row1)
+                    got = ((want >> r) & 1).astype(bool) | owned
+                    gi, ni = torch.from_numpy(np.nonzero(got)[0]).to(dev), torch.from_numpy(np.nonzero(~got)[0]).to(dev)
+                    assert torch.equal(px[r].xv[dst][:, gi], ref[:, gi]), f"masked epoch rank {r}"
+                    assert bool((px[r].xv[dst][:, ni] == -7.0).all())
+            assert torch.isinf(ref[:, :7]).all() and torch.isfinite(ref[:, 7:]).any()
+    finally:
+        for q in px:
+            q.close()
