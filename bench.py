@@ -62,7 +62,9 @@ def parse_args():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU: the cross-GPU step as one kernel over NVLink peer memory (csrc/exchange.cu), or "
                          "NCCL all_reduce(MAX) + epilogue kernel")
-    ap.add_argument("--exchange-ctas", type=int, default=32, help="grid of the peer exchange kernel (512-thread CTAs, two per SM)")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="launch every step from Python instead of replaying a CUDA graph of the step")
+    ap.add_argument("--exchange-ctas", type=int, default=64, help="grid of the peer exchange kernel (512-thread CTAs, two per SM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
@@ -381,8 +383,30 @@ def run_native(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing -----------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(2):
         step(d_in)
+    barrier()
+    # The step is launch-bound from Python once the kernels are short (20-30 launches of 20-150 us, more so when
+    # sharded): capture it once -- streams, events, programmatic launch edges and all -- and replay the graph.
+    run_step, graphed, launches_per_step = (lambda: step(d_in)), False, None
+    if not args.no_graph and not (world > 1 and args.exchange == "nccl"):
+        try:
+            graph = torch.cuda.CUDAGraph()
+            l0 = fgnn_b200.launch_count()
+            with torch.cuda.graph(graph):
+                step(d_in)
+            launches_per_step = fgnn_b200.launch_count() - l0
+            run_step, graphed = graph.replay, True
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"bench: CUDA graph capture failed ({type(e).__name__}: {e}); launching from Python\n")
+            torch.cuda.synchronize()
+    if world > 1:
+        ok = torch.tensor([1 if graphed else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if graphed and not bool(ok.item()):
+            run_step, graphed = (lambda: step(d_in)), False
+    for _ in range(max(args.warmup, 3)):
+        run_step()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -392,11 +416,11 @@ def run_native(args):
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        step(d_in)
+        run_step()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = fgnn_b200.launch_count() - launches0
+    launches = (launches_per_step * args.steps) if graphed else (fgnn_b200.launch_count() - launches0)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         tt = torch.tensor([ms], device=dev)
@@ -535,7 +559,8 @@ def run_native(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "messages_per_layer": msgs_layer, "layers": L,
-                   "kernel": args.kernel, "source_stationary_calls": sorted(plans), "l2": "per-step working set (~%d MB/layer) exceeds the 126 MB L2; no explicit flush"
+                   "kernel": args.kernel, "source_stationary_calls": sorted(plans),
+                   "launch": "CUDA graph of the step, replayed" if graphed else "from Python, call by call", "l2": "per-step working set (~%d MB/layer) exceeds the 126 MB L2; no explicit flush"
                    % (bytes_layer // 1_000_000), "parallelism": ("factor-sharded x%d + %s per layer" % (world, "fused max-reduce/epilogue/broadcast kernel over NVLink peer memory"
                                                                          if args.exchange == "peer" else "NCCL max-all-reduce"))
                    if world > 1 else "single GPU"},

@@ -70,12 +70,12 @@ __device__ __forceinline__ float4 ld_peer_f4_if(const float* p, bool on) {
   return v;
 }
 
-__device__ __forceinline__ void wait_all(const ExParams& p, int phase) {
+__device__ __forceinline__ void wait_all(const ExParams& p, int phase, uint32_t epoch) {
   if ((int)threadIdx.x < p.world) {
     const uint32_t* f = p.flags[p.rank] + phase * kMaxRanks + threadIdx.x;
     uint32_t spins = 0;
     // epochs only grow; a peer may already be an epoch ahead in phase A of the next layer
-    while ((int32_t)(ld_acquire_sys(f) - p.epoch) < 0) {
+    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
       if (++spins > kSpinLimit) __trap();
       __nanosleep(64);
     }
@@ -89,10 +89,18 @@ __device__ __forceinline__ void wait_all(const ExParams& p, int phase) {
 template <int WORLD, int UNROLL, int kJ>            // kJ: factor types per load batch (J is 1-2 in FGNN; larger J loops)
 __global__ void __launch_bounds__(512, 2)
 exchange_kernel(const ExParams p) {
+  // The epoch of this launch.  epoch == 0 in the arguments: derive it from this rank's block counter -- every launch
+  // adds gridDim.x to it, and it cannot reach the next multiple before the block reading it here has finished -- so a
+  // launch captured in a CUDA graph (frozen arguments) still counts up on every replay, in step on all ranks.
+  __shared__ uint32_t s_epoch;
+  if (threadIdx.x == 0)
+    s_epoch = p.epoch ? p.epoch : (uint32_t)(*reinterpret_cast<volatile unsigned long long*>(p.counter) / gridDim.x) + 1u;
+  __syncthreads();
+  const uint32_t epoch = s_epoch;
   // A: my raw buffer is complete (stream order) -> tell every rank, once
   if (blockIdx.x == 0 && (int)threadIdx.x < WORLD)
-    st_release_sys(p.flags[threadIdx.x] + 0 * kMaxRanks + p.rank, p.epoch);
-  wait_all(p, 0);
+    st_release_sys(p.flags[threadIdx.x] + 0 * kMaxRanks + p.rank, epoch);
+  wait_all(p, 0, epoch);
 
   const int O4 = p.O >> 2, JO = p.J * p.O;
   const int64_t total = (p.row1 - p.row0) * O4;
@@ -176,10 +184,10 @@ exchange_kernel(const ExParams p) {
     const unsigned long long done = atomicAdd(p.counter, 1ull) + 1ull;
     if (done % gridDim.x == 0) {                              // every launch adds gridDim.x: the last block of this launch
       __threadfence_system();
-      for (int q = 0; q < WORLD; ++q) st_release_sys(p.flags[q] + 1 * kMaxRanks + p.rank, p.epoch);
+      for (int q = 0; q < WORLD; ++q) st_release_sys(p.flags[q] + 1 * kMaxRanks + p.rank, epoch);
     }
   }
-  wait_all(p, 1);
+  wait_all(p, 1, epoch);
 }
 
 template <int WORLD, int UNROLL, int kJ>
@@ -230,7 +238,7 @@ int fgnn_exchange_forward(const fgnn_exchange_args* a, void* stream_) {
   if (!a || a->world < 1 || a->world > kMaxRanks || a->rank < 0 || a->rank >= a->world) return FGNN_ERR_INVALID_ARG;
   if (a->rows <= 0 || a->J <= 0 || a->O <= 0 || (a->O & 3) || a->row0 < 0 || a->row1 < a->row0 || a->row1 > a->rows)
     return FGNN_ERR_INVALID_ARG;
-  if (!a->counter || a->epoch == 0) return FGNN_ERR_INVALID_ARG;
+  if (!a->counter) return FGNN_ERR_INVALID_ARG;
   if ((a->bn_scale == nullptr) != (a->bn_shift == nullptr)) return FGNN_ERR_INVALID_ARG;
   ExParams p;
   for (int q = 0; q < kMaxRanks; ++q) {

@@ -141,8 +141,8 @@ class PeerExchange:
     def forward(self, dst, bias, scale, shift, activation=_lib.ACT_RELU, slope=0.0, stream=None, raw_index=0,
                 raw_mask=None, out_mask=None):
         """Launch the exchange of raw buffer `raw_index` into xv[dst] of every rank (asynchronous).
-        raw_mask / out_mask: uint32-as-int32 [rows] device tensors (fgnn_exchange_args), or None = dense."""
-        self.epoch += 1
+        raw_mask / out_mask: uint32-as-int32 [rows] device tensors (fgnn_exchange_args), or None = dense.
+        The kernel numbers its launches itself (epoch 0), so the launch can be captured in a CUDA graph."""
         a = _lib.ExchangeArgs()
         for q in range(self.world):
             a.raw[q] = self.peer_base[q] + self.raw_offs[raw_index]
@@ -154,7 +154,7 @@ class PeerExchange:
         a.bn_shift = shift.data_ptr() if shift is not None else None
         a.rows, a.row0, a.row1 = self.rows, self.row0, self.row1
         a.world, a.rank, a.J, a.O = self.world, self.rank, self.J, self.O
-        a.activation, a.act_slope, a.epoch, a.ctas = int(activation), float(slope), self.epoch, self.ctas
+        a.activation, a.act_slope, a.epoch, a.ctas = int(activation), float(slope), 0, self.ctas
         a.raw_mask = raw_mask.data_ptr() if raw_mask is not None else None
         a.out_mask = out_mask.data_ptr() if out_mask is not None else None
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
@@ -181,7 +181,7 @@ class ShardedLayerPlan:
     `types` = list of fgnn_b200.graphs.FactorType (full graph, host); tables are built once.
     """
 
-    def __init__(self, types, rank, world, device, group=None, comm_sms=16, exchange="nccl", exchange_ctas=32):
+    def __init__(self, types, rank, world, device, group=None, comm_sms=16, exchange="nccl", exchange_ctas=64):
         self.rank, self.world, self.device, self.group = rank, world, device, group
         # "nccl": all_reduce(MAX) + epilogue kernel; "peer": one fused kernel over NVLink peer memory (PeerExchange)
         self.exchange = exchange

@@ -210,7 +210,8 @@ typedef struct fgnn_exchange_args {
   int32_t world, rank, J, O;
   int32_t activation;    /* fgnn_activation */
   float act_slope;
-  uint32_t epoch;        /* > 0, the same on every rank, growing by one per call                                          */
+  uint32_t epoch;        /* 0: the kernel numbers its launches itself from `counter` (launches captured in a CUDA graph
+                            keep counting on replay); else > 0, the same on every rank, growing by one per call            */
   int32_t ctas;          /* grid of 512-thread CTAs, two per SM (<= 128; 0 = 64): small, so the kernel is co-resident beside
                             sm_limit-ed launches                                                                          */
   /* Static sparsity of the shards (both optional, device, [rows] uint32): a rank's factors touch only some variables,
