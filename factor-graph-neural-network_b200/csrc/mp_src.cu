@@ -437,7 +437,7 @@ int launch_mp_src(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream)
   uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
   if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255)) return FGNN_ERR_WORKSPACE;
   const int OT = p.O * p.T;
-  const int wrc = tc_prepare_weights(p.W, ws, OT, a->filters_version, stream);
+  const int wrc = tc_prepare_weights(p.W, ws, tc::kC, OT, a->filters_version, stream);
   if (wrc != FGNN_OK) return wrc;
   SrcParams sp;
   sp.x = p.x; sp.src_ptr = a->src_ptr; sp.et_edges = reinterpret_cast<const float*>(a->etype_edges);

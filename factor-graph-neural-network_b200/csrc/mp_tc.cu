@@ -68,11 +68,12 @@ __device__ unsigned long long g_trace[16 * 4096];
 // 16-byte chunks XOR-swizzled with row % 8): image[part][n][c], n = column o*T+t; part 0 = bf16(W)
 // (all the bf16-I/O kernel uses), part 1 = bf16(W - part 0).
 // ---------------------------------------------------------------------------------------------
-__global__ void w_split_kernel(const float* __restrict__ W, uint8_t* __restrict__ ws, int OT, int64_t version) {
+__global__ void w_split_kernel(const float* __restrict__ W, uint8_t* __restrict__ ws, int C, int OT, int64_t version) {
   tc::Header* h = reinterpret_cast<tc::Header*>(ws);
-  if (version != 0 && h->version == version && h->filters == W && h->C == tc::kC && h->OT == OT) return;
+  if (version != 0 && h->version == version && h->filters == W && h->C == C && h->OT == OT) return;
   uint8_t* img = ws + tc::kHeaderBytes;
-  const int total = OT * (tc::kC / 8);                       // one 16-byte chunk (8 channels) per thread-iteration
+  const int KA = C / tc::kC;                                 // K atoms of 64 channels: image[part][ka][n][64 bf16]
+  const int total = OT * (C / 8);                            // one 16-byte chunk (8 channels) per thread-iteration
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int n = i % OT, chunk = i / OT;                    // consecutive threads: consecutive columns (coalesced)
     uint32_t hi[4], lo[4];
@@ -85,12 +86,13 @@ __global__ void w_split_kernel(const float* __restrict__ W, uint8_t* __restrict_
       hi[j] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
       lo[j] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
     }
-    const size_t off = (size_t)n * 128 + (size_t)((chunk ^ (n & 7)) * 16);
+    const int ka = chunk >> 3, cc = chunk & 7;
+    const size_t off = (size_t)ka * OT * 128 + (size_t)n * 128 + (size_t)((cc ^ (n & 7)) * 16);
     *reinterpret_cast<uint4*>(img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(img + (size_t)OT * 128 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(img + (size_t)KA * OT * 128 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {                 // read by later launches only (stream order)
-    h->version = version; h->filters = W; h->C = tc::kC; h->OT = OT;
+    h->version = version; h->filters = W; h->C = C; h->OT = OT;
   }
 }
 
@@ -98,8 +100,10 @@ __global__ void w_split_kernel(const float* __restrict__ W, uint8_t* __restrict_
 // main kernel
 //   T   edge types (columns per output channel)        NC  accumulator columns per MMA chunk
 //   NCH chunks per CTA (CTA column slice = NC*NCH)     AGG aggregator      XB  bf16 x / etype / out
+//   KA  K atoms: input channels / 64 (1, or 2 for the C = 128 layers of the LDPC model, fp32 I/O only).  With two
+//       atoms an A stage takes 128 TMEM columns, so there are two accumulator stages instead of three.
 // ---------------------------------------------------------------------------------------------
-template <int T, int NC, int NCH, int AGG, bool XB>
+template <int T, int NC, int NCH, int AGG, bool XB, int KA>
 __global__ void __launch_bounds__(tc::kThreads, 1)
 mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, const int n_workers,
              const int n_tiles) {
@@ -110,8 +114,11 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
   constexpr int NLD = NC / (16 * kEpiGroups);  // 16-column loads per chunk per epilogue group
   constexpr int CPG = NC / (T * kEpiGroups);   // channels per chunk per epilogue group
   constexpr int CHG = CPG * NCH;               // channels (accumulator registers) per epilogue thread
-  constexpr int NST = a_stages(COLS, CH, XB);  // raw-ring stages that fit beside the filter slice and the output tile
-  constexpr int ROWB = row_bytes(XB), STAGEB = stage_bytes(XB);
+  constexpr int NST = a_stages(COLS, CH, XB, KA);   // raw-ring stages that fit beside the filter slice and the output tile
+  constexpr int ROWB = row_bytes(XB, KA), STAGEB = stage_bytes(XB, KA);
+  constexpr int ACC = KA == 2 ? 2 : kAcc;      // accumulator stages
+  constexpr int TACOL0 = ACC * kAccCols, TACOLS = KA * kTACols;      // TMEM: ACC x 128 accumulator + 2 x KA*64 A-stage columns
+  static_assert(TACOL0 + kTA * TACOLS <= 512 && (KA == 1 || !XB), "tensor memory budget");
   constexpr int OB = XB ? 2 : 4;               // bytes per output element
   constexpr int NTERMS = XB ? 1 : 3;           // MMA terms per K step
   static_assert(NC % (16 * kEpiGroups) == 0 && NC <= kAccCols && 16 % T == 0 && CH <= 64 && NST >= 2 && CPG % 4 == 0 &&
@@ -121,7 +128,7 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
   // 1 KB alignment by OFFSET (not by integer round-trip) so the compiler keeps the shared state space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sB = smem;                                        // [1|2 parts][COLS rows][128 B]  UMMA K-major SW128
-  uint8_t* sA = sB + w_bytes(COLS, XB);                      // [NST][128 rows][ROWB]          raw ring
+  uint8_t* sA = sB + w_bytes(COLS, XB, KA);                  // [NST][128 rows][ROWB]          raw ring
   uint8_t* sOut = sA + NST * STAGEB;                         // [4 quarters][32 rows][CH*OB]   output staging (swizzled chunks)
   float* s_epi = reinterpret_cast<float*>(sOut + out_tile_bytes(CH, XB));   // [3][64]: bias, BN scale, BN shift (16-byte aligned)
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + 3 * 64);
@@ -252,8 +259,8 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
         if (k + 1 < kt) fetch(tile, k + 1); else fetch(tile + n_workers, 0);
 #pragma unroll
         for (int chunk = 0; chunk < NCH; ++chunk) {
-          const uint32_t st = ct % kAcc;
-          mbar_wait(t_full(st), (ct / kAcc) & 1);
+          const uint32_t st = ct % ACC;
+          mbar_wait(t_full(st), (ct / ACC) & 1);
           tc_fence_after();
 #ifdef FGNN_TC_TRACE
           if (chunk == 0 && warp == 0) TC_TRACE(ei, 6);
@@ -405,7 +412,7 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     reg_dec<kRegConv>();
     const int cr = tid - kConvWarp0 * 32;
     const uint32_t row_u = smem_u32(sA) + (uint32_t)cr * ROWB;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTACol0;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + TACOL0;
     uint32_t i = 0;
     for (ItemIter it = first_item(); it.tile < n_tiles; next_item(it), ++i) {
       const uint32_t st = i % NST, use = i / NST;
@@ -422,26 +429,39 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
         mbar_arrive(raw_empty(st));                          // ring stage is free again
         mbar_wait(ta_empty(ta), (tuse & 1) ^ 1);
         tc_fence_after();
-        tmem_st32(lane_addr + ta * kTACols, a);
+        tmem_st32(lane_addr + ta * TACOLS, a);
       } else {
-        float4 v[16];                                        // channels 4c .. 4c+3 in chunk c (stored at c ^ (row & 15))
+        // per K atom (64 channels = 256 bytes of the row): channels 4c .. 4c+3 of the atom in chunk c, stored at
+        // c ^ (row & 15) inside the atom's 16 chunks
+        uint32_t hi[KA][32], lo[KA][32];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] = lds_f4(row_u + st * STAGEB + (uint32_t)((c ^ (cr & 15)) * 16));
-        uint32_t hi[32], lo[32];
+        for (int ka = 0; ka < KA; ++ka) {
+          float4 v[16];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[c].x, v[c].y), h1 = __floats2bfloat162_rn(v[c].z, v[c].w);
-          const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-          hi[2 * c] = pack_bf16(h0);
-          hi[2 * c + 1] = pack_bf16(h1);
-          lo[2 * c] = pack_bf16(__floats2bfloat162_rn(v[c].x - f0.x, v[c].y - f0.y));
-          lo[2 * c + 1] = pack_bf16(__floats2bfloat162_rn(v[c].z - f1.x, v[c].w - f1.y));
+          for (int c = 0; c < 16; ++c) v[c] = lds_f4(row_u + st * STAGEB + (uint32_t)(ka * 256 + (c ^ (cr & 15)) * 16));
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[c].x, v[c].y), h1 = __floats2bfloat162_rn(v[c].z, v[c].w);
+            const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+            hi[ka][2 * c] = pack_bf16(h0);
+            hi[ka][2 * c + 1] = pack_bf16(h1);
+            lo[ka][2 * c] = pack_bf16(__floats2bfloat162_rn(v[c].x - f0.x, v[c].y - f0.y));
+            lo[ka][2 * c + 1] = pack_bf16(__floats2bfloat162_rn(v[c].z - f1.x, v[c].w - f1.y));
+          }
+          if (KA == 2 && ka == 0) {                          // two atoms: the first goes to tensor memory before the second is read
+            mbar_wait(ta_empty(ta), (tuse & 1) ^ 1);
+            tc_fence_after();
+            tmem_st32(lane_addr + ta * TACOLS, hi[0]);
+            tmem_st32(lane_addr + ta * TACOLS + KA * 32, lo[0]);
+          }
         }
         mbar_arrive(raw_empty(st));                          // ring stage is free again: every chunk has been consumed above
-        mbar_wait(ta_empty(ta), (tuse & 1) ^ 1);
-        tc_fence_after();
-        tmem_st32(lane_addr + ta * kTACols, hi);
-        tmem_st32(lane_addr + ta * kTACols + 32, lo);
+        if (KA == 1) {
+          mbar_wait(ta_empty(ta), (tuse & 1) ^ 1);
+          tc_fence_after();
+        }
+        tmem_st32(lane_addr + ta * TACOLS + (KA - 1) * 32, hi[KA - 1]);
+        tmem_st32(lane_addr + ta * TACOLS + KA * 32 + (KA - 1) * 32, lo[KA - 1]);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -486,7 +506,9 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     // chunk q of tile row rr lands at position q ^ (rr & (LPR-1)) (the converter's per-row reads are then
     // conflict-free).  The swizzle term repeats every NDO instructions, so the shared-memory offset is one
     // of NDO lane constants plus a compile-time multiple of LPR rows.
-    constexpr int NIT = ROWS_W / RPW, NDO = LPR / RPW;
+    // (two K atoms: 32 lanes per 512-byte row, the swizzle acts inside each atom's 16 chunks and the offset is
+    // computed per copy)
+    constexpr int NIT = ROWS_W / RPW, NDO = KA == 1 ? LPR / RPW : 1, SWZ = (LPR < 16 ? LPR : 16) - 1;
     uint32_t dst_off[NDO];
 #pragma unroll
     for (int c = 0; c < NDO; ++c)
@@ -518,7 +540,9 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int u = u0 + j;
-          const uint32_t dst = stage + dst_off[u % NDO] + (uint32_t)((u / NDO) * LPR * ROWB);
+          const uint32_t dst = KA == 1 ? stage + dst_off[u % NDO] + (uint32_t)((u / NDO) * LPR * ROWB)
+                                       : stage + (uint32_t)(pw * ROWS_W + u) * ROWB +
+                                             (uint32_t)(((q & ~SWZ) | ((q ^ u) & SWZ)) * 16);
           const bool ok = o[j] != 0xffffffffu;
           cp_async16(dst, xq + (ok ? o[j] : 0u), ok ? 16u : 0u);
         }
@@ -536,10 +560,10 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     const uint32_t sB_u = smem_u32(sB);
     if (elect_one()) {
       const int OT = p.O * p.T;
-      constexpr uint32_t part = COLS * 128, piece = part < 32768u ? part : 32768u;
+      constexpr uint32_t part = COLS * 128, piece = part < 32768u ? part : 32768u;      // one (part, K atom) slab
       constexpr int parts = XB ? 1 : 2;
-      mbar_expect_tx(w_full, parts * part);
-      for (int h = 0; h < parts; ++h) {
+      mbar_expect_tx(w_full, parts * KA * part);
+      for (int h = 0; h < parts * KA; ++h) {                   // image and shared memory: [part][ka][column][64 bf16]
         const uint8_t* src = wimg + kHeaderBytes + (size_t)h * OT * 128 + (size_t)col0 * 128;
         for (uint32_t o = 0; o < part; o += piece) bulk_g2s(sB_u + h * part + o, src + o, piece, w_full);
       }
@@ -554,22 +578,25 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
       const uint32_t ta = i % kTA, tuse = i / kTA;
       mbar_wait(ta_full(ta), tuse & 1);
       TC_TRACE(i, 4);
-      const uint32_t a_hi = tmem_base + kTACol0 + ta * kTACols, a_lo = a_hi + 32;
+      const uint32_t a_hi = tmem_base + TACOL0 + ta * TACOLS, a_lo = a_hi + KA * 32;
 #pragma unroll
       for (int chunk = 0; chunk < NCH; ++chunk) {
-        const uint32_t ts = ct % kAcc;
-        mbar_wait(t_empty(ts), ((ct / kAcc) & 1) ^ 1);
+        const uint32_t ts = ct % ACC;
+        mbar_wait(t_empty(ts), ((ct / ACC) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ts * kAccCols;
-        const uint32_t b_hi = (sB_u + (uint32_t)chunk * NC * 128u) >> 4, b_lo = b_hi + ((uint32_t)COLS * 128u >> 4);
+        const uint32_t b_hi = (sB_u + (uint32_t)chunk * NC * 128u) >> 4, b_lo = b_hi + ((uint32_t)(KA * COLS) * 128u >> 4);
         if (elect_one()) {
 #pragma unroll
           for (int term = 0; term < NTERMS; ++term) {        // fp32 I/O: xl*Wh + xh*Wl + xh*Wh; bf16 I/O: x*Wh
             const uint32_t a = (!XB && term == 0) ? a_lo : a_hi;
             const uint32_t bb = (!XB && term == 1) ? b_lo : b_hi;
 #pragma unroll
-            for (int ks = 0; ks < kC / 16; ++ks)             // 16 bf16 of K = 8 TMEM columns of A = 32 bytes of a B row
-              umma_bf16_ts(d_tmem, a + ks * 8, desc_hi | (uint64_t)(bb + ks * 2), idesc, (term | ks) != 0);
+            for (int ka = 0; ka < KA; ++ka)
+#pragma unroll
+              for (int ks = 0; ks < kC / 16; ++ks)           // 16 bf16 of K = 8 TMEM columns of A = 32 bytes of a B row
+                umma_bf16_ts(d_tmem, a + ka * 32 + ks * 8, desc_hi | (uint64_t)(bb + ka * ((uint32_t)COLS * 128u >> 4) + ks * 2),
+                             idesc, (term | ka | ks) != 0);
           }
           umma_commit(t_full(ts));                           // accumulator ready when these MMAs retire
           if (chunk == NCH - 1) umma_commit(ta_empty(ta));   // A stage reusable when its readers retire
@@ -601,7 +628,7 @@ struct TcConfig {
   bool ok;
 };
 
-TcConfig pick_config(int T, int agg, int OT, bool xb) {
+TcConfig pick_config(int T, int agg, int OT, bool xb, int ka = 1) {
   // accumulator chunks of NC <= 128 columns (TMEM: 3 x 128 accumulator + 2 x 64 A-stage columns);
   // channels per CTA (NC*NCH/T) <= 64; accumulator registers per epilogue thread = half of that
   // (twice for softmax).  bf16 I/O: the image has one part, so twice the columns fit a CTA.
@@ -615,21 +642,22 @@ TcConfig pick_config(int T, int agg, int OT, bool xb) {
     case 1: c.NC = sm ? 32 : 64; break;
     default: return c;
   }
+  if (ka == 2) c.NCH = 1;       // C = 128: the image of 128 columns (two K atoms, hi + lo) is 64 KB beside a 2 x 64 KB ring
   c.ok = OT % (c.NC * c.NCH) == 0;
   return c;
 }
 
-size_t smem_bytes(const TcConfig& c, bool xb) {
+size_t smem_bytes(const TcConfig& c, bool xb, int ka = 1) {
   const int cols = c.NC * c.NCH, ch = cols / c.T;
-  return 1024 + (size_t)tc::w_bytes(cols, xb) + (size_t)tc::a_stages(cols, ch, xb) * tc::stage_bytes(xb) +
+  return 1024 + (size_t)tc::w_bytes(cols, xb, ka) + (size_t)tc::a_stages(cols, ch, xb, ka) * tc::stage_bytes(xb, ka) +
          (size_t)tc::out_tile_bytes(ch, xb) + tc::kNumBars * 8 + 16 + 3 * 64 * 4;
 }
 
 bool g_pdl = true;      // programmatic dependent launch between consecutive tensor-core launches
 
-template <int T, int NC, int NCH, int AGG, bool XB>
+template <int T, int NC, int NCH, int AGG, bool XB, int KA>
 int launch_one(const MpParams& p, const uint8_t* wimg, int S, int workers, int tiles, size_t smem, cudaStream_t st) {
-  auto kern = mp_tc_kernel<T, NC, NCH, AGG, XB>;
+  auto kern = mp_tc_kernel<T, NC, NCH, AGG, XB, KA>;
   static bool attr_set = false;                              // per instantiation; the value never changes
   if (!attr_set) {
     // the in-kernel setmaxnreg budget assumes the launch register count ptxas chose (see tc::kRegLaunch):
@@ -657,12 +685,12 @@ int launch_one(const MpParams& p, const uint8_t* wimg, int S, int workers, int t
 }
 
 // NCHm: chunks per CTA for max & mean, NCHs: for softmax (must mirror pick_config)
-template <int T, int NCm, int NCHm, int NCs, int NCHs, bool XB>
+template <int T, int NCm, int NCHm, int NCs, int NCHs, bool XB, int KA = 1>
 int launch_agg(const MpParams& p, const uint8_t* wimg, int S, int workers, int tiles, size_t smem, cudaStream_t st) {
   switch (p.agg) {
-    case FGNN_AGG_MAX: return launch_one<T, NCm, NCHm, FGNN_AGG_MAX, XB>(p, wimg, S, workers, tiles, smem, st);
-    case FGNN_AGG_SOFTMAX: return launch_one<T, NCs, NCHs, FGNN_AGG_SOFTMAX, XB>(p, wimg, S, workers, tiles, smem, st);
-    case FGNN_AGG_MEAN: return launch_one<T, NCm, NCHm, FGNN_AGG_MEAN, XB>(p, wimg, S, workers, tiles, smem, st);
+    case FGNN_AGG_MAX: return launch_one<T, NCm, NCHm, FGNN_AGG_MAX, XB, KA>(p, wimg, S, workers, tiles, smem, st);
+    case FGNN_AGG_SOFTMAX: return launch_one<T, NCs, NCHs, FGNN_AGG_SOFTMAX, XB, KA>(p, wimg, S, workers, tiles, smem, st);
+    case FGNN_AGG_MEAN: return launch_one<T, NCm, NCHm, FGNN_AGG_MEAN, XB, KA>(p, wimg, S, workers, tiles, smem, st);
   }
   return FGNN_ERR_UNSUPPORTED;
 }
@@ -680,24 +708,25 @@ extern "C" int fgnn_debug_trace_read(unsigned long long* host, size_t count) {
 // The bf16 image of `W` in `ws` is rebuilt unless this workspace is known to hold the image of exactly these
 // filters (pointer + caller-supplied version).  Host-side mirror of the device header: a cached image costs
 // no launch at all.  version == 0 always rebuilds.
-int tc_prepare_weights(const float* W, uint8_t* ws, int OT, int64_t version, cudaStream_t stream) {
+int tc_prepare_weights(const float* W, uint8_t* ws, int C, int OT, int64_t version, cudaStream_t stream) {
   static std::mutex mu;
   static std::unordered_map<const void*, tc::Header> known;
   bool fresh = false;
   if (version != 0) {
     std::lock_guard<std::mutex> lock(mu);
     auto it = known.find(ws);
-    fresh = it != known.end() && it->second.version == version && it->second.filters == W && it->second.OT == OT;
+    fresh = it != known.end() && it->second.version == version && it->second.filters == W && it->second.OT == OT &&
+            it->second.C == C;
     if (!fresh) {
       if (known.size() > 4096) known.clear();
-      known[ws] = tc::Header{version, W, tc::kC, OT};
+      known[ws] = tc::Header{version, W, C, OT};
     }
   } else {
     std::lock_guard<std::mutex> lock(mu);
     known.erase(ws);
   }
   if (!fresh) {
-    w_split_kernel<<<(OT * (tc::kC / 8) + 255) / 256, 256, 0, stream>>>(W, ws, OT, 0);
+    w_split_kernel<<<(OT * (C / 8) + 255) / 256, 256, 0, stream>>>(W, ws, C, OT, 0);
     count_launch();
     if (cudaGetLastError() != cudaSuccess) return FGNN_ERR_CUDA;
   }
@@ -721,35 +750,37 @@ bool tc_supported(const fgnn_mp_args* a) {
   if (a->extension != FGNN_NO_EXTENSION) return false;
   if (a->dtype != FGNN_F32 && a->dtype != FGNN_BF16) return false;
   const bool xb = a->dtype == FGNN_BF16;
-  if (a->C != tc::kC) return false;
+  if (a->C != tc::kC && !(a->C == 2 * tc::kC && !xb)) return false;        // C = 128: fp32 I/O only
+  const int ka = a->C / tc::kC;
   if (a->aggregator == FGNN_AGG_NONE) return false;
   if (a->x_sc != 1 || a->x_sn != a->C) return false;                              // node-major rows
   if (a->B > 1 && a->x_sb != (int64_t)a->N * a->C) return false;                  // batch-contiguous
-  if ((int64_t)a->B * a->N * tc::row_bytes(xb) >= (int64_t)UINT32_MAX) return false;   // 32-bit source byte offsets
+  if ((int64_t)a->B * a->N * tc::row_bytes(xb, ka) >= (int64_t)UINT32_MAX) return false;   // 32-bit source byte offsets
   if (a->out_sm * (xb ? 2 : 4) >= (int64_t)INT32_MAX) return false;
   if ((reinterpret_cast<uintptr_t>(a->x) & 15) || (reinterpret_cast<uintptr_t>(a->out) & 15)) return false;
   if (a->out_so != 1 || (a->out_sm & (xb ? 7 : 3))) return false;                   // 16-byte aligned output rows
   if (a->B > 1 && a->out_sb != (int64_t)a->M * a->out_sm) return false;             // batch-contiguous rows
   if (a->O % (xb ? 8 : 4)) return false;
-  const TcConfig c = pick_config(a->T, a->aggregator, a->O * a->T, xb);
+  const TcConfig c = pick_config(a->T, a->aggregator, a->O * a->T, xb, ka);
   if (!c.ok) return false;
-  if (smem_bytes(c, xb) > (size_t)tc::kSmemBudget || tc::a_stages(c.NC * c.NCH, c.NC * c.NCH / c.T, xb) < 2) return false;
+  if (smem_bytes(c, xb, ka) > (size_t)tc::kSmemBudget || tc::a_stages(c.NC * c.NCH, c.NC * c.NCH / c.T, xb, ka) < 2) return false;
   if ((int64_t)a->B * a->M >= (int64_t)INT32_MAX - 256) return false;
   return true;
 }
 
 size_t tc_workspace_bytes(const fgnn_mp_args* a) {
-  return tc::kHeaderBytes + (size_t)2 * a->O * a->T * 128;
+  return tc::kHeaderBytes + (size_t)2 * (a->C > tc::kC ? 2 : 1) * a->O * a->T * 128;
 }
 
 int launch_mp_tc(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream) {
   const bool xb = a->dtype == FGNN_BF16;
-  TcConfig c = pick_config(p.T, p.agg, p.O * p.T, xb);
+  const int ka = p.C / tc::kC;
+  TcConfig c = pick_config(p.T, p.agg, p.O * p.T, xb, ka);
   if (!c.ok) return FGNN_ERR_UNSUPPORTED;
   uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
   if (reinterpret_cast<uintptr_t>(ws) & 255) return FGNN_ERR_WORKSPACE;
   const int OT = p.O * p.T;
-  const int wrc = tc_prepare_weights(p.W, ws, OT, a->filters_version, stream);
+  const int wrc = tc_prepare_weights(p.W, ws, p.C, OT, a->filters_version, stream);
   if (wrc != FGNN_OK) return wrc;
 
   const int num_sms = tc_num_sms();
@@ -761,7 +792,17 @@ int launch_mp_tc(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream) 
   if (S > sms) return FGNN_ERR_UNSUPPORTED;
   int workers = sms / S;
   if (workers > tiles) workers = tiles;
-  const size_t smem = smem_bytes(c, xb);
+  const size_t smem = smem_bytes(c, xb, ka);
+  if (ka == 2) {                    // C = 128 (fp32 I/O): one 128-column chunk per CTA
+    switch (p.T) {
+      case 16: return launch_agg<16, 128, 1, 128, 1, false, 2>(p, ws, S, workers, tiles, smem, stream);
+      case 8: return launch_agg<8, 128, 1, 128, 1, false, 2>(p, ws, S, workers, tiles, smem, stream);
+      case 4: return launch_agg<4, 128, 1, 128, 1, false, 2>(p, ws, S, workers, tiles, smem, stream);
+      case 2: return launch_agg<2, 128, 1, 64, 1, false, 2>(p, ws, S, workers, tiles, smem, stream);
+      case 1: return launch_agg<1, 64, 1, 32, 1, false, 2>(p, ws, S, workers, tiles, smem, stream);
+    }
+    return FGNN_ERR_UNSUPPORTED;
+  }
   if (xb) {
     switch (p.T) {
       case 16: return launch_agg<16, 128, 8, 128, 4, true>(p, ws, S, workers, tiles, smem, stream);

@@ -51,14 +51,15 @@ struct Header {                       // first bytes of the workspace
 };
 
 // shared-memory geometry, by I/O type (xb: bf16 I/O)
-__host__ __device__ constexpr int row_bytes(bool xb) { return xb ? kC * 2 : kC * 4; }          // one source row in the ring
-__host__ __device__ constexpr int stage_bytes(bool xb) { return kTileM * row_bytes(xb); }       // 16 / 32 KB
-__host__ __device__ constexpr int w_bytes(int cols, bool xb) { return (xb ? 1 : 2) * cols * 128; }   // hi (+ lo) image rows
+// ka = K atoms: the input channels in units of kC (one 128-byte swizzle atom of bf16): 1 (C = 64) or 2 (C = 128)
+__host__ __device__ constexpr int row_bytes(bool xb, int ka = 1) { return ka * (xb ? kC * 2 : kC * 4); }   // one source row in the ring
+__host__ __device__ constexpr int stage_bytes(bool xb, int ka = 1) { return kTileM * row_bytes(xb, ka); }  // 16 / 32 / 64 KB
+__host__ __device__ constexpr int w_bytes(int cols, bool xb, int ka = 1) { return (xb ? 1 : 2) * ka * cols * 128; }   // hi (+ lo) image rows
 __host__ __device__ constexpr int out_tile_bytes(int ch, bool xb) { return kTileM * ch * (xb ? 2 : 4); }
 // raw-ring stages that fit beside a filter slice of `cols` columns and the output staging tile of `ch`
 // channels (plus 1 KB alignment slack, barriers, epilogue params)
-__host__ __device__ constexpr int a_stages(int cols, int ch, bool xb) {
-  int n = (kSmemBudget - 1024 - w_bytes(cols, xb) - out_tile_bytes(ch, xb) - 2048) / stage_bytes(xb);
+__host__ __device__ constexpr int a_stages(int cols, int ch, bool xb, int ka = 1) {
+  int n = (kSmemBudget - 1024 - w_bytes(cols, xb, ka) - out_tile_bytes(ch, xb) - 2048) / stage_bytes(xb, ka);
   return n > kMaxAStages ? kMaxAStages : n;
 }
 

@@ -146,15 +146,15 @@ def timeit_src(N, M, K, T, reps=10):
     print(f"time src  N{N} M{M} K{K} T{T}: {us:9.1f} us  {M * K / us:8.1f} Mslots/s (fan-out {plan.fan_out:.1f})", flush=True)
 
 
-def timeit(B, N, M, K, T, kernel, reps=10, dtype=torch.float32):
+def timeit(B, N, M, K, T, kernel, reps=10, dtype=torch.float32, C=64):
     rng = np.random.default_rng(0)
-    x = torch.randn(B, N, 64, device=dev).to(dtype).permute(0, 2, 1).unsqueeze(-1)
+    x = torch.randn(B, N, C, device=dev).to(dtype).permute(0, 2, 1).unsqueeze(-1)
     idx = torch.from_numpy(rng.integers(0, N, (B, M, K))).to(dev)
     et = torch.randn(B, T, M, K, device=dev).to(dtype)
-    W = torch.randn(64, 64 * T, device=dev) * 0.1
+    W = torch.randn(C, 64 * T, device=dev) * 0.1
     bias = torch.zeros(64, device=dev)
     out = torch.empty(B, 64, M, 1, device=dev, dtype=dtype, memory_format=torch.channels_last)
-    ws = torch.zeros(64 * 64 * T * 4 + 4096, dtype=torch.uint8, device=dev)
+    ws = torch.zeros(C * 64 * T * 4 + 4096, dtype=torch.uint8, device=dev)
     f = lambda: fgnn_b200.mp_forward(x, idx, et, W, bias, None, None, extension=0, aggregator=0, kernel=kernel, out=out,
                                      workspace=ws, filters_version=7)
     for _ in range(3):
@@ -168,8 +168,8 @@ def timeit(B, N, M, K, T, kernel, reps=10, dtype=torch.float32):
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / reps * 1e3
     sz = 2 if dtype == torch.bfloat16 else 4
-    byt = 4 * M * K * B + sz * T * M * K * B + sz * 64 * N * B + sz * 64 * M * B
-    print(f"time {'bf16' if sz == 2 else 'fp32'} B{B} N{N} M{M} K{K} T{T} kernel{kernel}: {us:9.1f} us  {B * M * K / us:8.1f} Mslots/s  "
+    byt = 4 * M * K * B + sz * T * M * K * B + sz * C * N * B + sz * 64 * M * B
+    print(f"time {'bf16' if sz == 2 else 'fp32'} C{C} B{B} N{N} M{M} K{K} T{T} kernel{kernel}: {us:9.1f} us  {B * M * K / us:8.1f} Mslots/s  "
           f"{byt / us / 1e3:7.1f} GB/s algorithmic", flush=True)
 
 
@@ -197,6 +197,11 @@ if __name__ == "__main__":
     ok &= run(1, 5000, 20000, 3, 16, agg=2)
     ok &= run(1, 500, 3000, 4, 16, mask=True)
     ok &= run(1, 500, 3000, 4, 4, O=128)
+    ok &= run(1, 500, 3000, 4, 4, C=128)                 # two K atoms (the 128 -> 64 layer of the LDPC model)
+    ok &= run(1, 500, 3000, 3, 16, C=128)
+    ok &= run(2, 96, 48, 6, 1, C=128, agg=1)
+    ok &= run(64, 48, 96, 3, 4, C=128)
+    ok &= run(1, 700, 2000, 2, 8, C=128, agg=2, O=128)
     ok &= run_bf16(1, 200, 128, 1, 16)
     ok &= run_bf16(1, 300, 1000, 3, 16)
     ok &= run_bf16(1, 300, 1000, 3, 4)
@@ -228,5 +233,7 @@ if __name__ == "__main__":
         for T in (16, 4):
             for (N, M, K) in ((100_000, 300_000, 2), (300_000, 100_000, 6), (1_000_000, 3_000_000, 2)):
                 timeit(1, N, M, K, T, _lib.KERNEL_TCGEN05, dtype=torch.bfloat16)
+        timeit(4096, 96, 48, 6, 4, _lib.KERNEL_TCGEN05, C=128)
+        timeit(4096, 96, 48, 6, 4, _lib.KERNEL_SIMT, C=128, reps=2)
         timeit(4096, 96, 48, 6, 4, _lib.KERNEL_TCGEN05)
         timeit(4096, 48, 96, 3, 4, _lib.KERNEL_TCGEN05)
