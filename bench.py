@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--edge-types", type=int, default=16)
     ap.add_argument("--dim", type=int, default=64)
     ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
+                    help="f32 = BASELINE configs[1]; bf16 = features / edge types / output in bf16, fp32 accumulate "
+                         "(configs[3]: --dtype bf16 --vars 1000000 --pairwise 3000000 --high 500000 --high-order 4 --layers 8)")
     ap.add_argument("--local-band", type=int, default=0, help="0 = uniform-random incidence (primary)")
     ap.add_argument("--src-calls", default="auto",
                     help="which core calls run source-stationary (one row-product per source row, csrc/mp_src.cu): "
@@ -119,7 +122,7 @@ def host_inputs(args, types, rng):
 
 def algorithmic_bytes_per_layer(args, types):
     """per core call 4*M*K (idx as int32) + s*T*M*K (etype) + s*C*N_src + s*O*M."""
-    s, C, O, T = 4, args.dim, args.dim, args.edge_types
+    s, C, O, T = (2 if args.dtype == "bf16" else 4), args.dim, args.dim, args.edge_types
     total = 0
     for t in types:
         total += 4 * t.n_factors * t.order + s * T * t.n_factors * t.order + s * C * t.n_vars + s * O * t.n_factors
@@ -129,7 +132,7 @@ def algorithmic_bytes_per_layer(args, types):
 
 def workload_name(args):
     return (f"synthetic MAP inference: {args.vars} vars, {args.pairwise} pairwise + {args.high} order-{args.high_order} "
-            f"factors, {args.layers} FGNN layers, C=O={args.dim}, T={args.edge_types}, fp32, "
+            f"factors, {args.layers} FGNN layers, C=O={args.dim}, T={args.edge_types}, {'bf16 I/O' if args.dtype == 'bf16' else 'fp32'}, "
             f"{'uniform-random' if not args.local_band else f'band-{args.local_band}'} incidence")
 
 
@@ -273,7 +276,7 @@ def executed_mma_flops_per_layer(args, types, plans):
     for j, t in enumerate(types):
         rows += t.n_vars if ("v2f%d" % j) in plans else t.n_factors * t.order
         rows += t.n_factors if ("f2v%d" % j) in plans else t.n_vars * t.kv
-    return 3 * 2 * C * O * T * rows
+    return (1 if args.dtype == "bf16" else 3) * 2 * C * O * T * rows
 
 
 def run_native(args):
@@ -317,8 +320,12 @@ def run_native(args):
     for l in range(L):
         for j in range(J):
             ws[l][j]["ver_v2f"], ws[l][j]["ver_f2v"] = 1 + l * 16 + j * 2, 2 + l * 16 + j * 2
-    d_in = dict(x_v=to_dev(inp["x_v"]), x_f=[to_dev(a) for a in inp["x_f"]],
-                et_v2f=[to_dev(a) for a in inp["et_v2f"]], et_f2v=[to_dev(a) for a in inp["et_f2v"]],
+    bf16 = args.dtype == "bf16"
+    if bf16 and world > 1:
+        raise RuntimeError("bench.py: --dtype bf16 is a single-GPU measurement in this round (the sharded layer is fp32)")
+    fdev = (lambda a: to_dev(a).to(torch.bfloat16)) if bf16 else to_dev
+    d_in = dict(x_v=fdev(inp["x_v"]), x_f=[fdev(a) for a in inp["x_f"]],
+                et_v2f=[fdev(a) for a in inp["et_v2f"]], et_f2v=[fdev(a) for a in inp["et_f2v"]],
                 idx_v2f=[to_dev(a) for a in inp["idx_v2f"]], idx_f2v=[to_dev(a) for a in inp["idx_f2v"]])
     if world > 1:
         # factor-sharded: this rank keeps its factor ranges, the compacted F->V tables and their edge types
@@ -336,7 +343,7 @@ def run_native(args):
     # source-stationary plans of the index tables (static across layers and steps: built once, outside the
     # timed region, like the reference's own table construction)
     plans = {}
-    if plan is None and args.src_calls != "none" and kernel != _lib.KERNEL_SIMT and C == 64 and args.edge_types in (4, 8, 16):
+    if plan is None and args.src_calls != "none" and kernel != _lib.KERNEL_SIMT and C == 64 and args.edge_types in (4, 8, 16) and not bf16:
         rule = fgnn_b200.mp_conv_v2.AUTO_FAN_OUT[args.edge_types]
         for j, ty in enumerate(types):
             for name, idx, n_src in (("v2f%d" % j, d_in["idx_v2f"][j], ty.n_vars), ("f2v%d" % j, d_in["idx_f2v"][j], ty.n_factors)):
@@ -431,7 +438,7 @@ def run_native(args):
 
     # ---- end to end through the module API with host buffers --------------------------------
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e and world == 1 and not bf16:
         mods = []
         for l in range(L):
             row = []
@@ -557,7 +564,7 @@ def run_native(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": workload_name(args), "messages_per_layer": msgs_layer, "layers": L,
                    "kernel": args.kernel, "source_stationary_calls": sorted(plans),
                    "launch": "CUDA graph of the step, replayed" if graphed else "from Python, call by call", "l2": "per-step working set (~%d MB/layer) exceeds the 126 MB L2; no explicit flush"

@@ -54,13 +54,10 @@
 #include <mutex>
 #include <unordered_map>
 
+#define FGNN_TC_TRACE_TU          // this translation unit owns the trace buffer of -DFGNN_TC_TRACE builds
 #include "tc_common.cuh"
 
 namespace fgnn {
-
-#ifdef FGNN_TC_TRACE
-__device__ unsigned long long g_trace[16 * 4096];
-#endif
 
 
 // ---------------------------------------------------------------------------------------------
@@ -269,8 +266,12 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
           // this group's half of the chunk comes to registers in one go, and the accumulator stage goes
           // back to the MMA warp before the arithmetic starts
           uint32_t d[NLD][16];
+          if constexpr (NLD == 4) {
+            tmem_ld64(taddr, reinterpret_cast<uint32_t(&)[64]>(d));
+          } else {
 #pragma unroll
-          for (int gq = 0; gq < NLD; ++gq) tmem_ld16(taddr + gq * 16, d[gq]);
+            for (int gq = 0; gq < NLD; ++gq) tmem_ld16(taddr + gq * 16, d[gq]);
+          }
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(t_empty(st));
