@@ -56,6 +56,33 @@ def test_struct_layout_matches_header(tmp_path):
         assert getattr(_lib.MpArgs, f).offset == off, f
 
 
+def test_exchange_struct_layout_matches_header(tmp_path):
+    fields = [f[0] for f in _lib.ExchangeArgs._fields_]
+    prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){',
+            'printf("%zu\\n", sizeof(fgnn_exchange_args));']
+    prog += [f'printf("%zu\\n", offsetof(fgnn_exchange_args, {f}));' for f in fields]
+    prog += ['return 0;}']
+    src = tmp_path / "layout_ex.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout_ex"
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([cc, "-std=c11", "-o", str(exe), str(src)])
+    out = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert out[0] == ctypes.sizeof(_lib.ExchangeArgs)
+    for f, off in zip(fields, out[1:]):
+        assert getattr(_lib.ExchangeArgs, f).offset == off, f
+
+
+def test_exchange_validation_without_gpu():
+    lib = _lib.lib()
+    a = _lib.ExchangeArgs()
+    assert lib.fgnn_exchange_forward(None, None) == _lib.ERR_INVALID_ARG
+    a.world, a.rank, a.rows, a.J, a.O, a.row1 = 9, 0, 10, 1, 64, 10          # more ranks than the arena flags hold
+    assert lib.fgnn_exchange_forward(ctypes.byref(a), None) == _lib.ERR_INVALID_ARG
+    a.world = 2
+    assert lib.fgnn_exchange_forward(ctypes.byref(a), None) == _lib.ERR_INVALID_ARG   # no counter / buffers
+
+
 def test_enums_match_header():
     src = open(HEADER).read()
     for name, val in [("FGNN_AGG_MAX", _lib.AGG_MAX), ("FGNN_AGG_SOFTMAX", _lib.AGG_SOFTMAX),
