@@ -80,6 +80,10 @@ EXPORTS = {
     "fgnn_epilogue_sum_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
                                                  ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                  ctypes.c_int32, ctypes.c_float, ctypes.c_int32, ctypes.c_void_p]),
+    "fgnn_instance_norm_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
+                                                   ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                                   ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_float,
+                                                   ctypes.c_int32, ctypes.c_float, ctypes.c_void_p]),
     "fgnn_to_node_major": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                           ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
                                           ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),

@@ -148,6 +148,71 @@ __global__ void epilogue_sum_kernel(const float* __restrict__ in, float* __restr
   }
 }
 
+// InstanceNorm2d (affine = false, biased variance) + activation over [B,C,N] with arbitrary strides; the statistics
+// of instance (b, c) run over its N nodes (base_model.py:83-90: the v2v / f2f maps of FactorNN).
+// Channels-last memory (x_sc == 1): block = 32 channels x 8 row groups, coalesced 128-byte rows, three passes over
+// a 32-channel column block that stays in L1.
+__global__ void __launch_bounds__(256)
+instance_norm_cl_kernel(const float* __restrict__ x, float* __restrict__ out, int C, int N, int64_t x_sb, int64_t x_sn,
+                        int64_t o_sb, int64_t o_sn, float eps, int act, float slope) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx, b = blockIdx.y;
+  const bool ok = c < C;
+  const float* xb = x + (int64_t)b * x_sb + c;
+  float s = 0.f;
+  if (ok) for (int n = ty; n < N; n += 8) s += xb[(int64_t)n * x_sn];
+  red[ty][tx] = s;
+  __syncthreads();
+  float mean = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mean += red[j][tx];
+  mean /= (float)N;
+  __syncthreads();
+  float q = 0.f;
+  if (ok) for (int n = ty; n < N; n += 8) { const float d = xb[(int64_t)n * x_sn] - mean; q = fmaf(d, d, q); }
+  red[ty][tx] = q;
+  __syncthreads();
+  float var = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) var += red[j][tx];
+  const float inv = rsqrtf(var / (float)N + eps);
+  const float neg = act == FGNN_ACT_NONE ? 1.f : (act == FGNN_ACT_RELU ? 0.f : slope);
+  float* ob = out + (int64_t)b * o_sb + c;
+  if (ok) for (int n = ty; n < N; n += 8) {
+    const float y = (xb[(int64_t)n * x_sn] - mean) * inv;
+    ob[(int64_t)n * o_sn] = y >= 0.f ? y : y * neg;
+  }
+}
+
+// Any other strides (channels-first: x_sn == 1 is the coalesced case): one warp per instance (b, c).
+__global__ void __launch_bounds__(256)
+instance_norm_warp_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int C, int N, int64_t x_sb,
+                          int64_t x_sc, int64_t x_sn, int64_t o_sb, int64_t o_sc, int64_t o_sn, float eps, int act,
+                          float slope) {
+  const int lane = threadIdx.x & 31;
+  const int64_t inst = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (inst >= (int64_t)B * C) return;
+  const int b = (int)(inst / C), c = (int)(inst % C);
+  const float* xi = x + (int64_t)b * x_sb + (int64_t)c * x_sc;
+  float s = 0.f;
+  for (int n = lane; n < N; n += 32) s += xi[(int64_t)n * x_sn];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)N;
+  float q = 0.f;
+  for (int n = lane; n < N; n += 32) { const float d = xi[(int64_t)n * x_sn] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float inv = rsqrtf(q / (float)N + eps);
+  const float neg = act == FGNN_ACT_NONE ? 1.f : (act == FGNN_ACT_RELU ? 0.f : slope);
+  float* oi = out + (int64_t)b * o_sb + (int64_t)c * o_sc;
+  for (int n = lane; n < N; n += 32) {
+    const float y = (xi[(int64_t)n * x_sn] - mean) * inv;
+    oi[(int64_t)n * o_sn] = y >= 0.f ? y : y * neg;
+  }
+}
+
 static int device_ok() {
   static int cached = -100;
   if (cached != -100) return cached;
@@ -248,6 +313,25 @@ int fgnn_src_permute_etype(const float* etype, int64_t et_sb, const int32_t* edg
                                    reinterpret_cast<cudaStream_t>(stream_));
   if (rc == FGNN_ERR_CUDA) g_last_cuda_error = (int)cudaGetLastError();
   return rc;
+}
+
+int fgnn_instance_norm_forward(const float* x, float* out, int32_t B, int32_t C, int32_t N, int64_t x_sb, int64_t x_sc,
+                               int64_t x_sn, int64_t out_sb, int64_t out_sc, int64_t out_sn, float eps,
+                               int32_t activation, float act_slope, void* stream_) {
+  if (!x || !out || B <= 0 || C <= 0 || N <= 0 || activation < 0 || activation > 2) return FGNN_ERR_INVALID_ARG;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (x_sc == 1 && out_sc == 1 && B <= 65535) {
+    dim3 grid((C + 31) / 32, B);
+    instance_norm_cl_kernel<<<grid, 256, 0, stream>>>(x, out, C, N, x_sb, x_sn, out_sb, out_sn, eps, activation, act_slope);
+  } else {
+    const int64_t inst = (int64_t)B * C;
+    if ((inst + 7) / 8 > INT32_MAX) return FGNN_ERR_UNSUPPORTED;
+    instance_norm_warp_kernel<<<(unsigned)((inst + 7) / 8), 256, 0, stream>>>(x, out, B, C, N, x_sb, x_sc, x_sn, out_sb, out_sc,
+                                                                          out_sn, eps, activation, act_slope);
+  }
+  count_launch();
+  FGNN_CUDA(cudaGetLastError());
+  return FGNN_OK;
 }
 
 int fgnn_to_node_major(const float* x, float* out, int32_t B, int32_t C, int32_t N, int64_t x_sb,

@@ -47,6 +47,25 @@ class _InstanceNorm2d(torch.nn.InstanceNorm2d):
         return super().forward(x)
 
 
+def instance_norm_act(x, eps=1e-5, activation=None):
+    """InstanceNorm2d (affine = False) + activation (None | 'relu') on a CUDA fp32 [B,C,N,1] tensor in ONE pass of the
+    library's kernel (`fgnn_instance_norm_forward`); memory format of x is kept.  PyTorch's instance_norm spends
+    2.7 ms per call on the LDPC shapes ([4096, 64..256, 96, 1]: its statistics kernel reduces 96 elements per block);
+    it was 47 % of a FactorNN forward once the message-passing cores ran on tensor cores."""
+    import ctypes
+    from . import _lib
+    B, C, N, W = x.shape
+    assert W == 1
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().fgnn_instance_norm_forward(
+            ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()), B, C, N, x.stride(0), x.stride(1), x.stride(2),
+            out.stride(0), out.stride(1), out.stride(2), float(eps), _lib.ACT_RELU if activation == "relu" else _lib.ACT_NONE,
+            0.0, ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    _lib.check(rc, "instance_norm_forward")
+    return out
+
+
 class iid_mapping_in(torch.nn.Module):
     """1x1 conv + InstanceNorm + ReLU per node (base_model.py:83-90)."""
 
@@ -56,6 +75,12 @@ class iid_mapping_in(torch.nn.Module):
                                         _InstanceNorm2d(nout), torch.nn.ReLU())
 
     def forward(self, x):
+        norm = self.main[1]
+        if (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[3] == 1 and x.shape[2] > 1
+                and not norm.affine and not norm.track_running_stats
+                and not (self.training and torch.is_grad_enabled()
+                         and (x.requires_grad or self.main[0].weight.requires_grad))):      # forward-only, like the core
+            return instance_norm_act(self.main[0](x), norm.eps, "relu")     # norm + ReLU fused into one native pass
         return self.main(x)
 
 

@@ -225,6 +225,13 @@ typedef struct fgnn_exchange_args {
  * peer still reads its `raw` (epoch flags, system-scope release/acquire).  All ranks launch it with the same epoch. */
 int fgnn_exchange_forward(const fgnn_exchange_args* args, void* stream);
 
+/* InstanceNorm2d (affine = false, biased variance, statistics of instance (b,c) over its N nodes) + activation on a
+ * logical [B,C,N] tensor with element strides: the v2v / f2f maps of FactorNN's layer body (reference
+ * base_model.py:83-90, iid_mapping_in) after their 1x1 convolution.  out may alias x. */
+int fgnn_instance_norm_forward(const float* x, float* out, int32_t B, int32_t C, int32_t N, int64_t x_sb, int64_t x_sc,
+                               int64_t x_sn, int64_t out_sb, int64_t out_sc, int64_t out_sn, float eps,
+                               int32_t activation, float act_slope, void* stream);
+
 /* Layout helper: channel-major [B,C,N] -> node-major [B,N,C] (the reference's
  * x.permute(0,2,3,1).contiguous(), mp_nn.py:125). */
 int fgnn_to_node_major(const float* x, float* out, int32_t B, int32_t C, int32_t N, int64_t x_sb,

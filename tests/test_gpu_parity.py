@@ -602,3 +602,22 @@ def test_peer_exchange_two_ranks_on_one_device():
     finally:
         for q in px:
             q.close()
+
+
+@pytest.mark.parametrize("shape", [(5, 64, 96), (3, 130, 48), (2, 7, 1000), (4, 256, 33)])
+@pytest.mark.parametrize("layout", ["channels_first", "channels_last"])
+def test_instance_norm_act_matches_torch(shape, layout):
+    """fgnn_instance_norm_forward (the InstanceNorm + ReLU of FactorNN's v2v / f2f maps, base_model.py:83-90)
+    against torch.nn.functional.instance_norm + relu, both memory formats."""
+    from fgnn_b200.factor_nn import instance_norm_act
+    B, C, N = shape
+    x = torch.randn(B, C, N, 1, device=DEV) * 3 + 1
+    if layout == "channels_last":
+        x = x.contiguous(memory_format=torch.channels_last)
+    ref = torch.relu(torch.nn.functional.instance_norm(x, eps=1e-5))
+    before = fgnn_b200.launch_count()
+    y = instance_norm_act(x, 1e-5, "relu")
+    assert fgnn_b200.launch_count() == before + 1 and y.stride() == x.stride()
+    assert_close(y.cpu().numpy(), ref.cpu().numpy(), 1e-5, f"instance norm {shape} {layout}")
+    y0 = instance_norm_act(x, 1e-5, None)
+    assert_close(y0.cpu().numpy(), torch.nn.functional.instance_norm(x, eps=1e-5).cpu().numpy(), 1e-5, "no activation")
