@@ -563,10 +563,35 @@ class mp_conv_residual(base_mp_nn):
         self.with_residual = with_residual
         self.with_hop = with_hop
 
+    def _conv_bn_act(self, seq, x):
+        """Conv2d(1x1) + BatchNorm2d + LeakyReLU.  In eval mode the BatchNorm is folded into the convolution
+        (W' = W * gamma / sqrt(var + eps), b' = (b - mean) * gamma / sqrt(var + eps) + beta; cached per parameter
+        version), which removes one full pass over the features per map; train mode is PyTorch's own sequence."""
+        conv, bn, act = seq[0], seq[1], seq[2]
+        if (self.training or bn.training or not isinstance(bn, torch.nn.BatchNorm2d) or bn.running_mean is None
+                or not isinstance(act, torch.nn.LeakyReLU) or (torch.is_grad_enabled() and x.requires_grad)):
+            return seq(x)
+        ver = (conv.weight._version, conv.weight.data_ptr(), -1 if conv.bias is None else conv.bias._version,
+               bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+               bn.running_mean.data_ptr())
+        cache = self.__dict__.setdefault("_folded", {})
+        ent = cache.get(id(seq))
+        if ent is None or ent[0] != ver:
+            with torch.no_grad():
+                scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+                w = (conv.weight * scale.view(-1, 1, 1, 1)).contiguous()
+                b0 = conv.bias if conv.bias is not None else torch.zeros_like(bn.running_mean)
+                b = ((b0 - bn.running_mean) * scale + bn.bias).contiguous()
+            ent = (ver, w, b)
+            cache[id(seq)] = ent
+        with torch.no_grad():
+            y = torch.nn.functional.conv2d(x, ent[1], ent[2])
+            return torch.nn.functional.leaky_relu_(y, act.negative_slope)
+
     def forward(self, node_feature, nn_idx, etype):
-        nfeature = self.conv1(node_feature)
+        nfeature = self._conv_bn_act(self.conv1, node_feature)
         nfeature = self.mp_conv(nfeature, nn_idx, etype)
-        nfeature = self.conv2(nfeature)
+        nfeature = self._conv_bn_act(self.conv2, nfeature)
         if self.with_residual:
             nfeature = nfeature + node_feature
         return nfeature

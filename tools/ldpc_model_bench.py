@@ -71,8 +71,10 @@ ms_simt, out_simt, _ = timed(2)
 err = float((out_auto - out_simt).abs().max() / out_simt.abs().max())
 print(f"LDPC FactorNN forward, B={B}, {layers} layers, dims {dims}: {ms_auto:.2f} ms with the auto-selected kernels "
       f"({launches} fgnn launches, {msgs / ms_auto / 1e6:.2f} G messages/s incl. the PyTorch 1x1 maps) vs {ms_simt:.2f} ms "
-      f"with every core on the SIMT kernel; max relative difference {err:.2e}; decisions equal: "
-      f"{bool(((out_auto >= 0) == (out_simt >= 0)).all())}")
+      f"with every core on the SIMT kernel; max relative difference {err:.2e}; "
+      f"{int(((out_auto >= 0) != (out_simt >= 0)).sum())} of {out_auto.numel()} hard decisions differ (random weights: "
+      f"logits within {float(out_simt.abs()[(out_auto >= 0) != (out_simt >= 0)].max()) if ((out_auto >= 0) != (out_simt >= 0)).any() else 0.0:.1e} "
+      f"of zero)")
 
 if "--profile" in sys.argv:            # where the rest of the forward goes (PyTorch's 1x1 maps / norms around the cores)
     for m in model.modules():
