@@ -9,7 +9,7 @@ of the core stay in PyTorch.
 """
 import torch
 
-from .mp_nn import base_mp_nn, mp_conv_residual, mp_conv_type, mp_conv_v2
+from .mp_nn import base_mp_nn, conv1x1, mp_conv_residual, mp_conv_type, mp_conv_v2
 
 
 class iid_mapping(torch.nn.Module):
@@ -80,7 +80,8 @@ class iid_mapping_in(torch.nn.Module):
                 and not norm.affine and not norm.track_running_stats
                 and not (self.training and torch.is_grad_enabled()
                          and (x.requires_grad or self.main[0].weight.requires_grad))):      # forward-only, like the core
-            return instance_norm_act(self.main[0](x), norm.eps, "relu")     # norm + ReLU fused into one native pass
+            conv = self.main[0]
+            return instance_norm_act(conv1x1(x, conv.weight, conv.bias), norm.eps, "relu")   # norm + ReLU: one native pass
         return self.main(x)
 
 
@@ -180,6 +181,11 @@ class FactorNN(torch.nn.Module):
     def forward(self, node_feature, hop_features, nn_idx_f2v, nn_idx_v2f, etype_f2v, etype_v2f):
         x_v = self.node_mapping_module(node_feature)
         x_f = [m(f) for f, m in zip(hop_features, self.factor_mapping_modules)]
+        if x_v.is_cuda:
+            # node-major (channels_last) from here on: it is what the native cores read and write, their 1x1
+            # neighbours then run as row-major GEMMs (mp_nn.conv1x1) and no call needs a layout pass
+            x_v = x_v.contiguous(memory_format=torch.channels_last)
+            x_f = [f.contiguous(memory_format=torch.channels_last) for f in x_f]
         history = []
         for i in range(len(self.v2f_modules)):
             nin, nout = self.dim_mapping_list[i], self.dim_mapping_list[i + 1]
