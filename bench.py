@@ -140,6 +140,14 @@ def workload_name(args):
 # CPU arm: the oracle's C restatement of the reference algorithm (bounded sample)
 # ---------------------------------------------------------------------------------------------
 
+def host_threads():
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which is not the machine)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_layer_pass(args, types, inp, weights, threads=0):
     """One FGNN layer (all types, both directions) on the CPU oracle; returns seconds."""
     from oracle import fgnn_oracle as orc
@@ -165,9 +173,9 @@ def cpu_baseline(args, passes=5):
     types = build_graph(args, scale)
     inp = host_inputs(args, types, rng)
     weights = layer_weights(args, len(types), rng)[0]
-    cores = orc.c_threads()
-    cpu_layer_pass(args, types, inp, weights)                 # warm-up
-    times = [cpu_layer_pass(args, types, inp, weights) for _ in range(passes)]
+    cores = host_threads()
+    cpu_layer_pass(args, types, inp, weights, cores)          # warm-up
+    times = [cpu_layer_pass(args, types, inp, weights, cores) for _ in range(passes)]
     msgs = sum(t.real_messages for t in types)
     return dict(value=msgs / (sum(times) / len(times)), unit=UNIT, cores=cores, kind="port",
                 sample=(f"1 FGNN layer on a 1/{scale}-scale instance of the workload ({types[0].n_vars} vars, "
@@ -191,15 +199,15 @@ def run_reference(args):
     msgs = sum(t.real_messages for t in types)
     steps = max(1, min(args.steps, 3))
     warm = 1
+    cores = host_threads()
     for _ in range(warm):
-        cpu_layer_pass(args, types, inp, weights[0])
+        cpu_layer_pass(args, types, inp, weights[0], cores)
     t0 = time.perf_counter()
     for s in range(steps):
         for l in range(args.layers):
-            cpu_layer_pass(args, types, inp, weights[l])
+            cpu_layer_pass(args, types, inp, weights[l], cores)
     dt = time.perf_counter() - t0
     value = msgs * args.layers * steps / dt
-    cores = orc.c_threads()
     sample = (f"each step = {args.layers} FGNN layers on a 1/{scale}-scale instance of the workload "
               f"({types[0].n_vars} vars, {msgs} messages/layer)")
     print(json.dumps({
