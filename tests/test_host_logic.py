@@ -173,3 +173,48 @@ def test_source_plan_layout():
     # cached per table object
     tbl = torch.from_numpy(idx)
     assert fgnn_b200.SourcePlan.for_table(tbl, N, True) is fgnn_b200.SourcePlan.for_table(tbl, N, True)
+
+
+def test_conv_bn_fold_and_conv1x1_match_pytorch():
+    """Host-side rewrites around the core (eval mode): BatchNorm folded into the 1x1 convolution of
+    mp_conv_residual's maps, and the 1x1 convolution as a row-major GEMM on node-major tensors, equal PyTorch's own
+    Conv2d -> BatchNorm2d -> LeakyReLU sequence."""
+    import torch
+    import fgnn_b200
+    from fgnn_b200.mp_nn import conv1x1
+    torch.manual_seed(0)
+    m = fgnn_b200.mp_conv_residual(48, 64, 4, extension=fgnn_b200.mp_conv_type.NO_EXTENSION, nout=32).eval()
+    for seq in (m.conv1, m.conv2):
+        seq[1].running_mean.uniform_(-0.3, 0.3)
+        seq[1].running_var.uniform_(0.5, 1.5)
+        seq[1].weight.data.uniform_(0.5, 1.5)
+        seq[1].bias.data.uniform_(-0.2, 0.2)
+    x = torch.randn(3, 48, 17, 1)
+    with torch.no_grad():
+        ref = m.conv1(x.clone())
+        got = m._conv_bn_act(m.conv1, x.clone())
+    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-6)
+    # the cache follows the parameters
+    with torch.no_grad():
+        m.conv1[0].weight.mul_(1.5)
+        assert torch.allclose(m._conv_bn_act(m.conv1, x.clone()), m.conv1(x.clone()), rtol=1e-5, atol=1e-6)
+    # train mode keeps PyTorch's sequence (batch statistics)
+    m.train()
+    a = m._conv_bn_act(m.conv1, x.clone())
+    assert a.requires_grad
+    w, b = torch.randn(20, 48, 1, 1), torch.randn(20)
+    xl = x.contiguous(memory_format=torch.channels_last)
+    assert torch.allclose(conv1x1(xl, w, b), torch.nn.functional.conv2d(x, w, b), rtol=1e-5, atol=1e-5)
+
+
+def test_static_table_use_counter():
+    """A source plan is only built for an index table that is demonstrably static: the counter restarts whenever the
+    tensor object is written in place (new _version) or replaced."""
+    import torch
+    from fgnn_b200 import mp_nn
+    t = torch.zeros(1, 4, 2, dtype=torch.long)
+    assert [mp_nn._table_use_count(t) for _ in range(3)] == [1, 2, 3]
+    t.add_(1)                                   # in-place write: a different table as far as the cache goes
+    assert mp_nn._table_use_count(t) == 1
+    u = torch.zeros(1, 4, 2, dtype=torch.long)
+    assert mp_nn._table_use_count(u) == 1 and mp_nn._table_use_count(t) == 2
