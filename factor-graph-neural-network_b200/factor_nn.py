@@ -9,7 +9,7 @@ of the core stay in PyTorch.
 """
 import torch
 
-from .mp_nn import base_mp_nn, conv1x1, mp_conv_residual, mp_conv_type, mp_conv_v2
+from .mp_nn import base_mp_nn, conv1x1, conv1x1_native, mp_conv_residual, mp_conv_type, mp_conv_v2
 
 
 class iid_mapping(torch.nn.Module):
@@ -81,7 +81,11 @@ class iid_mapping_in(torch.nn.Module):
                 and not (self.training and torch.is_grad_enabled()
                          and (x.requires_grad or self.main[0].weight.requires_grad))):      # forward-only, like the core
             conv = self.main[0]
-            return instance_norm_act(conv1x1(x, conv.weight, conv.bias), norm.eps, "relu")   # norm + ReLU: one native pass
+            with torch.no_grad():
+                y = conv1x1_native(x, conv.weight, conv.bias)              # tensor-core pass when the shape qualifies
+                if y is None:
+                    y = conv1x1(x, conv.weight, conv.bias)
+            return instance_norm_act(y, norm.eps, "relu")                   # norm + ReLU: one native pass
         return self.main(x)
 
 

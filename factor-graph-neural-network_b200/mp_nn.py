@@ -562,6 +562,45 @@ def conv1x1(x, weight, bias=None):
     return torch.nn.functional.conv2d(x, weight, bias)
 
 
+_identity_tables = {}      # (device, N) -> (nn_idx [1,N,1] int32 = arange, etype [1,1,N,1] = 1)
+_map_images = {}           # id(weight) -> (weakref, version, filters [C,O], workspace)
+
+
+def conv1x1_native(x, weight, bias=None, bn_scale=None, bn_shift=None, activation=_lib.ACT_NONE, act_slope=0.01):
+    """A per-node 1x1 map with its bias / folded eval-BatchNorm / activation as ONE launch of the tensor-core
+    message-passing kernel: with the identity index table, a single slot and a single edge type equal to 1 the call
+    computes out[n] = act(bn(bias + x[n] . W)) -- the split-bf16 MMA keeps fp32 accuracy (measured 5e-6), and the
+    whole map is one pass over the features instead of GEMM + BatchNorm + activation passes.  First step of SURVEY 8f
+    rank 1 (the maps either side of the core, mp_nn_residual.py:25-35).  Returns None when the call does not qualify
+    (x must be a node-major fp32 CUDA tensor [B,C,N,1] with C in {64, 128} and Cout a multiple of 64)."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[3] == 1 and x.shape[1] in (64, 128)
+            and x.stride(1) == 1 and x.stride(2) == x.shape[1] and (x.shape[0] == 1 or x.stride(0) == x.shape[1] * x.shape[2])
+            and weight.shape[2:] == (1, 1) and weight.shape[0] % 64 == 0 and weight.shape[0] <= 256
+            and x.shape[0] * x.shape[2] >= 4096):
+        return None
+    B, C, N, _ = x.shape
+    O = weight.shape[0]
+    dev = x.device
+    tab = _identity_tables.get((dev, N))
+    if tab is None:
+        tab = (torch.arange(N, dtype=torch.int32, device=dev).view(1, N, 1), torch.ones((1, 1, N, 1), dtype=torch.float32, device=dev))
+        _identity_tables[(dev, N)] = tab
+    key = id(weight)
+    ver = (weight._version, weight.data_ptr())
+    ent = _map_images.get(key)
+    if ent is None or ent[0]() is not weight or ent[1] != ver:
+        with torch.no_grad():
+            filt = weight.detach().view(O, C).t().contiguous()                  # [C, O]: column o = output channel o (T = 1)
+        ws = torch.zeros(C * O * 4 + 4096, dtype=torch.uint8, device=dev)
+        ref = weakref.ref(weight, lambda _r, key=key: _map_images.pop(key, None))
+        ent = (ref, ver, filt, ws)
+        _map_images[key] = ent
+    fver = ((ver[0] + 1) * 1000003 + (ver[1] >> 4)) & 0x7fffffffffffffff or 1
+    return mp_forward(x, tab[0].expand(B, N, 1), tab[1].expand(B, 1, N, 1), ent[2], bias, bn_scale, bn_shift,
+                      extension=0, aggregator=_lib.AGG_MAX, activation=activation, act_slope=act_slope,
+                      kernel=_lib.KERNEL_TCGEN05, validate=False, workspace=ent[3], filters_version=fver)
+
+
 class mp_conv_residual(base_mp_nn):
     """conv1 (1x1 + BN + LeakyReLU) -> mp_conv_v2 -> conv2 (1x1 + BN + LeakyReLU) [+ residual];
     reference mp_nn_residual.py:8-56.  The 1x1 maps stay in PyTorch."""
@@ -587,6 +626,12 @@ class mp_conv_residual(base_mp_nn):
         if (self.training or bn.training or not isinstance(bn, torch.nn.BatchNorm2d) or bn.running_mean is None
                 or not isinstance(act, torch.nn.LeakyReLU) or (torch.is_grad_enabled() and x.requires_grad)):
             return seq(x)
+        if x.is_cuda:                         # conv + BN + LeakyReLU as one tensor-core pass when the shape qualifies
+            with torch.no_grad():
+                scale, shift = _fold_bn(bn)
+                y = conv1x1_native(x, conv.weight, conv.bias, scale, shift, _lib.ACT_LEAKY_RELU, float(act.negative_slope))
+            if y is not None:
+                return y
         ver = (conv.weight._version, conv.weight.data_ptr(), -1 if conv.bias is None else conv.bias._version,
                bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
                bn.running_mean.data_ptr())

@@ -621,3 +621,27 @@ def test_instance_norm_act_matches_torch(shape, layout):
     assert_close(y.cpu().numpy(), ref.cpu().numpy(), 1e-5, f"instance norm {shape} {layout}")
     y0 = instance_norm_act(x, 1e-5, None)
     assert_close(y0.cpu().numpy(), torch.nn.functional.instance_norm(x, eps=1e-5).cpu().numpy(), 1e-5, "no activation")
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 64), (64, 128), (128, 64), (64, 256)])
+def test_conv1x1_native_matches_pytorch(cin, cout):
+    """mp_nn.conv1x1_native: a 1x1 map + bias + folded eval BatchNorm + LeakyReLU as one launch of the tensor-core
+    kernel (identity table, one slot, one edge type == 1) against Conv2d -> BatchNorm2d -> LeakyReLU in fp32."""
+    from fgnn_b200.mp_nn import conv1x1_native, _fold_bn
+    torch.manual_seed(cin + cout)
+    seq = torch.nn.Sequential(torch.nn.Conv2d(cin, cout, 1), torch.nn.BatchNorm2d(cout), torch.nn.LeakyReLU()).to(DEV).eval()
+    seq[1].running_mean.uniform_(-0.3, 0.3)
+    seq[1].running_var.uniform_(0.5, 1.5)
+    seq[1].weight.data.uniform_(0.5, 1.5)
+    seq[1].bias.data.uniform_(-0.2, 0.2)
+    x = torch.randn(37, cin, 129, 1, device=DEV).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        ref = seq(x)
+        scale, shift = _fold_bn(seq[1])
+        before = fgnn_b200.launch_count()
+        y = conv1x1_native(x, seq[0].weight, seq[0].bias, scale, shift, _lib.ACT_LEAKY_RELU, 0.01)
+        assert y is not None and fgnn_b200.launch_count() > before and y.stride(1) == 1
+        assert_close(y.cpu().numpy(), ref.cpu().numpy(), RTOL, f"native 1x1 map {cin}->{cout}")
+        raw = conv1x1_native(x, seq[0].weight, seq[0].bias)
+        assert_close(raw.cpu().numpy(), seq[0](x).cpu().numpy(), RTOL, "plain map")
+        assert conv1x1_native(x[:, :, :3], seq[0].weight) is None          # too small / not node-major: caller falls back
