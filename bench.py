@@ -74,7 +74,18 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
-    return ap.parse_args()
+    ap.add_argument("--config", default=None, choices=["cfg2", "cfg4", "cfg5"],
+                    help="BASELINE.json presets: cfg2 = the default (configs[1]); cfg4 = configs[3] sizes on this many GPUs "
+                         "(1 M variables, 3 M pairwise + 500 K order-4, 8 layers, bf16 I/O: single GPU); cfg5 = configs[4] "
+                         "sizes (65 536 variables, 524 288 pairwise + 8 192 order-16, 12 layers; random incidence)")
+    args = ap.parse_args()
+    if args.config == "cfg4":
+        args.vars, args.pairwise, args.high, args.high_order, args.layers, args.dtype = 1_000_000, 3_000_000, 500_000, 4, 8, "bf16"
+        args.cpu_sample_scale = max(args.cpu_sample_scale, 10)
+    elif args.config == "cfg5":
+        args.vars, args.pairwise, args.high, args.high_order, args.layers = 65_536, 524_288, 8_192, 16, 12
+        args.cpu_sample_scale = max(args.cpu_sample_scale, 4)
+    return args
 
 
 # ---------------------------------------------------------------------------------------------
