@@ -615,7 +615,11 @@ def run_native(args):
                                                                          if args.exchange == "peer" else "NCCL max-all-reduce"))
                    if world > 1 else "single GPU"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src,
+                     "traffic": traffic,
+                     "traffic_note": ("DRAM bytes per core call from ncu (profiles/r01_traffic.json). Above the algorithmic bytes on purpose: the "
+                                      "source-stationary calls write and re-read one O-wide message per edge (2*4*O bytes) to cut the tensor "
+                                      "work, which is what bounds this path; --src-calls none: 90.9 MB per call, 4 % slower") if traffic else None,
+                     "peak_source": peak_src,
                      "kernel": ("mp_tc_kernel / mp_src_kernel + mp_reduce_kernel (tcgen05; average over the step's %d core calls, "
                                 "a source-stationary call being two launches)" % (2 * J * L))
                      if args.kernel != "simt" else "mp_simt_kernel",
