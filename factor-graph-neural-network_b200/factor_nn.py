@@ -12,6 +12,10 @@ import torch
 from .mp_nn import base_mp_nn, conv1x1, conv1x1_native, mp_conv_residual, mp_conv_type, mp_conv_v2
 
 
+def _as_index(t):
+    return t if t.dtype in (torch.int64, torch.int32) else t.long()
+
+
 class iid_mapping(torch.nn.Module):
     """1x1 conv + LeakyReLU per node (base_model.py:43-60)."""
 
@@ -196,9 +200,11 @@ class FactorNN(torch.nn.Module):
             new_v = self.v2v_modules[i](x_v)
             new_f = [m(f) for f, m in zip(x_f, self.f2f_modules[i])]
             for j in range(len(self.f2v_modules[i])):
+                # the reference casts with .long() (factor_mpnn_sp.py:145,150); int32 tables go through as they are
+                # (the core takes both) so the per-table validation / plan caches keep hitting on the caller's object
                 new_v = new_v + self.mpnn_forward(self.f2v_modules[i][j], x_f[j],
-                                                  nn_idx_f2v[j].long(), etype_f2v[j])
-                new_f[j] = new_f[j] + self.v2f_modules[i][j](x_v, nn_idx_v2f[j].long(), etype_v2f[j])
+                                                  _as_index(nn_idx_f2v[j]), etype_f2v[j])
+                new_f[j] = new_f[j] + self.v2f_modules[i][j](x_v, _as_index(nn_idx_v2f[j]), etype_v2f[j])
             if nin == nout:
                 x_v = x_v + new_v
                 x_f = [a + b for a, b in zip(new_f, x_f)]

@@ -113,16 +113,45 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def _bn_version(bn):
+    """Identity of a BatchNorm's eval-mode state: in-place version counters and addresses of the four tensors."""
+    parts = []
+    for t in (bn.running_var, bn.running_mean, bn.weight, bn.bias):
+        parts += [None, None] if t is None else [t._version, t.data_ptr()]
+    return tuple(parts) + (bn.eps, _cache_epoch)
+
+
 def _fold_bn(bn):
-    """Eval-mode BatchNorm2d folded to y = x * scale + shift (mp_nn.py:169-170)."""
-    rv, rm = bn.running_var, bn.running_mean
-    scale = torch.rsqrt(rv.float() + bn.eps)
-    if bn.weight is not None:
-        scale = scale * bn.weight.detach().float()
-    shift = -rm.float() * scale
-    if bn.bias is not None:
-        shift = shift + bn.bias.detach().float()
-    return scale.contiguous(), shift.contiguous()
+    """Eval-mode BatchNorm2d folded to y = x * scale + shift (mp_nn.py:169-170).  Cached on the module per
+    `_bn_version` (five tiny launches per call otherwise); `.data` writes that bypass the version counters need
+    `invalidate_caches()`."""
+    ver = _bn_version(bn)
+    ent = bn.__dict__.get("_fgnn_folded")
+    if ent is not None and ent[0] == ver:
+        return ent[1], ent[2]
+    with torch.no_grad():
+        rv, rm = bn.running_var, bn.running_mean
+        scale = torch.rsqrt(rv.float() + bn.eps)
+        if bn.weight is not None:
+            scale = scale * bn.weight.detach().float()
+        shift = -rm.float() * scale
+        if bn.bias is not None:
+            shift = shift + bn.bias.detach().float()
+        scale, shift = scale.contiguous(), shift.contiguous()
+    bn.__dict__["_fgnn_folded"] = (ver, scale, shift)
+    return scale, shift
+
+
+_cache_epoch = 0      # bumped by invalidate_caches(): part of every weight-image version
+
+
+def invalidate_caches():
+    """Forget every cached weight image / folded BatchNorm.  Needed only after writes that bypass autograd's
+    version counters (`param.data.uniform_()`, the reference's own init idiom, mp_nn.py:49) on a module that has
+    already run; ordinary in-place ops, optimizer steps and load_state_dict are seen without this."""
+    global _cache_epoch
+    _cache_epoch += 1
+    _map_images.clear()
 
 
 class _Workspace:
@@ -267,8 +296,8 @@ def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=Non
     if nn_idx.dtype not in (torch.int64, torch.int32):
         nn_idx = nn_idx.long()
     # index table: rows contiguous, batch stride free (0 for .expand()-ed tables)
-    if nn_idx.stride(2) != 1 or nn_idx.stride(1) != K:
-        nn_idx = nn_idx.contiguous()
+    if nn_idx.stride(2) != 1 or nn_idx.stride(1) != K or (B > 1 and nn_idx.stride(0) not in (0, M * K)):
+        nn_idx = nn_idx.contiguous()              # (the range check scans numel() contiguous entries)
     idx_sb = nn_idx.stride(0) if B > 1 else M * K
     if etype.dtype != x3.dtype:
         etype = etype.to(x3.dtype)
@@ -453,7 +482,7 @@ class mp_conv_v2(base_mp_nn):
     def _filters_version(self):
         # changes whenever `filters` is re-assigned, moved or written in place through autograd-visible ops
         f = self.filters
-        return ((f._version + 1) * 1000003 + (f.data_ptr() >> 4) + (self._nonce << 20)) & 0x7fffffffffffffff or 1
+        return ((f._version + 1) * 1000003 + (f.data_ptr() >> 4) + (self._nonce << 20) + _cache_epoch * 7919) & 0x7fffffffffffffff or 1
 
     def _workspace_for(self, x):
         """Private scratch so the split-bf16 image of `filters` is cached across calls."""
@@ -468,7 +497,9 @@ class mp_conv_v2(base_mp_nn):
             raise NotImplementedError(
                 "fgnn_b200.mp_conv_v2 is forward-only (autograd is outside this boundary, SURVEY 8b/8f): "
                 "call .eval() or torch.no_grad(), or use the reference module for training")
-        ext = self.extension.value if isinstance(self.extension, mp_conv_type) else int(self.extension)
+        # `install()` leaves the REFERENCE package's enum on .extension (its own isinstance checks see it): any Enum
+        # or plain int is accepted here
+        ext = int(getattr(self.extension, "value", self.extension))
         act_code, slope, post_act = self._activation_code()
         fused_agg = self._agg if self._agg is not None else _lib.AGG_NONE
         custom_agg = self._agg is None and aggregtor is not None          # user callable
@@ -593,9 +624,12 @@ def conv1x1_native(x, weight, bias=None, bn_scale=None, bn_shift=None, activatio
             filt = weight.detach().view(O, C).t().contiguous()                  # [C, O]: column o = output channel o (T = 1)
         ws = torch.zeros(C * O * 4 + 4096, dtype=torch.uint8, device=dev)
         ref = weakref.ref(weight, lambda _r, key=key: _map_images.pop(key, None))
-        ent = (ref, ver, filt, ws)
+        # per-entry nonce: a rebuilt model can get the same weight / workspace addresses and version back from the
+        # caching allocator, and the library's host-side record of "this workspace holds the image of these filters"
+        # outlives the freed workspace -- the image version must differ or the fresh (zeroed) workspace is trusted
+        ent = (ref, ver, filt, ws, int.from_bytes(os.urandom(5), "little"))
         _map_images[key] = ent
-    fver = ((ver[0] + 1) * 1000003 + (ver[1] >> 4)) & 0x7fffffffffffffff or 1
+    fver = ((ver[0] + 1) * 1000003 + (ver[1] >> 4) + (ent[4] << 20)) & 0x7fffffffffffffff or 1
     return mp_forward(x, tab[0].expand(B, N, 1), tab[1].expand(B, 1, N, 1), ent[2], bias, bn_scale, bn_shift,
                       extension=0, aggregator=_lib.AGG_MAX, activation=activation, act_slope=act_slope,
                       kernel=_lib.KERNEL_TCGEN05, validate=False, workspace=ent[3], filters_version=fver)

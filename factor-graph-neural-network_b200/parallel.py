@@ -276,11 +276,7 @@ class ShardedLayerPlan:
                            mask_negative=True, out=nm(view), tile_slots=self.tile_slots[j], out_rows=self.out_rows[j],
                            workspace=wsj.get("f2v"), filters_version=wsj.get("ver_f2v", 0),
                            sm_limit=sms if self.limit_f2v else 0)
-        key = tuple(w["f2v"]["bias"].data_ptr() for w in weights)
-        if getattr(self, "_epi_key", None) != key:
-            self._epi = [torch.cat([w["f2v"][k] for w in weights]).contiguous() for k in ("bias", "scale", "shift")]
-            self._epi_key = key
-        bias, scale, shift = self._epi
+        bias, scale, shift = self._epilogue_params(weights)
         ready = torch.cuda.Event()
         ready.record(main)
         self._comm_stream.wait_event(ready)
@@ -301,6 +297,19 @@ class ShardedLayerPlan:
                            out=nm(out_f_local[j]), workspace=wsj.get("v2f"), filters_version=wsj.get("ver_v2f", 0),
                            sm_limit=sms)
         return xv[src ^ 1]
+
+    def _epilogue_params(self, weights):
+        """Concatenated bias / BN scale / BN shift [J*O] of the F->V modules of one layer, cached per layer on the
+        (address, in-place version) of every tensor involved."""
+        key = tuple((w["f2v"][k].data_ptr(), w["f2v"][k]._version) for w in weights for k in ("bias", "scale", "shift"))
+        cache = self.__dict__.setdefault("_epi_cache", {})
+        ent = cache.get(key)
+        if ent is None:
+            if len(cache) > 256:
+                cache.clear()
+            ent = [torch.cat([w["f2v"][k] for w in weights]).contiguous() for k in ("bias", "scale", "shift")]
+            cache[key] = ent
+        return ent
 
     def peer_wait(self):
         """Make the current stream wait for the last launched exchange (its output buffer is then complete)."""
@@ -353,11 +362,7 @@ class ShardedLayerPlan:
         """out_v = sum_j ReLU(BN_j(raw_j + bias_j)) on the (reduced) raw aggregate [1,N,J*O]: one kernel."""
         J = len(self.types)
         O = raw.shape[-1] // J
-        key = tuple(w["f2v"]["bias"].data_ptr() for w in weights)
-        if getattr(self, "_epi_key", None) != key:
-            self._epi = [torch.cat([w["f2v"][k] for w in weights]).contiguous() for k in ("bias", "scale", "shift")]
-            self._epi_key = key
-        bias, scale, shift = self._epi
+        bias, scale, shift = self._epilogue_params(weights)
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         _lib.check(_lib.lib().fgnn_epilogue_sum_forward(raw.data_ptr(), out_v.data_ptr(), self.n_vars, O, J, bias.data_ptr(),
                                                         scale.data_ptr(), shift.data_ptr(), _lib.ACT_RELU, 0.0, 0, stream),

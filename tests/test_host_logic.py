@@ -151,6 +151,93 @@ def test_install_drops_into_reference_package():
             mods[n].mp_conv_v2 = v
 
 
+def _oracle_core(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=None, *, extension=0, aggregator=0,
+                 activation=1, act_slope=0.01, gamma=3.0, **_ignored):
+    """CPU stand-in for fgnn_b200.mp_nn.mp_forward in host-logic tests: the same call contract (folded BN as
+    scale/shift, enum ints, [B,O,M,Kout] result) evaluated by the numpy oracle."""
+    import torch
+    from oracle import fgnn_oracle as orc
+    assert isinstance(extension, int) and isinstance(aggregator, int) and isinstance(activation, int)
+    y = orc.mp_conv_forward(x.detach().numpy(), nn_idx.numpy(), etype.detach().numpy(), filters.detach().numpy(),
+                            None, None, extension=extension, aggregator=aggregator, activation=None, gamma=gamma)
+    y = torch.from_numpy(y)
+    if bias is not None:
+        y = y + bias.detach().view(1, -1, 1, 1)
+    if bn_scale is not None:
+        y = y * bn_scale.view(1, -1, 1, 1) + bn_shift.view(1, -1, 1, 1)
+    if activation == 1:
+        y = torch.relu(y)
+    elif activation == 2:
+        y = torch.nn.functional.leaky_relu(y, act_slope)
+    return y
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree only exists in the build container")
+def test_installed_module_forward_through_reference_wrappers(monkeypatch):
+    """After install() the REFERENCE's own mp_conv_residual / FactorNN / mp_sequential run a forward through
+    fgnn_b200.mp_conv_v2.forward: enum handling (the reference's mp_conv_type lands on .extension), argument
+    marshalling, BN folding and the epilogue selection are exercised on CPU with the device call replaced by the
+    numpy oracle, and the result must equal the unpatched reference module with the same weights."""
+    import sys
+    import torch
+    from fgnn_b200 import mp_nn as native_mp_nn
+    mpnn = refload.load()
+    orig = mpnn.mp_conv_v2
+    mods = {n: sys.modules["lib.model.mpnn." + n] for n in ("mp_nn", "mp_nn_residual", "factor_mpnn_sp", "factor_mpnn")}
+    saved = {n: m.mp_conv_v2 for n, m in mods.items()}
+    torch.manual_seed(3)
+    B, N, K, T = 2, 12, 3, 4
+
+    def randomise(m):
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.uniform_(-0.2, 0.2)
+                mod.running_var.uniform_(0.5, 1.5)
+        for name, p in m.named_parameters():
+            if name.endswith("filters"):
+                p.data.uniform_(-0.3, 0.3)
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref_res = mpnn.mp_conv_residual(8, 8, T)                                    # ORIG_WITH_DIFF inside
+        ref_fnn = mpnn.FactorNN(2, [4], [16, 16], [T], 2)
+        ref_v2 = mpnn.mp_conv_v2(8, 6, T, extension=mpnn.mp_conv_type.ORIG_WITH_NEIGHBOR)   # softmax default
+    for m in (ref_res, ref_fnn, ref_v2):
+        randomise(m)
+        m.eval()
+    x = torch.randn(B, 8, N, 1)
+    idx = torch.randint(0, N, (B, N, K))
+    et = torch.randn(B, T, N, K)
+    nf, hf = torch.randn(B, 2, N, 1), [torch.randn(B, 4, 7, 1)]
+    idx_f2v, idx_v2f = [torch.randint(0, 7, (B, N, 2))], [torch.randint(0, N, (B, 7, 3))]
+    et_f2v, et_v2f = [torch.randn(B, T, N, 2)], [torch.randn(B, T, 7, 3)]
+    with torch.no_grad():
+        want_res = ref_res(x, idx, et)
+        want_v2 = ref_v2(x, idx, et)
+        want_fnn = ref_fnn(nf, hf, idx_f2v, idx_v2f, et_f2v, et_v2f)
+    try:
+        native = fgnn_b200.install(mpnn)
+        monkeypatch.setattr(native_mp_nn, "mp_forward", _oracle_core)
+        with contextlib.redirect_stdout(io.StringIO()):
+            got_res = mpnn.mp_conv_residual(8, 8, T)
+            got_fnn = mpnn.FactorNN(2, [4], [16, 16], [T], 2)
+            got_v2 = mpnn.mp_conv_v2(8, 6, T, extension=mpnn.mp_conv_type.ORIG_WITH_NEIGHBOR)
+        assert isinstance(got_res.mp_conv, native) and isinstance(got_fnn.v2f_modules[0][0].mp_conv, native)
+        for g, r in ((got_res, ref_res), (got_fnn, ref_fnn), (got_v2, ref_v2)):
+            g.load_state_dict(r.state_dict())
+            g.eval()
+        with torch.no_grad():
+            assert torch.allclose(got_res(x, idx, et), want_res, rtol=1e-5, atol=1e-6)
+            assert torch.allclose(got_v2(x, idx, et), want_v2, rtol=1e-5, atol=1e-6)
+            assert torch.allclose(got_fnn(nf, hf, idx_f2v, idx_v2f, et_f2v, et_v2f), want_fnn, rtol=1e-4, atol=1e-5)
+            # int extension values (base_mp_nn.NO_EXTENSION style) are accepted too
+            got_v2.extension = 1
+            assert torch.allclose(got_v2(x, idx, et), want_v2, rtol=1e-5, atol=1e-6)
+    finally:
+        mpnn.mp_conv_v2 = orig
+        for n, v in saved.items():
+            mods[n].mp_conv_v2 = v
+
+
 def test_source_plan_layout():
     """SourcePlan (host side of the source-stationary path): edges = live slots in source order."""
     import torch
