@@ -372,8 +372,8 @@ def run_native(args):
                 fan = idx.numel() / n_src
                 if (args.src_calls == "auto" and fan >= rule) or name in args.src_calls.split(","):
                     sp = fgnn_b200.SourcePlan(idx, n_src)
-                    if args.src_calls != "auto" or sp.max_fan_out <= fgnn_b200.mp_conv_v2.AUTO_MAX_FAN_OUT:
-                        plans[name] = sp        # auto: not for tables with hub sources (the reference's pad target)
+                    if args.src_calls != "auto" or sp.n_rows * 1.25 <= idx.numel():
+                        plans[name] = sp        # (hub sources -- the reference's pad target -- are split into virtual rows)
 
     def call(x, idx, et, w, out, accumulate, wsb, ver, name=None):
         fgnn_b200.mp_forward(nm(x), idx, et, w["filters"], w["bias"], w["scale"], w["shift"], extension=0,

@@ -452,6 +452,7 @@ int fgnn_mp_forward_host(const fgnn_mp_args* h) {
     d.out_sb = (int64_t)h->O * h->M * Kout; d.out_so = (int64_t)h->M * Kout; d.out_sm = Kout; d.out_sk = 1;
     d.filters_version = 0;
     d.tile_slots = nullptr; d.out_rows = nullptr;
+    d.src_ptr = nullptr; d.slot_edge = nullptr; d.etype_edges = nullptr; d.messages = nullptr; d.src_rows = nullptr;
     d.workspace = nullptr; d.workspace_bytes = 0;
     const size_t ws = fgnn_mp_workspace_bytes(&d);
     if (ws) { HCHK(cudaMalloc(&dws, ws)); d.workspace = dws; d.workspace_bytes = ws; }

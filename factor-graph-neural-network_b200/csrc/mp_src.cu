@@ -9,11 +9,13 @@
 // variable->factor call of a pairwise type whose variables each sit in six factors).  At T = 16 that
 // kernel runs at the tensor pipe's sustained rate, so the only way forward is fewer row-products:
 //
-//   pass 1 (mp_src_kernel):  a tile = 128 consecutive SOURCE rows.  H = x W for the tile is accumulated in
-//            TMEM exactly as in mp_tc.cu (split-bf16, three MMA terms, stationary filter slice); each
-//            epilogue thread owns one source row and walks that row's OUT-EDGES (src_ptr, source-sorted
-//            edge order): it contracts the H chunk with the edge's edge-type vector and stores the
-//            O-wide MESSAGE of the edge -- H itself (O*T wide) still never leaves the SM.
+//   pass 1 (mp_src_kernel):  a tile = 128 consecutive VIRTUAL source rows.  A virtual row is a source row
+//            with at most RC of its out-edges (the plan splits rows with more edges -- the reference's pad
+//            target collects every padded slot -- into several virtual rows, so no thread ever walks a long
+//            edge list).  H = x W for the tile is accumulated in TMEM exactly as in mp_tc.cu (split-bf16,
+//            three MMA terms, stationary filter slice); the epilogue thread of a row contracts its H chunk
+//            with the edge-type vectors of the row's edges and stores the O-wide MESSAGE of every edge --
+//            H itself (O*T wide) still never leaves the SM.
 //   pass 2 (mp_reduce_kernel): every destination aggregates the messages of its K slots (slot_edge maps a
 //            slot to its edge), then bias / eval-BN / activation -- pure streaming.
 //
@@ -21,9 +23,22 @@
 // row-products.  The caller chooses (fgnn_mp_args.src_ptr != NULL); the results are bit-identical to the
 // destination-stationary kernel (same MMA terms per row, same contraction order, same aggregation order).
 //
-// CTA roles as in mp_tc.cu (512 threads): warps 0-7 epilogue, 8-11 converters, 12-13 gatherers (the
-// "gather" is the identity here: contiguous rows), 14 MMA.  The two epilogue groups split a row's EDGES
-// (group g takes edges g, g+2, ...), not the accumulator columns: every thread reads whole chunks.
+// What bounds pass 1 (measured, profiles/r01_full.txt -> r02): tensor memory reads (~32 B/clk per SM
+// sub-partition: a 128 x 512 fp32 accumulator tile takes 2048 clk to read ONCE, against 3072 clk of MMA), the
+// L1 wavefront rate of row-per-thread global accesses (one wavefront per lane: the round-1 kernel spent 9 000
+// of them per tile on 16-byte message stores and edge-type loads) and shared-memory bandwidth (the B operand
+// alone takes half of it).  Hence:
+//   * two epilogue warps share a TMEM lane quadrant.  ES = false (tables with <= 3 edges per row): they
+//     ALTERNATE over the accumulator chunks, so every accumulator element is read once.  ES = true (up to 6
+//     edges per row, e.g. variables of a pairwise type): both read every chunk and split the row's edges --
+//     that call has few tiles and is bound by its message traffic, not by the tensor pipe;
+//   * the edge-type vectors of a tile are staged by the loader warps with COALESCED cp.async into a padded
+//     shared-memory layout ([row][slot][T] with an odd row pitch: row-per-thread reads are conflict-free) and
+//     live in registers for the whole tile;
+//   * a message leaves as whole 32-byte sectors (one 256-bit store per edge and chunk).
+//
+// CTA roles (512 threads): warps 0-7 epilogue, 8-11 converters (raw fp32 row -> split-bf16 A stage in TMEM),
+// 12-13 loaders (x rows and edge types, cp.async), 14 MMA.
 #include "tc_common.cuh"
 
 namespace fgnn {
@@ -32,37 +47,69 @@ namespace {
 
 using namespace tc;
 
-constexpr int kEB = 3;                 // edges per epilogue thread per pass over an accumulator chunk
+constexpr int kEB = 3;                 // edges per epilogue thread
 
 struct SrcParams {
   const float* x;                      // [rows, 64] source rows, node-major
-  const int32_t* src_ptr;              // [rows + 1]
+  const int32_t* vptr;                 // [vrows + 1]: edges of virtual row v are vptr[v] .. vptr[v+1]-1 (at most RC)
+  const int32_t* xrow;                 // [vrows - rows]: source row of virtual row v >= rows (v < rows: itself)
   const float* et_edges;               // [E, T]
   float* msg;                          // [E, O]
   uint32_t rows;                       // B * N
+  uint32_t vrows;                      // virtual rows (>= rows)
   int O, T;
 };
 
-template <int T, int NCH>
+// raw x stages by mode: the edge-splitting mode stages twice the edge types and its tiles take longer
+#ifdef FGNN_SRC_DBG_NST1
+__host__ __device__ constexpr int src_x_stages(bool es) { return 1; }
+#else
+__host__ __device__ constexpr int src_x_stages(bool es) { return es ? 1 : 2; }
+#endif
+
+// Edge-type image: edge-major [E][T] floats, but the T/4 16-byte pieces of edge e are stored at piece position
+// j ^ et_key(e).  A tile's block is brought into shared memory as it is (one bulk copy) and read row-per-thread;
+// with the key a warp's reads (edges a fixed stride apart) spread over the eight 16-byte bank groups.
+template <int T>
+__host__ __device__ __forceinline__ uint32_t et_key(uint32_t e) {
+  constexpr uint32_t PPE = T / 4;                            // pieces per edge: 4 | 2 | 1
+  return PPE == 1 ? 0u : (e / (8u / PPE)) & (PPE - 1u);      // edges per 128 bytes: 8 / PPE
+}
+
+__device__ __forceinline__ void stg256(float* dst, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
+// T edge types, NCH accumulator chunks of 128 columns per CTA, ES: the two warps of a lane quadrant split the
+// row's EDGES (row cap 6) instead of alternating over the chunks (row cap 3)
+template <int T, int NCH, bool ES>
 __global__ void __launch_bounds__(tc::kThreads, 1)
 mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, const int n_workers, const int n_tiles) {
   constexpr int NC = 128;                      // accumulator columns per chunk
   constexpr int COLS = NC * NCH;               // columns of W this CTA owns
   constexpr int CPC = NC / T;                  // output channels per chunk
-  constexpr int CPH = 64 / T;                  // output channels per 64-column half chunk
-  constexpr int NST = 2;                       // raw-ring stages: one item per tile, the epilogue paces the CTA
+  constexpr int CPH = 64 / T;                  // output channels per 64-column piece
+  constexpr int RC = ES ? 2 * kEB : kEB;       // edges per virtual row (plan contract)
+  constexpr int EB = T * 4;                    // bytes of one edge-type vector
+  constexpr int ETB = kTileM * RC * EB;        // edge-type staging: the tile's (at most 128 RC) vectors, contiguous
+  constexpr int NST = src_x_stages(ES);        // raw x stages (a tile's rows must be in flight while the previous one converts)
   constexpr int ROWB = row_bytes(false), STAGEB = stage_bytes(false);
-  static_assert(16 % T == 0 && T >= 4 && CPH % 4 == 0, "unsupported edge-type count");
+  static_assert(16 % T == 0 && T >= 4 && CPH % 4 == 0 && NCH % 2 == 0, "unsupported shape");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sB = smem;                                        // [2 parts][COLS rows][128 B]  UMMA K-major SW128
-  uint8_t* sA = sB + w_bytes(COLS, false);                   // [NST][128 rows][256 B]      raw ring
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + NST * STAGEB);
+  uint8_t* sA = sB + w_bytes(COLS, false);                   // [NST][128 rows][256 B]      raw x tiles
+  uint8_t* sEt = sA + NST * STAGEB;                          // [<= 128 RC][T]              edge types of the tile's edges
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEt + ETB);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   const uint32_t bar0 = smem_u32(bars);
+  // barrier slots of tc_common.cuh: the raw ring has at most two stages here, a spare slot carries the edge-type staging
   auto raw_full = [&](uint32_t s) { return bar0 + 8u * s; };
   auto raw_empty = [&](uint32_t s) { return bar0 + 8u * (kMaxAStages + s); };
+  const uint32_t et_full = bar0 + 8u * 2, et_empty = bar0 + 8u * (kMaxAStages + 2);
   auto ta_full = [&](uint32_t s) { return bar0 + 8u * (2 * kMaxAStages + s); };
   auto ta_empty = [&](uint32_t s) { return bar0 + 8u * (2 * kMaxAStages + kTA + s); };
   auto t_full = [&](uint32_t s) { return bar0 + 8u * (2 * kMaxAStages + 2 * kTA + s); };
@@ -76,17 +123,23 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
 
   pdl_launch_dependents();
   if (tid == 0) {
-    for (int s = 0; s < kMaxAStages; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(raw_full(s), kGatherWarps * 32);
       mbar_init(raw_empty(s), 128);
     }
+    mbar_init(et_full, 1);                                   // one arrive.expect_tx + the bytes of the bulk copy
+    mbar_init(et_empty, kEpiWarps * 32);
     for (int s = 0; s < kTA; ++s) {
       mbar_init(ta_full(s), 128);
       mbar_init(ta_empty(s), 1);
     }
     for (int s = 0; s < kAcc; ++s) {
       mbar_init(t_full(s), 1);
+#ifdef FGNN_SRC_DBG_NOALT
       mbar_init(t_empty(s), kEpiWarps * 32);
+#else
+      mbar_init(t_empty(s), ES ? kEpiWarps * 32 : kEpiWarps * 16);      // the readers of one chunk
+#endif
     }
     mbar_init(w_full, 1);
     fence_barrier_init();
@@ -99,97 +152,116 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
 
   if (warp < kEpiWarps) {
     // =====================================================================================
-    // EPILOGUE: thread (eg, r) owns source row tile*128 + r == TMEM lane r and that row's out-edges
-    // e0 + eg, e0 + eg + 2, ...; per accumulator chunk it reads the whole chunk (two 64-column halves),
-    // contracts it with each of its edges' edge-type vectors and stores CPC message channels per edge
+    // EPILOGUE: thread (eg, r) works on virtual row tile*128 + r == TMEM lane r.
+    //   ES = false: all (<= 3) edges of the row, accumulator chunks eg, eg+2, ...
+    //   ES = true:  edges eg, eg+2, eg+4 of the row (<= 6), every chunk
     // =====================================================================================
     reg_inc<kRegEpi>();
     const int eg = warp >> 2, wq = warp & 3;
     const int r = wq * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
-    // edge range of this thread's row in a tile (0 edges past the end)
-    auto edge_range = [&](int tile, int32_t& e0, int32_t& e1) {
-      const uint32_t g = (uint32_t)tile * kTileM + r;
-      e0 = e1 = 0;
-      if (tile < n_tiles && g < p.rows) { e0 = __ldg(p.src_ptr + g); e1 = __ldg(p.src_ptr + g + 1); }
+    const uint32_t sEt_u = smem_u32(sEt);
+    // first edge of the tile (= of its row 0) and this row's edge range
+    auto edge_range = [&](int tile, int32_t& et0, int32_t& e0, int32_t& e1) {
+      const uint32_t v = (uint32_t)tile * kTileM + r;
+      et0 = e0 = e1 = 0;
+      if (tile < n_tiles) {
+        et0 = __ldg(p.vptr + (uint32_t)tile * kTileM);
+        if (v < p.vrows) { e0 = __ldg(p.vptr + v); e1 = __ldg(p.vptr + v + 1); }
+      }
     };
-    int32_t e0n, e1n;
-    edge_range(worker, e0n, e1n);
-    uint32_t ct = 0;
+    int32_t et0n, e0n, e1n;
+    edge_range(worker, et0n, e0n, e1n);
+    uint32_t it = 0;
     bool waited = false;
     float* const msg_base = p.msg + ch0;
-    for (int tile = worker; tile < n_tiles; tile += n_workers) {
-      const int32_t e0 = e0n, e1 = e1n;
-      edge_range(tile + n_workers, e0n, e1n);                // next tile's range: in flight during this tile
-      const int n_mine = e1 - e0 > eg ? (e1 - e0 - eg + 1) >> 1 : 0;       // edges e0 + eg + 2i, i < n_mine
+    for (int tile = worker; tile < n_tiles; tile += n_workers, ++it) {
+      const int32_t e0 = e0n, ne = e1n - e0n, el0 = e0n - et0n;        // el0: the row's first edge within the tile
+      edge_range(tile + n_workers, et0n, e0n, e1n);          // next tile's range: in flight during this tile
+      // my edges: slot ks(i) = ES ? eg + 2 i : i of the row, i < n_mine
+      const int n_mine = ES ? (ne > eg ? (ne - eg + 1) >> 1 : 0) : ne;
       const int n_warp = __reduce_max_sync(0xffffffffu, n_mine);
-      const int n_pass = (n_warp + kEB - 1) / kEB;
-      // edge-type vectors of the first pass stay in registers across the chunks of the tile
+      // edge-type vectors of my edges: staging -> registers, for the whole tile.  The image is edge-major with the
+      // 16-byte pieces of edge e XOR-swizzled by et_key(e) (et_permute_kernel), so that the row-per-thread reads of
+      // a warp spread over the banks.
+      mbar_wait(et_full, it & 1);
       float et[kEB][T];
-      auto load_et = [&](int pass) {
 #pragma unroll
-        for (int i = 0; i < kEB; ++i) {
-          const int ii = pass * kEB + i;
-          if (ii < n_mine) {
-            const float4* pe = reinterpret_cast<const float4*>(p.et_edges + (int64_t)(e0 + eg + 2 * ii) * T);
+      for (int i = 0; i < kEB; ++i) {
+        const int ks = ES ? eg + 2 * i : i;
+        if (i < n_mine) {
+          const uint32_t key = et_key<T>((uint32_t)(e0 + ks));
 #pragma unroll
-            for (int t4 = 0; t4 < T / 4; ++t4) {
-              const float4 v = __ldg(pe + t4);
-              et[i][4 * t4] = v.x; et[i][4 * t4 + 1] = v.y; et[i][4 * t4 + 2] = v.z; et[i][4 * t4 + 3] = v.w;
-            }
-          } else {
-#pragma unroll
-            for (int t = 0; t < T; ++t) et[i][t] = 0.f;
+          for (int t4 = 0; t4 < T / 4; ++t4) {
+            const float4 v = lds_f4(sEt_u + (uint32_t)(el0 + ks) * EB + (((uint32_t)t4 ^ key) << 4));
+            et[i][4 * t4] = v.x; et[i][4 * t4 + 1] = v.y; et[i][4 * t4 + 2] = v.z; et[i][4 * t4 + 3] = v.w;
           }
+        } else {
+#pragma unroll
+          for (int t = 0; t < T; ++t) et[i][t] = 0.f;
         }
-      };
-      load_et(0);
+      }
+      // The staging is handed back to the loader only after the first chunk below: by then every loaded value has
+      // been CONSUMED.  An arrive issued right behind the loads can overtake them -- they queue behind the burst of
+      // all eight warps and the MMA's operand reads -- and the next tile's bulk copy (async proxy) then overwrites
+      // what the last loads have yet to read (measured: the third edge's vector of a few rows per launch).
+      bool et_released = false;
       if (!waited) { pdl_wait(); waited = true; }            // first store: the preceding launch may still read msg
 #pragma unroll 1
-      for (int chunk = 0; chunk < NCH; ++chunk) {
+#ifdef FGNN_SRC_DBG_NOALT
+      for (int chunk = 0; chunk < NCH; chunk += 1) {
+#else
+      for (int chunk = ES ? 0 : eg; chunk < NCH; chunk += ES ? 1 : 2) {
+#endif
+        const uint32_t ct = it * NCH + chunk;
         const uint32_t st = ct % kAcc;
         mbar_wait(t_full(st), (ct / kAcc) & 1);
         tc_fence_after();
         const uint32_t taddr = lane_addr + st * kAccCols;
-        for (int pass = 0; pass < (n_pass > 0 ? n_pass : 1); ++pass) {
-          if (pass > 0 || (n_pass > 1 && chunk > 0)) load_et(pass);      // rows with many edges: reload per pass
+        // store groups of SG 64-column pieces: one or two 32-byte sectors per edge and group
+        constexpr int SG = CPH >= 8 ? 1 : 2, GCH = SG * CPH;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t d[4][16];
+        for (int hg = 0; hg < 2 / SG; ++hg) {
+          float o[kEB][GCH];
 #pragma unroll
-            for (int gq = 0; gq < 4; ++gq) tmem_ld16(taddr + h * 64 + gq * 16, d[gq]);
+          for (int hh = 0; hh < SG; ++hh) {
+            const int h = hg * SG + hh;
+            uint32_t d[64];
+            tmem_ld64(taddr + h * 64, d);
             tmem_ld_wait();
-            if (h == 1 && pass + 1 >= n_pass) {              // last read of this accumulator stage
+            if (h == 1) {                                    // last read of this accumulator stage
               tc_fence_before();
               mbar_arrive(t_empty(st));
             }
 #pragma unroll
             for (int i = 0; i < kEB; ++i) {
-              const int ii = pass * kEB + i;
-              if (ii < n_warp) {                             // warp-uniform
-                float o[CPH];
+              if (i < n_warp) {                              // warp-uniform
 #pragma unroll
-                for (int c = 0; c < CPH; ++c) {              // channel c of this half: columns c*T .. c*T+T-1
-                  o[c] = contract_types<T>(et[i], &d[(c * T) >> 4][(c * T) & 15]);      // same function as mp_tc.cu: bit-identical
-                }
-                if (ii < n_mine) {
-                  float4* dst = reinterpret_cast<float4*>(msg_base + (int64_t)(e0 + eg + 2 * ii) * p.O + chunk * CPC + h * CPH);
-#pragma unroll
-                  for (int c4 = 0; c4 < CPH; c4 += 4) dst[c4 >> 2] = make_float4(o[c4], o[c4 + 1], o[c4 + 2], o[c4 + 3]);
-                }
+                for (int c = 0; c < CPH; ++c)                // channel c of this piece: columns c*T .. c*T+T-1
+                  o[i][hh * CPH + c] = contract_types<T>(et[i], &d[c * T]);      // same function as mp_tc.cu: bit-identical
               }
             }
           }
+#pragma unroll
+          for (int i = 0; i < kEB; ++i) {
+            if (i < n_mine) {
+              const int ks = ES ? eg + 2 * i : i;
+              float* dst = msg_base + (int64_t)(e0 + ks) * p.O + chunk * CPC + hg * GCH;
+#pragma unroll
+              for (int c8 = 0; c8 < GCH; c8 += 8) stg256(dst + c8, reinterpret_cast<const float(&)[8]>(o[i][c8]));
+            }
+          }
         }
-        ++ct;
-      }
-      if (e1n > e0n + eg) {                                  // next tile's first edge-type rows towards L2
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.et_edges + (int64_t)(e0n + eg) * T));
+        if (!et_released) {                                  // the next tile's edge types may be staged
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(et_empty);
+          et_released = true;
+        }
       }
     }
   } else if (warp < kGatherWarp0) {
     // =====================================================================================
-    // CONVERTERS: raw fp32 row (ring) -> bf16 hi/lo pairs -> A stage in tensor memory (as mp_tc.cu)
+    // CONVERTERS: raw fp32 row -> bf16 hi/lo pairs -> A stage in tensor memory (as mp_tc.cu)
     // =====================================================================================
     reg_dec<kRegConv>();
     const int cr = tid - kConvWarp0 * 32;
@@ -226,8 +298,9 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
   reg_dec<kRegAux>();                                        // warps 12-15 together (one warpgroup)
   if (warp < kMmaWarp) {
     // =====================================================================================
-    // "GATHERERS": the tile's 128 source rows are consecutive; cp.async them into the raw ring in the
-    // converter's swizzled layout (chunk q of row rr at position q ^ (rr & 15))
+    // X LOADERS (two warps, 64 rows each): the x rows of the tile's 128 virtual rows (consecutive source rows for
+    // v < rows, xrow[] beyond) into a raw stage in the converter's swizzled layout (chunk q of row rr at position
+    // q ^ (rr & 15)), 16 lanes per row
     // =====================================================================================
     constexpr int LPR = ROWB / 16, RPW = 32 / LPR, ROWS_W = kTileM / kGatherWarps, NIT = ROWS_W / RPW, NDO = LPR / RPW;
     const int pw = warp - kGatherWarp0;
@@ -238,21 +311,74 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
 #pragma unroll
     for (int c = 0; c < NDO; ++c)
       dst_off[c] = (uint32_t)(pw * ROWS_W + RPW * c + sub) * ROWB + (uint32_t)((q ^ ((RPW * c + sub) & (LPR - 1))) * 16);
+    // per tile and lane: the x row of virtual rows pw*64 + lane and pw*64 + 32 + lane; loaded one tile ahead
+    struct Meta { uint32_t xr0, xr1; };
+    auto meta_of = [&](int tile, Meta& m) {
+      m.xr0 = m.xr1 = 0xffffffffu;
+      if (tile >= n_tiles) return;
+      const uint32_t v0 = (uint32_t)tile * kTileM + pw * ROWS_W + lane, v1 = v0 + 32;
+      if (v0 < p.vrows) m.xr0 = v0 < p.rows ? v0 : (uint32_t)__ldg(p.xrow + (v0 - p.rows));
+      if (v1 < p.vrows) m.xr1 = v1 < p.rows ? v1 : (uint32_t)__ldg(p.xrow + (v1 - p.rows));
+    };
+    Meta cur, nxt;
+    meta_of(worker, cur);
     pdl_wait();                                              // x is the preceding launch's output: order behind it
     uint32_t i = 0;
     for (int tile = worker; tile < n_tiles; tile += n_workers, ++i) {
       const uint32_t st = i % NST, use = i / NST;
+      meta_of(tile + n_workers, nxt);
       mbar_wait(raw_empty(st), (use & 1) ^ 1);
       const uint32_t stage = sA_u + st * STAGEB;
-      const uint32_t row0 = (uint32_t)tile * kTileM + pw * ROWS_W + sub;      // this lane's row in instruction 0
+      const uint32_t off0 = cur.xr0 == 0xffffffffu ? 0xffffffffu : cur.xr0 * ROWB;     // rows * 256 < 2^32 (src_supported)
+      const uint32_t off1 = cur.xr1 == 0xffffffffu ? 0xffffffffu : cur.xr1 * ROWB;
 #pragma unroll
-      for (int u = 0; u < NIT; ++u) {
-        const uint32_t row = row0 + RPW * u;
-        const bool ok = row < p.rows;
-        const uint32_t dst = stage + dst_off[u % NDO] + (uint32_t)((u / NDO) * LPR * ROWB);
-        cp_async16(dst, xq + (uint64_t)(ok ? row : 0u) * ROWB, ok ? 16u : 0u);
+      for (int u0 = 0; u0 < NIT; u0 += 8) {
+        uint32_t o8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int rl = RPW * (u0 + j);                     // + sub: this lane's row among the warp's 64
+          o8[j] = __shfl_sync(0xffffffffu, rl < 32 ? off0 : off1, (rl + sub) & 31);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int u = u0 + j;
+          const uint32_t dst = stage + dst_off[u % NDO] + (uint32_t)((u / NDO) * LPR * ROWB);
+          const bool ok = o8[j] != 0xffffffffu;
+          cp_async16(dst, xq + (ok ? o8[j] : 0u), ok ? 16u : 0u);
+        }
       }
       cp_async_arrive_noinc(raw_full(st));
+      cur = nxt;
+    }
+  } else if (warp == kMmaWarp + 1) {
+    // =====================================================================================
+    // EDGE-TYPE LOADER: the tile's edges are consecutive, so their vectors are ONE contiguous block of the
+    // edge-major image: a single TMA bulk copy per tile, issued as soon as the epilogue has taken the previous
+    // tile's vectors into registers
+    // =====================================================================================
+    if (lane == 0) {
+      const uint32_t sEt_u = smem_u32(sEt);
+      auto range = [&](int tile, int32_t& a, int32_t& b) {
+        a = b = 0;
+        if (tile >= n_tiles) return;
+        const uint32_t v0 = (uint32_t)tile * kTileM, v1 = v0 + kTileM < p.vrows ? v0 + kTileM : p.vrows;
+        a = __ldg(p.vptr + v0); b = __ldg(p.vptr + v1);
+      };
+      int32_t a, b, an, bn;
+      range(worker, a, b);
+      uint32_t i = 0;
+      for (int tile = worker; tile < n_tiles; tile += n_workers, ++i) {
+        range(tile + n_workers, an, bn);
+        mbar_wait(et_empty, (i & 1) ^ 1);
+        const uint32_t bytes = (uint32_t)(b - a) * EB;
+        if (bytes) {
+          mbar_expect_tx(et_full, bytes);
+          bulk_g2s(sEt_u, reinterpret_cast<const uint8_t*>(p.et_edges) + (int64_t)a * EB, bytes, et_full);
+        } else {
+          mbar_arrive(et_full);
+        }
+        a = an; b = bn;
+      }
     }
   } else if (warp == kMmaWarp) {
     // =====================================================================================
@@ -313,48 +439,65 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
 
 // ---------------------------------------------------------------------------------------------
 // pass 2: every destination aggregates the messages of its K slots, then bias / BN / activation.
-// One thread per (destination row, 4 channels); slots in order k = 0..K-1 like the other kernels.
+// One thread per (destination row, 8 channels): the slot -> edge map of the row is read first, then all of a
+// batch's 32-byte message pieces are in flight before the first is used; slots in order k = 0..K-1 like the
+// other kernels.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldg256(const float* src, float (&v)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(src));
+}
+
+template <int AGG>
 __global__ void __launch_bounds__(256)
 mp_reduce_kernel(const MpParams p, const float* __restrict__ msg, const int32_t* __restrict__ slot_edge) {
-  const int O4 = p.O >> 2;
-  const int64_t rows = (int64_t)p.B * p.M, total = rows * O4;
+  constexpr int KB = 6;                                      // slots per batch of loads
+  const int O8 = p.O >> 3;
+  const int64_t rows = (int64_t)p.B * p.M, total = rows * O8;
   const float neg = p.act == FGNN_ACT_NONE ? 1.f : (p.act == FGNN_ACT_RELU ? 0.f : p.slope);
   pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t g = i / O4;
-    const int o = (int)(i - g * O4) * 4;
+    const int64_t g = i / O8;
+    const int o = (int)(i - g * O8) * 8;
     const int32_t* se = slot_edge + g * p.K;
     const int kt = p.tile_k ? p.tile_k[g >> 7] : p.K;
-    float a[4], s[4];
+    float a[8], s[8];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { a[c] = p.agg == FGNN_AGG_MEAN ? 0.f : -INFINITY; s[c] = 0.f; }
+    for (int c = 0; c < 8; ++c) { a[c] = AGG == FGNN_AGG_MEAN ? 0.f : -INFINITY; s[c] = 0.f; }
     float live = 0.f;
-    for (int k = 0; k < kt; ++k) {
-      const int32_t e = __ldg(se + k);
-      if (e < 0) continue;
-      const float4 v4 = __ldg(reinterpret_cast<const float4*>(msg + (int64_t)e * p.O + o));
-      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
-      live += 1.f;
+    for (int k0 = 0; k0 < kt; k0 += KB) {
+      int32_t e[KB];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (p.agg == FGNN_AGG_MAX) {
-          a[c] = fmaxf(a[c], v[c]);
-        } else if (p.agg == FGNN_AGG_SOFTMAX) {
-          const float z = p.gamma * v[c], mx = fmaxf(a[c], z);
-          s[c] = s[c] * expf(a[c] - mx) + expf(z - mx);
-          a[c] = mx;
-        } else {
-          a[c] += v[c];
+      for (int j = 0; j < KB; ++j) e[j] = k0 + j < kt ? __ldg(se + k0 + j) : -1;
+      float v[KB][8];
+#pragma unroll
+      for (int j = 0; j < KB; ++j)
+        if (e[j] >= 0) ldg256(msg + (int64_t)e[j] * p.O + o, v[j]);
+#pragma unroll
+      for (int j = 0; j < KB; ++j) {
+        if (e[j] < 0) continue;
+        live += 1.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (AGG == FGNN_AGG_MAX) {
+            a[c] = fmaxf(a[c], v[j][c]);
+          } else if (AGG == FGNN_AGG_SOFTMAX) {
+            const float z = p.gamma * v[j][c], mx = fmaxf(a[c], z);
+            s[c] = s[c] * expf(a[c] - mx) + expf(z - mx);
+            a[c] = mx;
+          } else {
+            a[c] += v[j][c];
+          }
         }
       }
     }
-    float y[4];
+    float y[8];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 8; ++c) {
       float r;
-      if (p.agg == FGNN_AGG_MAX) r = a[c];
-      else if (p.agg == FGNN_AGG_SOFTMAX) r = live > 0.f ? (logf(s[c]) + a[c]) * (1.f / p.gamma) : -INFINITY;
+      if (AGG == FGNN_AGG_MAX) r = a[c];
+      else if (AGG == FGNN_AGG_SOFTMAX) r = live > 0.f ? (logf(s[c]) + a[c]) * (1.f / p.gamma) : -INFINITY;
       else r = a[c] * (live > 0.f ? 1.f / live : 0.f);
       const float bi = p.bias ? p.bias[o + c] : 0.f, sc = p.scale ? p.scale[o + c] : 1.f, sh = p.scale ? p.shift[o + c] : 0.f;
       float v = fmaf(r + bi, sc, sh);
@@ -363,16 +506,19 @@ mp_reduce_kernel(const MpParams p, const float* __restrict__ msg, const int32_t*
     }
     const int64_t orow = p.out_rows ? (int64_t)p.out_rows[g] : g;
     if (orow < 0) continue;
-    float4* dst = reinterpret_cast<float4*>(p.out + orow * p.o_sm + o);
+    float* dst = p.out + orow * p.o_sm + o;
     if (p.accumulate) {
       asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(y[0]), "f"(y[1]), "f"(y[2]), "f"(y[3]) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(y[4]), "f"(y[5]), "f"(y[6]), "f"(y[7]) : "memory");
     } else {
-      *dst = make_float4(y[0], y[1], y[2], y[3]);
+      *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(y[4], y[5], y[6], y[7]);
     }
   }
 }
 
-// etype [B,T,M,K] (reference layout) -> edge-major [E,T] in source-sorted edge order
+// etype [B,T,M,K] (reference layout) -> the plan's edge-type image: edge-major [E,T] in the plan's edge order,
+// 16-byte pieces swizzled by et_key (above)
 __global__ void et_permute_kernel(const float* __restrict__ et, int64_t et_sb, const int32_t* __restrict__ edge_slot,
                                   float* __restrict__ out, int T, int64_t MK, int64_t n_edges) {
   const int64_t total = n_edges * T;
@@ -381,14 +527,23 @@ __global__ void et_permute_kernel(const float* __restrict__ et, int64_t et_sb, c
     const int t = (int)(i - e * T);
     const int64_t slot = edge_slot[e];                       // (b*M + m)*K + k
     const int64_t b = slot / MK, mk = slot - b * MK;
-    out[i] = et[b * et_sb + (int64_t)t * MK + mk];
+    const uint32_t key = T == 16 ? et_key<16>((uint32_t)e) : (T == 8 ? et_key<8>((uint32_t)e) : 0u);
+    out[e * T + ((((uint32_t)t >> 2) ^ key) << 2) + (t & 3)] = et[b * et_sb + (int64_t)t * MK + mk];
   }
 }
 
-template <int T, int NCH>
+template <int T, int NCH, bool ES>
+constexpr size_t src_smem_bytes() {
+  constexpr int RC = ES ? 2 * kEB : kEB;
+  return 1024 + (size_t)tc::w_bytes(128 * NCH, false) + (size_t)src_x_stages(ES) * tc::stage_bytes(false) +
+         (size_t)tc::kTileM * RC * T * 4 + tc::kNumBars * 8 + 16;
+}
+
+template <int T, int NCH, bool ES>
 int launch_src(const SrcParams& sp, const uint8_t* wimg, int S, int workers, int tiles, cudaStream_t st) {
-  auto kern = mp_src_kernel<T, NCH>;
-  const size_t smem = 1024 + (size_t)tc::w_bytes(128 * NCH, false) + 2 * (size_t)tc::stage_bytes(false) + tc::kNumBars * 8 + 16;
+  auto kern = mp_src_kernel<T, NCH, ES>;
+  constexpr size_t smem = src_smem_bytes<T, NCH, ES>();
+  static_assert(smem <= (size_t)tc::kSmemBudget, "shared memory budget");
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncAttributes fa;
@@ -413,6 +568,11 @@ int launch_src(const SrcParams& sp, const uint8_t* wimg, int S, int workers, int
   return e == cudaSuccess ? (int)FGNN_OK : (int)FGNN_ERR_CUDA;
 }
 
+template <int T, int NCH>
+int launch_src_es(bool es, const SrcParams& sp, const uint8_t* wimg, int S, int workers, int tiles, cudaStream_t st) {
+  return es ? launch_src<T, NCH, true>(sp, wimg, S, workers, tiles, st) : launch_src<T, NCH, false>(sp, wimg, S, workers, tiles, st);
+}
+
 }  // namespace
 
 bool src_supported(const fgnn_mp_args* a) {
@@ -420,13 +580,17 @@ bool src_supported(const fgnn_mp_args* a) {
   if (a->extension != FGNN_NO_EXTENSION || a->dtype != FGNN_F32 || a->C != tc::kC) return false;
   if (a->aggregator == FGNN_AGG_NONE) return false;
   if (a->T != 16 && a->T != 8 && a->T != 4) return false;
-  if ((a->O * a->T) % 256 || a->O % 4 || a->O > 128) return false;
+  const int OT = a->O * a->T;
+  if ((OT != 256 && OT % 512) || a->O % 8 || a->O > 128) return false;            // a CTA owns 256 or 512 columns: no ragged slice
+  if (a->src_row_cap != kEB && a->src_row_cap != 2 * kEB) return false;
+  const int64_t rows = (int64_t)a->B * a->N;
+  if (a->n_src_rows < rows || a->n_src_rows >= INT32_MAX - 256 || (a->n_src_rows > rows && !a->src_rows)) return false;
   if (a->x_sc != 1 || a->x_sn != a->C) return false;                              // node-major rows
   if (a->B > 1 && a->x_sb != (int64_t)a->N * a->C) return false;                  // batch-contiguous
   if ((int64_t)a->B * a->N * tc::row_bytes(false) >= (int64_t)UINT32_MAX) return false;
   if (a->n_edges <= 0 || a->n_edges >= INT32_MAX) return false;
   if ((reinterpret_cast<uintptr_t>(a->x) & 15) || (reinterpret_cast<uintptr_t>(a->out) & 15) ||
-      (reinterpret_cast<uintptr_t>(a->messages) & 15) || (reinterpret_cast<uintptr_t>(a->etype_edges) & 15))
+      (reinterpret_cast<uintptr_t>(a->messages) & 31) || (reinterpret_cast<uintptr_t>(a->etype_edges) & 15))
     return false;
   if (a->out_so != 1 || (a->out_sm & 3)) return false;
   if (a->B > 1 && a->out_sb != (int64_t)a->M * a->out_sm) return false;
@@ -440,36 +604,41 @@ int launch_mp_src(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream)
   const int wrc = tc_prepare_weights(p.W, ws, tc::kC, OT, a->filters_version, stream);
   if (wrc != FGNN_OK) return wrc;
   SrcParams sp;
-  sp.x = p.x; sp.src_ptr = a->src_ptr; sp.et_edges = reinterpret_cast<const float*>(a->etype_edges);
+  sp.x = p.x; sp.vptr = a->src_ptr; sp.xrow = a->src_rows; sp.et_edges = reinterpret_cast<const float*>(a->etype_edges);
   sp.msg = reinterpret_cast<float*>(a->messages);
   sp.rows = (uint32_t)((int64_t)p.B * p.N);
+  sp.vrows = (uint32_t)a->n_src_rows;
   sp.O = p.O; sp.T = p.T;
-  // columns per CTA: 512 (the split-bf16 image of 512 columns is 128 KB), or all of them when fewer
+  const bool es = a->src_row_cap == 2 * kEB;
+  // columns per CTA: 512 (the split-bf16 image of 512 columns is 128 KB), or all 256 of them
   const int cols = OT < 512 ? OT : 512;
   const int NCH = cols / 128, S = OT / cols;
   int sms = tc_num_sms();
   if (a->sm_limit > 0 && a->sm_limit < sms) sms = a->sm_limit;
   if (S > sms) return FGNN_ERR_UNSUPPORTED;
-  const int tiles = (int)((sp.rows + tc::kTileM - 1) / tc::kTileM);
+  const int tiles = (int)((sp.vrows + tc::kTileM - 1) / tc::kTileM);
   int workers = sms / S;
   if (workers > tiles) workers = tiles;
   int rc = FGNN_ERR_UNSUPPORTED;
-  if (p.T == 16 && NCH == 4) rc = launch_src<16, 4>(sp, ws, S, workers, tiles, stream);
-  else if (p.T == 16 && NCH == 2) rc = launch_src<16, 2>(sp, ws, S, workers, tiles, stream);
-  else if (p.T == 8 && NCH == 4) rc = launch_src<8, 4>(sp, ws, S, workers, tiles, stream);
-  else if (p.T == 8 && NCH == 2) rc = launch_src<8, 2>(sp, ws, S, workers, tiles, stream);
-  else if (p.T == 4 && NCH == 4) rc = launch_src<4, 4>(sp, ws, S, workers, tiles, stream);
-  else if (p.T == 4 && NCH == 2) rc = launch_src<4, 2>(sp, ws, S, workers, tiles, stream);
+  if (p.T == 16 && NCH == 4) rc = launch_src_es<16, 4>(es, sp, ws, S, workers, tiles, stream);
+  else if (p.T == 16 && NCH == 2) rc = launch_src_es<16, 2>(es, sp, ws, S, workers, tiles, stream);
+  else if (p.T == 8 && NCH == 4) rc = launch_src_es<8, 4>(es, sp, ws, S, workers, tiles, stream);
+  else if (p.T == 8 && NCH == 2) rc = launch_src_es<8, 2>(es, sp, ws, S, workers, tiles, stream);
+  else if (p.T == 4 && NCH == 4) rc = launch_src_es<4, 4>(es, sp, ws, S, workers, tiles, stream);
+  else if (p.T == 4 && NCH == 2) rc = launch_src_es<4, 2>(es, sp, ws, S, workers, tiles, stream);
   if (rc != FGNN_OK) return rc;
   // pass 2
-  const int64_t total = (int64_t)p.B * p.M * (p.O / 4);
+  const int64_t total = (int64_t)p.B * p.M * (p.O / 8);
   int64_t blocks = (total + 255) / 256;
   if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)blocks);
   cfg.blockDim = dim3(256);
   cfg.stream = stream;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, mp_reduce_kernel, p, (const float*)sp.msg, a->slot_edge);
+  cudaError_t e;
+  if (p.agg == FGNN_AGG_MAX) e = cudaLaunchKernelEx(&cfg, mp_reduce_kernel<FGNN_AGG_MAX>, p, (const float*)sp.msg, a->slot_edge);
+  else if (p.agg == FGNN_AGG_SOFTMAX) e = cudaLaunchKernelEx(&cfg, mp_reduce_kernel<FGNN_AGG_SOFTMAX>, p, (const float*)sp.msg, a->slot_edge);
+  else e = cudaLaunchKernelEx(&cfg, mp_reduce_kernel<FGNN_AGG_MEAN>, p, (const float*)sp.msg, a->slot_edge);
   count_launch();
   return e == cudaSuccess ? (int)FGNN_OK : (int)FGNN_ERR_CUDA;
 }

@@ -169,37 +169,61 @@ class _Workspace:
 
 
 class SourcePlan:
-    """Source-stationary plan of one index table (include/fgnn_b200.h, `src_ptr` ...): the live slots
-    (b,m,k) -- the EDGES -- numbered in order of their flattened source row b*N + nn_idx[b,m,k].
+    """Source-stationary plan of one index table (include/fgnn_b200.h, `src_ptr` ...).
 
     The reference computes H = x W once per source node and gathers rows of H (mp_nn.py:124-134); the
     destination-stationary kernel recomputes the row-product once per slot.  With this plan the call
-    computes it once per source row, stores one message per edge and aggregates per destination in a
-    second pass (csrc/mp_src.cu) -- bit-identical output.  Built once per table with torch sorting ops
-    on the table's device (tables are static across layers and steps) and cached on the table object
-    by `SourcePlan.for_table`.
+    computes it once per (virtual) source row, stores one message per edge and aggregates per destination in a
+    second pass (csrc/mp_src.cu) -- bit-identical output.
+
+    EDGES are the live slots (b,m,k).  A VIRTUAL ROW is a source row with at most `row_cap` of its edges: virtual
+    row v < B*N is source row v with its first `row_cap` edges (slot order); rows with more edges -- the reference
+    pads with a VALID index and a zero edge type, so the pad target collects every padded slot -- continue in extra
+    virtual rows appended after B*N (`src_rows` names their source row).  Edges are numbered virtual row by virtual
+    row, so every tile of 128 virtual rows owns a contiguous range of edges.  `row_cap` is 3 (every accumulator
+    element is read once) or 6 (the kernel splits a row's edges over two warps: fewer row-products for tables whose
+    rows mostly have 4-6 edges); None picks the cheaper of the two by the kernel's measured cost per tile.
+
+    Built once per table with torch sorting ops on the table's device (tables are static across layers and steps)
+    and cached on the table object by `SourcePlan.for_table`.
     """
     _cache = {}
+    TILE_COST = {3: 1.0, 6: 1.4}       # relative cost of a 128-row tile (row_cap 6 reads the accumulators twice)
 
-    def __init__(self, nn_idx, n_src, mask_negative=False):
+    def __init__(self, nn_idx, n_src, mask_negative=False, row_cap=None):
         B, M, K = nn_idx.shape
         dev = nn_idx.device
+        R = B * n_src
         flat = nn_idx.reshape(B, M * K).long()
         valid = (flat >= 0) & (flat < n_src)          # anything else is an empty slot here; range errors are the validator's job
         key = flat + torch.arange(B, device=dev, dtype=torch.long)[:, None] * n_src
-        key = torch.where(valid, key, torch.full_like(key, B * n_src)).reshape(-1)
+        key = torch.where(valid, key, torch.full_like(key, R)).reshape(-1)
         order = torch.argsort(key, stable=True)
         E = int(valid.sum().item())
+        src = key[order[:E]]                                                     # source row of every edge, ascending
+        counts = torch.bincount(src, minlength=R)[:R] if E else torch.zeros(R, dtype=torch.long, device=dev)
+        if row_cap is None:
+            tiles = {c: -(-(R + int(torch.clamp((counts + c - 1) // c - 1, min=0).sum().item())) // 128) for c in (3, 6)}
+            row_cap = min((3, 6), key=lambda c: tiles[c] * self.TILE_COST[c])
+        if row_cap not in (3, 6):
+            raise ValueError("row_cap must be 3 or 6")
+        start = torch.cumsum(counts, 0) - counts
+        rank = torch.arange(E, device=dev) - start[src]                          # position of the edge among its row's edges
+        n_extra = torch.clamp((counts + row_cap - 1) // row_cap - 1, min=0)      # extra virtual rows per source row
+        extra_base = torch.cumsum(n_extra, 0) - n_extra
+        vrow = torch.where(rank < row_cap, src, R + extra_base[src] + torch.div(rank, row_cap, rounding_mode="floor") - 1)
+        perm = torch.argsort(vrow, stable=True)                                  # edges virtual row by virtual row
+        V = R + int(n_extra.sum().item())
         self.B, self.M, self.K, self.n_src, self.n_edges = B, M, K, n_src, E
-        self.edge_slot = order[:E].to(torch.int32).contiguous()                 # [E] slot of every edge
+        self.row_cap, self.n_rows = row_cap, V
+        self.edge_slot = order[:E][perm].to(torch.int32).contiguous()             # [E] slot of every edge
         self.slot_edge = torch.full((B * M * K,), -1, dtype=torch.int32, device=dev)
-        self.slot_edge[order[:E]] = torch.arange(E, dtype=torch.int32, device=dev)
-        counts = torch.bincount(key[order[:E]], minlength=B * n_src)[:B * n_src]
-        self.src_ptr = torch.zeros(B * n_src + 1, dtype=torch.int32, device=dev)
-        self.src_ptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
-        self.fan_out = E / max(1, B * n_src)
-        # a source row is one thread of the first pass: a hub (the reference pads with a VALID index and a zero
-        # edge type, so the pad target collects every padded slot) would serialise its whole edge list there
+        self.slot_edge[self.edge_slot.long()] = torch.arange(E, dtype=torch.int32, device=dev)
+        vcounts = torch.bincount(vrow, minlength=V)[:V] if E else torch.zeros(V, dtype=torch.long, device=dev)
+        self.src_ptr = torch.zeros(V + 1, dtype=torch.int32, device=dev)
+        self.src_ptr[1:] = torch.cumsum(vcounts, 0).to(torch.int32)
+        self.src_rows = torch.repeat_interleave(torch.arange(R, device=dev), n_extra).to(torch.int32).contiguous()
+        self.fan_out = E / max(1, R)
         self.max_fan_out = int(counts.max().item()) if counts.numel() else 0
         self._msg = None
         self._et = None                    # (weakref(etype), version, data_ptr, permuted)
@@ -217,7 +241,7 @@ class SourcePlan:
 
     def messages(self, O):
         if self._msg is None or self._msg.numel() < self.n_edges * O:
-            self._msg = torch.empty(max(1, self.n_edges * O), dtype=torch.float32, device=self.src_ptr.device)
+            self._msg = torch.empty(max(8, self.n_edges * O), dtype=torch.float32, device=self.src_ptr.device)
         return self._msg
 
     def etype_edges(self, etype, et_sb):
@@ -392,6 +416,8 @@ def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=Non
         keep = (plan.etype_edges(etype, et_sb), plan.messages(O))
         a.src_ptr, a.slot_edge = plan.src_ptr.data_ptr(), plan.slot_edge.data_ptr()
         a.etype_edges, a.messages, a.n_edges = keep[0].data_ptr(), keep[1].data_ptr(), plan.n_edges
+        a.src_rows = plan.src_rows.data_ptr() if plan.src_rows.numel() else None
+        a.n_src_rows, a.src_row_cap = plan.n_rows, plan.row_cap
     with torch.cuda.device(dev):
         need = lib.fgnn_mp_workspace_bytes(ctypes.byref(a))
         if need:
@@ -533,9 +559,8 @@ class mp_conv_v2(base_mp_nn):
     # fan-out (edges per source row) from which the source-stationary path is chosen automatically, by
     # edge-type count (measured on B200, DESIGN.md 6: it pays at T = 16, where the destination-stationary
     # kernel is tensor-bound; at T <= 8 the message round trip costs more than the saved row-products), and
-    # the largest single fan-out tolerated (hub rows serialise in one thread)
-    AUTO_FAN_OUT = {16: 2.0, 8: float("inf"), 4: float("inf")}
-    AUTO_MAX_FAN_OUT = 64
+    # hub rows -- the reference's pad target -- are split into virtual rows by the plan)
+    AUTO_FAN_OUT = {16: 1.4, 8: float("inf"), 4: float("inf")}
     AUTO_MIN_SLOTS = 200_000
     AUTO_MIN_USES = 8                  # uses of the unchanged table object before a plan is built (a plan costs ~50 calls' worth of its gain)
 
@@ -544,16 +569,17 @@ class mp_conv_v2(base_mp_nn):
         if not mode or self.kernel == _lib.KERNEL_SIMT:
             return None
         T = self.nedge_types
+        OT = self.nou * T
         ok = (ext == 0 and agg != _lib.AGG_NONE and x.is_cuda and x.dtype == torch.float32 and self.nin == 64
-              and T in (4, 8, 16) and (self.nou * T) % 256 == 0 and self.nou % 4 == 0 and self.nou <= 128
+              and T in (4, 8, 16) and (OT == 256 or OT % 512 == 0) and self.nou % 8 == 0 and self.nou <= 128
               and nn_idx.dim() == 3 and x.dim() in (3, 4))
         if not ok:
             if mode is True:
                 raise RuntimeError("fgnn_b200: this call does not qualify for the source-stationary path")
             return None
         n_src = x.shape[2]
+        B, M, K = nn_idx.shape
         if mode == "auto":
-            B, M, K = nn_idx.shape
             if B * M * K < self.AUTO_MIN_SLOTS or B * M * K < self.AUTO_FAN_OUT[T] * B * n_src:
                 return None
             if self.index_check is not True and not _table_seen(nn_idx, n_src, False):
@@ -561,8 +587,8 @@ class mp_conv_v2(base_mp_nn):
             if _table_use_count(nn_idx) < self.AUTO_MIN_USES:
                 return None                 # not (yet) known to be static: a plan would cost more than it saves
         plan = SourcePlan.for_table(nn_idx, n_src)
-        if mode == "auto" and (plan.fan_out < self.AUTO_FAN_OUT[T] or plan.max_fan_out > self.AUTO_MAX_FAN_OUT):
-            return None
+        if mode == "auto" and plan.n_rows * 1.25 > B * M * K:
+            return None                     # (hub rows split into virtual rows) too few row-products saved
         return plan
 
     def enable_weight_cache(self, device=None):

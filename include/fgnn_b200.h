@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define FGNN_B200_VERSION 100 /* 0.1.0 */
+#define FGNN_B200_VERSION 200 /* 0.2.0 */
 
 typedef enum fgnn_status {
   FGNN_OK = 0,
@@ -125,13 +125,23 @@ typedef struct fgnn_mp_args {
      recomputes x[n] W once per slot.  With a plan of the index table (built by the caller from nn_idx, layout
      below) the call computes H once per source row on the tensor cores, stores one O-wide message per edge and
      aggregates every destination's messages in a second streaming pass -- bit-identical results, fewer
-     row-products when sources feed several slots.  fp32, NO_EXTENSION, C = 64, T in {4,8,16}, O*T % 256 == 0.
-     An EDGE is a live slot (b,m,k); edges are numbered in order of their flattened source row b*N + idx[b,m,k]. */
-  const int32_t* src_ptr;    /* [B*N + 1]: the edges of source row g are src_ptr[g] .. src_ptr[g+1]-1            */
+     row-products when sources feed several slots.  fp32, NO_EXTENSION, C = 64, T in {4,8,16}, O*T = 256 or a
+     multiple of 512, O % 8 == 0.
+     An EDGE is a live slot (b,m,k).  A VIRTUAL ROW is a source row with at most src_row_cap of its edges: virtual
+     row v < B*N is source row v with its first src_row_cap edges, the rows beyond (src_rows) carry the remaining
+     edges of rows that have more (the reference pads with a valid index and a zero edge type, so the pad target
+     collects every padded slot).  Edges are numbered virtual row by virtual row. */
+  const int32_t* src_ptr;    /* [n_src_rows + 1]: the edges of virtual row v are src_ptr[v] .. src_ptr[v+1]-1 (<= src_row_cap) */
   const int32_t* slot_edge;  /* [B*M*K]: edge number of slot (b*M + m)*K + k, -1 = empty slot                    */
   const void* etype_edges;   /* [E, T]: edge-type vector of every edge, edge-major (fgnn_src_permute_etype)      */
-  void* messages;            /* [E, O] scratch for the per-edge messages                                        */
+  void* messages;            /* [E, O] scratch for the per-edge messages, 32-byte aligned                       */
   int64_t n_edges;           /* E                                                                                */
+  const int32_t* src_rows;   /* [n_src_rows - B*N]: flattened source row b*N + n of virtual row v >= B*N (may be NULL
+                                when n_src_rows == B*N)                                                          */
+  int64_t n_src_rows;        /* virtual rows, >= B*N                                                             */
+  int32_t src_row_cap;       /* 3: tables with few edges per row; 6: the epilogue splits a row's edges over two warps
+                                (tables whose rows mostly have 4-6 edges)                                        */
+  int32_t reserved2_;
 } fgnn_mp_args;
 
 int fgnn_version(void);

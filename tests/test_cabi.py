@@ -26,7 +26,7 @@ def test_library_built_and_loads():
     fgnn_b200.build()
     assert os.path.exists(_lib.LIB_PATH)
     lib = _lib.lib()
-    assert lib.fgnn_version() == 100
+    assert lib.fgnn_version() == 200
 
 
 def test_every_declared_symbol_is_exported_and_bound():

@@ -364,20 +364,21 @@ def test_programmatic_launch_chain_bit_identical():
     dict(B=1, N=2500, M=5000, K=2, C=64, O=64, T=16),      # cfg-2 F2V order-3 shape
     dict(B=1, N=5000, M=15000, K=2, C=64, O=64, T=4),
     dict(B=1, N=900, M=1001, K=3, C=64, O=64, T=8),
-    dict(B=1, N=37, M=3000, K=5, C=64, O=64, T=16),        # fan-out ~400: many passes over each chunk
+    dict(B=1, N=37, M=3000, K=5, C=64, O=64, T=16),        # fan-out ~400: hub rows split into many virtual rows
     dict(B=3, N=130, M=257, K=4, C=64, O=64, T=16),        # batched, ragged tiles
     dict(B=1, N=300, M=500, K=2, C=64, O=128, T=16),
 ], ids=lambda s: "B{B}_N{N}_M{M}_K{K}_C{C}_O{O}_T{T}".format(**s))
+@pytest.mark.parametrize("row_cap", [3, 6])
 @pytest.mark.parametrize("agg", ["max", "softmax", "mean"])
-def test_source_stationary_equals_destination_stationary(shape, agg):
+def test_source_stationary_equals_destination_stationary(shape, agg, row_cap):
     """The source-stationary evaluation (one row-product per source row, per-edge messages, second pass)
     is bit-identical to the destination-stationary kernel and within 1e-4 of the oracle."""
     rng = np.random.default_rng(hash((shape["M"], shape["K"], shape["T"], 3)) & 0xffff)
     x, idx, et, W, bias, bn = _random_call(rng, **shape)
     code = {"max": 0, "softmax": 1, "mean": 2}[agg]
     d_idx = t(idx)
-    plan = fgnn_b200.SourcePlan(d_idx, shape["N"])
-    assert plan.n_edges == idx.size and int(plan.src_ptr[-1]) == idx.size
+    plan = fgnn_b200.SourcePlan(d_idx, shape["N"], row_cap=row_cap)
+    assert plan.n_edges == idx.size and int(plan.src_ptr[-1]) == idx.size and int(plan.src_ptr.diff().max()) <= row_cap
     y_dst = _native(x, idx, et, W, bias, bn, agg=code, kernel=_lib.KERNEL_TCGEN05)
     before = fgnn_b200.launch_count()
     scale = bn["weight"] / np.sqrt(bn["running_var"] + 1e-5)
@@ -419,6 +420,32 @@ def test_source_stationary_masked_accumulate_and_module_auto():
         mod.source_stationary = False
         y_off = mod(xe, big, ete)
     assert torch.equal(y_auto, y_off)
+
+
+def test_source_stationary_column_slices():
+    """O*T must be 256 or a multiple of 512 (a CTA owns 256 or 512 filter columns; round-1 advice: widths like
+    O = 48 at T = 16 silently skipped the trailing 256 columns).  O = 48: the explicit plan raises and the module
+    falls back to the destination-stationary kernel; O = 96 (three slices of 512) runs source-stationary."""
+    rng = np.random.default_rng(5)
+    for O in (48, 96):
+        x, idx, et, W, bias, bn = _random_call(rng, B=1, N=300, M=900, K=2, C=64, O=O, T=16)
+        d_idx = t(idx)
+        plan = fgnn_b200.SourcePlan(d_idx, 300)
+        args = (t(x).contiguous(memory_format=torch.channels_last), d_idx, t(et), t(W), t(bias), None, None)
+        ref = orc.mp_conv_forward_c(x, idx, et, W, bias, None, extension=0, aggregator="max")
+        mod = fgnn_b200.mp_conv_v2(64, O, 16, extension=fgnn_b200.mp_conv_type.NO_EXTENSION, aggregtor="max", bn=False).to(DEV).eval()
+        mod.AUTO_MIN_SLOTS, mod.AUTO_MIN_USES = 100, 1
+        with torch.no_grad():
+            mod.filters.copy_(t(W)); mod.bias.copy_(t(bias))
+            if O == 48:
+                with pytest.raises(fgnn_b200.FgnnError):
+                    fgnn_b200.mp_forward(*args, extension=0, aggregator=0, plan=plan)
+                assert mod._plan_for(args[0], d_idx, args[2], 0, _lib.AGG_MAX) is None
+            else:
+                y_src = fgnn_b200.mp_forward(*args, extension=0, aggregator=0, plan=plan)
+                assert_close(y_src.cpu().numpy(), ref, RTOL, f"O={O} source-stationary")
+            y = mod(args[0], d_idx, args[2])
+        assert_close(y.cpu().numpy(), ref, RTOL, f"O={O}")
 
 
 def test_masked_slots_and_epilogue_split_equal_fused():

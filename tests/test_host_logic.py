@@ -238,28 +238,57 @@ def test_installed_module_forward_through_reference_wrappers(monkeypatch):
             mods[n].mp_conv_v2 = v
 
 
-def test_source_plan_layout():
-    """SourcePlan (host side of the source-stationary path): edges = live slots in source order."""
+@pytest.mark.parametrize("row_cap", [3, 6, None])
+def test_source_plan_layout(row_cap):
+    """SourcePlan (host side of the source-stationary path): edges = live slots, numbered virtual row by virtual
+    row; a virtual row is a source row with at most row_cap of its edges (slot order), overflow rows appended."""
     import torch
     import fgnn_b200
     rng = np.random.default_rng(0)
-    B, N, M, K = 2, 7, 11, 3
+    B, N, M, K = 2, 7, 23, 3
     idx = rng.integers(-1, N, (B, M, K))
-    plan = fgnn_b200.SourcePlan(torch.from_numpy(idx), N, mask_negative=True)
+    idx[0, :, 0] = 2                                            # a hub: 23+ edges on source row 2 of batch 0
+    plan = fgnn_b200.SourcePlan(torch.from_numpy(idx), N, mask_negative=True, row_cap=row_cap)
+    cap = plan.row_cap
+    assert cap in (3, 6) and (row_cap is None or cap == row_cap)
     live = idx >= 0
+    R = B * N
     assert plan.n_edges == int(live.sum())
-    ptr, slot_edge, edge_slot = plan.src_ptr.numpy(), plan.slot_edge.numpy(), plan.edge_slot.numpy()
-    assert ptr[0] == 0 and ptr[-1] == plan.n_edges and np.all(np.diff(ptr) >= 0)
+    ptr, slot_edge, edge_slot, xrow = plan.src_ptr.numpy(), plan.slot_edge.numpy(), plan.edge_slot.numpy(), plan.src_rows.numpy()
+    V = plan.n_rows
+    assert ptr.shape == (V + 1,) and xrow.shape == (V - R,)
+    assert ptr[0] == 0 and ptr[-1] == plan.n_edges and np.all(np.diff(ptr) >= 0) and np.all(np.diff(ptr) <= cap)
     flat_src = (idx + np.arange(B)[:, None, None] * N).reshape(-1)
-    for g in range(B * N):
-        slots = edge_slot[ptr[g]:ptr[g + 1]]
+    seen = {g: [] for g in range(R)}
+    for v in range(V):
+        g = v if v < R else int(xrow[v - R])
+        slots = edge_slot[ptr[v]:ptr[v + 1]]
         assert np.all(flat_src[slots] == g) and np.all(live.reshape(-1)[slots])
-        assert np.all(np.diff(slots) > 0)                       # stable: slot order within a source
+        if v >= R:
+            assert len(slots) > 0                                # extra rows exist only for overflow edges
+        seen[g].append((v, list(slots)))
+    for g in range(R):
+        want = np.nonzero((flat_src == g) & live.reshape(-1))[0]
+        got = [s for _, sl in sorted(seen[g]) for s in sl]
+        assert got == list(want)                                # slot order within a source, first row_cap on the row itself
+        assert len(seen[g][0][1]) == min(cap, len(want))
+    assert np.all(np.diff(xrow) >= 0)
     assert np.array_equal(slot_edge[edge_slot], np.arange(plan.n_edges))
     assert np.all(slot_edge[~live.reshape(-1)] == -1)
     # cached per table object
     tbl = torch.from_numpy(idx)
     assert fgnn_b200.SourcePlan.for_table(tbl, N, True) is fgnn_b200.SourcePlan.for_table(tbl, N, True)
+
+
+def test_source_plan_picks_row_cap_by_cost():
+    import torch
+    import fgnn_b200
+    n = 4096
+    six = torch.arange(n).repeat_interleave(6).view(1, -1, 2)        # every source feeds six slots
+    two = torch.arange(n).repeat_interleave(2).view(1, -1, 2)
+    assert fgnn_b200.SourcePlan(six, n).row_cap == 6 and fgnn_b200.SourcePlan(six, n).n_rows == n
+    assert fgnn_b200.SourcePlan(six, n, row_cap=3).n_rows == 2 * n
+    assert fgnn_b200.SourcePlan(two, n).row_cap == 3
 
 
 def test_conv_bn_fold_and_conv1x1_match_pytorch():
