@@ -43,6 +43,24 @@
 
 namespace fgnn {
 
+#ifdef FGNN_TC_TRACE
+// Debug builds only (-DFGNN_TC_TRACE): per-tile timestamps of CTA 0, read back by tools/src_trace.py.
+__device__ unsigned long long g_src_trace[16 * 4096];
+#define SRC_TRACE(item, slot)                                                                   \
+  do {                                                                                          \
+    if (blockIdx.x == 0 && (item) < 4096u && (threadIdx.x & 31) == 0) {                         \
+      unsigned long long _t;                                                                    \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                                    \
+      g_src_trace[(item) * 16 + (slot)] = _t;                                                   \
+    }                                                                                           \
+  } while (0)
+extern "C" int fgnn_debug_src_trace_read(unsigned long long* host, size_t count) {
+  return cudaMemcpyFromSymbol(host, g_src_trace, count * sizeof(unsigned long long)) == cudaSuccess ? 0 : -6;
+}
+#else
+#define SRC_TRACE(item, slot) do { } while (0)
+#endif
+
 namespace {
 
 using namespace tc;
@@ -74,6 +92,24 @@ template <int T>
 __host__ __device__ __forceinline__ uint32_t et_key(uint32_t e) {
   constexpr uint32_t PPE = T / 4;                            // pieces per edge: 4 | 2 | 1
   return PPE == 1 ? 0u : (e / (8u / PPE)) & (PPE - 1u);      // edges per 128 bytes: 8 / PPE
+}
+
+// wait for this thread's outstanding tcgen05.ld; the registers of the load pass through the statement, so their
+// consumers cannot be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait_on(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+
+// a real instruction that reads `v` (a compare against one NaN payload, guarding a harmless nanosleep): the warp
+// cannot run past it before the load that produces `v` has completed
+__device__ __forceinline__ void touch_reg(float v) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %0, 0x7fc5a5a5;\n\t@p nanosleep.u32 1;\n\t}" ::"r"(__float_as_uint(v)) : "memory");
 }
 
 __device__ __forceinline__ void stg256(float* dst, const float (&v)[8]) {
@@ -184,7 +220,9 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
       // edge-type vectors of my edges: staging -> registers, for the whole tile.  The image is edge-major with the
       // 16-byte pieces of edge e XOR-swizzled by et_key(e) (et_permute_kernel), so that the row-per-thread reads of
       // a warp spread over the banks.
+      if ((warp & 3) == 0) SRC_TRACE(it, 6 + 4 * eg);         // epilogue: tile start
       mbar_wait(et_full, it & 1);
+      if ((warp & 3) == 0) SRC_TRACE(it, 7 + 4 * eg);         // edge types landed
       float et[kEB][T];
 #pragma unroll
       for (int i = 0; i < kEB; ++i) {
@@ -201,11 +239,15 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
           for (int t = 0; t < T; ++t) et[i][t] = 0.f;
         }
       }
-      // The staging is handed back to the loader only after the first chunk below: by then every loaded value has
-      // been CONSUMED.  An arrive issued right behind the loads can overtake them -- they queue behind the burst of
-      // all eight warps and the MMA's operand reads -- and the next tile's bulk copy (async proxy) then overwrites
-      // what the last loads have yet to read (measured: the third edge's vector of a few rows per launch).
-      bool et_released = false;
+      // The staging goes back to the loader once every loaded value has ARRIVED in its register: an arrive issued
+      // right behind the loads can overtake them -- they queue behind the burst of all eight warps and the MMA's
+      // operand reads -- and the next tile's bulk copy (async proxy) then overwrites what the last loads have yet to
+      // read (measured: the third edge's vector of a few rows per launch).  Shared-memory loads of a warp complete in
+      // order, so touching the last piece of every vector is enough.
+#pragma unroll
+      for (int i = 0; i < kEB; ++i) touch_reg(et[i][T - 1]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(et_empty);                                 // the next tile's edge types may be staged
       if (!waited) { pdl_wait(); waited = true; }            // first store: the preceding launch may still read msg
 #pragma unroll 1
 #ifdef FGNN_SRC_DBG_NOALT
@@ -217,47 +259,45 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
         const uint32_t st = ct % kAcc;
         mbar_wait(t_full(st), (ct / kAcc) & 1);
         tc_fence_after();
+        if ((warp & 3) == 0 && chunk < 2) SRC_TRACE(it, 8 + 4 * eg);      // first accumulator chunk of the tile ready
         const uint32_t taddr = lane_addr + st * kAccCols;
-        // store groups of SG 64-column pieces: one or two 32-byte sectors per edge and group
-        constexpr int SG = CPH >= 8 ? 1 : 2, GCH = SG * CPH;
+        // The chunk comes to registers in four quarters of 32 columns, double-buffered: quarter q+1 is in flight
+        // while quarter q is contracted (tensor-memory reads are the scarce resource here).  A message leaves as
+        // whole 32-byte sectors: eight channels = QPS quarters.
+        constexpr int CPQ = 32 / T;                          // channels per quarter: 2 | 4 | 8
+        constexpr int QPS = 8 / CPQ;                         // quarters per 32-byte store: 4 | 2 | 1
+        float o[kEB][8];
+        uint32_t d[2][32];
+        tmem_ld32(taddr, d[0]);
+        tmem_ld_wait_on(d[0]);
 #pragma unroll
-        for (int hg = 0; hg < 2 / SG; ++hg) {
-          float o[kEB][GCH];
+        for (int q = 0; q < 4; ++q) {
+          if (q + 1 < 4) tmem_ld32(taddr + (q + 1) * 32, d[(q + 1) & 1]);
 #pragma unroll
-          for (int hh = 0; hh < SG; ++hh) {
-            const int h = hg * SG + hh;
-            uint32_t d[64];
-            tmem_ld64(taddr + h * 64, d);
-            tmem_ld_wait();
-            if (h == 1) {                                    // last read of this accumulator stage
-              tc_fence_before();
-              mbar_arrive(t_empty(st));
+          for (int i = 0; i < kEB; ++i) {
+            if (i < n_warp) {                                // warp-uniform
+#pragma unroll
+              for (int c = 0; c < CPQ; ++c)                  // channel c of this quarter: columns c*T .. c*T+T-1
+                o[i][(q % QPS) * CPQ + c] = contract_types<T>(et[i], &d[q & 1][c * T]);      // same function as mp_tc.cu: bit-identical
             }
+          }
+          if ((q + 1) % QPS == 0) {
 #pragma unroll
             for (int i = 0; i < kEB; ++i) {
-              if (i < n_warp) {                              // warp-uniform
-#pragma unroll
-                for (int c = 0; c < CPH; ++c)                // channel c of this piece: columns c*T .. c*T+T-1
-                  o[i][hh * CPH + c] = contract_types<T>(et[i], &d[c * T]);      // same function as mp_tc.cu: bit-identical
+              if (i < n_mine) {
+                const int ks = ES ? eg + 2 * i : i;
+                stg256(msg_base + (int64_t)(e0 + ks) * p.O + chunk * CPC + (q / QPS) * 8, o[i]);
               }
             }
           }
-#pragma unroll
-          for (int i = 0; i < kEB; ++i) {
-            if (i < n_mine) {
-              const int ks = ES ? eg + 2 * i : i;
-              float* dst = msg_base + (int64_t)(e0 + ks) * p.O + chunk * CPC + hg * GCH;
-#pragma unroll
-              for (int c8 = 0; c8 < GCH; c8 += 8) stg256(dst + c8, reinterpret_cast<const float(&)[8]>(o[i][c8]));
-            }
+          if (q + 1 < 4) tmem_ld_wait_on(d[(q + 1) & 1]);
+          if (q == 2) {                                      // the last read of this accumulator stage has landed
+            tc_fence_before();
+            mbar_arrive(t_empty(st));
           }
         }
-        if (!et_released) {                                  // the next tile's edge types may be staged
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(et_empty);
-          et_released = true;
-        }
       }
+      if ((warp & 3) == 0) SRC_TRACE(it, 9 + 4 * eg);         // tile done
     }
   } else if (warp < kGatherWarp0) {
     // =====================================================================================
@@ -272,6 +312,7 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
       const uint32_t st = i % NST, use = i / NST;
       const uint32_t ta = i % kTA, tuse = i / kTA;
       mbar_wait(raw_full(st), use & 1);
+      if (cr < 32) SRC_TRACE(i, 2);                           // x rows landed
       float4 v[16];
 #pragma unroll
       for (int c = 0; c < 16; ++c) v[c] = lds_f4(row_u + st * STAGEB + (uint32_t)((c ^ (cr & 15)) * 16));
@@ -293,6 +334,7 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(ta_full(ta));
+      if (cr < 32) SRC_TRACE(i, 3);                           // A stage written
     }
   } else {
   reg_dec<kRegAux>();                                        // warps 12-15 together (one warpgroup)
@@ -328,6 +370,7 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
       const uint32_t st = i % NST, use = i / NST;
       meta_of(tile + n_workers, nxt);
       mbar_wait(raw_empty(st), (use & 1) ^ 1);
+      if (pw == 0) SRC_TRACE(i, 0);                           // x stage free
       const uint32_t stage = sA_u + st * STAGEB;
       const uint32_t off0 = cur.xr0 == 0xffffffffu ? 0xffffffffu : cur.xr0 * ROWB;     // rows * 256 < 2^32 (src_supported)
       const uint32_t off1 = cur.xr1 == 0xffffffffu ? 0xffffffffu : cur.xr1 * ROWB;
@@ -348,6 +391,7 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
         }
       }
       cp_async_arrive_noinc(raw_full(st));
+      if (pw == 0) SRC_TRACE(i, 1);                           // x copies issued
       cur = nxt;
     }
   } else if (warp == kMmaWarp + 1) {
@@ -370,6 +414,7 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
       for (int tile = worker; tile < n_tiles; tile += n_workers, ++i) {
         range(tile + n_workers, an, bn);
         mbar_wait(et_empty, (i & 1) ^ 1);
+        SRC_TRACE(i, 14);                                    // edge-type staging free: bulk copy issued
         const uint32_t bytes = (uint32_t)(b - a) * EB;
         if (bytes) {
           mbar_expect_tx(et_full, bytes);
@@ -402,6 +447,7 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
     for (int tile = worker; tile < n_tiles; tile += n_workers, ++i) {
       const uint32_t ta = i % kTA, tuse = i / kTA;
       mbar_wait(ta_full(ta), tuse & 1);
+      SRC_TRACE(i, 4);                                       // A stage ready
       const uint32_t a_hi = tmem_base + kTACol0 + ta * kTACols, a_lo = a_hi + 32;
 #pragma unroll
       for (int chunk = 0; chunk < NCH; ++chunk) {
@@ -425,6 +471,7 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
         __syncwarp();
         ++ct;
       }
+      SRC_TRACE(i, 5);                                       // all chunks of the tile issued
     }
   }
   }
