@@ -18,8 +18,15 @@ Prints ONE JSON line (rank 0).  `value` = messages/s with inputs resident in HBM
 same through the public module API with HOST buffers (pinned), H2D of the step's inputs and D2H
 of the resulting variable features inside the timed region.  `roofline` is the HBM roofline of
 the message-passing kernel: algorithmic bytes (SURVEY 8d formula) / CUDA-event time, against
-MEASURED_PEAKS.json.  `cpu_baseline` times oracle/ (the C restatement of the reference's
-algorithm, OpenMP) on a bounded 1/2-scale sample of the same workload on the host cores.
+MEASURED_PEAKS.json (per GPU when N > 1).  `cpu_baseline` times the reference's own op chain
+(oracle/fgnn_oracle_torch.py: mm -> index repeat -> gather -> bmm -> max, PyTorch CPU, all threads) on a
+bounded sample of the workload, with the C/OpenMP restatement beside it; `gpu_aten_baseline` runs that same op
+chain on the B200.  `checksum` = exact integer sum of the final variable
+features' bit patterns: identical for every N (the sharded layer is bit-identical to the single-GPU one).
+`--impl reference` runs the C restatement on the host cores at full scale, honouring --steps / --warmup.
+
+`--config cfg3` = BASELINE configs[2]: the LDPC 96.3.963 decoding graph (check factors), batch 4096 codewords,
+T = 4, 10 message-passing iterations; multi-GPU shards the batch (independent codewords: replicas, no collective).
 """
 import argparse
 import json
@@ -74,7 +81,11 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--config", default=None, choices=["cfg2", "cfg4", "cfg5"],
+    ap.add_argument("--batch", type=int, default=1, help="graphs per step (cfg3: codewords)")
+    ap.add_argument("--sustain-seconds", type=float, default=2.0,
+                    help="also report the rate over a back-to-back run of at least this many seconds (0 = skip)")
+    ap.add_argument("--no-aten-baseline", action="store_true")
+    ap.add_argument("--config", default=None, choices=["cfg2", "cfg3", "cfg4", "cfg5"],
                     help="BASELINE.json presets: cfg2 = the default (configs[1]); cfg4 = configs[3] sizes on this many GPUs "
                          "(1 M variables, 3 M pairwise + 500 K order-4, 8 layers, bf16 I/O: single GPU); cfg5 = configs[4] "
                          "sizes (65 536 variables, 524 288 pairwise + 8 192 order-16, 12 layers; random incidence)")
@@ -85,6 +96,10 @@ def parse_args():
     elif args.config == "cfg5":
         args.vars, args.pairwise, args.high, args.high_order, args.layers = 65_536, 524_288, 8_192, 16, 12
         args.cpu_sample_scale = max(args.cpu_sample_scale, 4)
+    elif args.config == "cfg3":
+        args.layers, args.edge_types = 10, 4
+        if args.batch == 1:
+            args.batch = 4096
     return args
 
 
@@ -94,6 +109,11 @@ def parse_args():
 
 def build_graph(args, scale=1):
     from fgnn_b200 import graphs
+    if args.config == "cfg3":
+        # the parity-check graph of ldpc_codes/96.3.963 as the reference's get_mpnn_sp_structure emits it
+        # (lib/data/ldpc_dataset.py:92-106); the tables travel in the committed golden fixture
+        z = np.load(os.path.join(ROOT, "tests", "golden", "ldpc_factornn.npz"))
+        return [graphs.FactorType(z["idx_v2f"], z["idx_f2v"], np.zeros(z["idx_f2v"].shape, bool), "ldpc-checks")]
     return graphs.synthetic_map_graph(args.vars // scale, args.pairwise // scale, args.high // scale,
                                       args.high_order, seed=args.seed, local_band=args.local_band)
 
@@ -120,14 +140,17 @@ def layer_weights(args, n_types, rng):
     return ws
 
 
-def host_inputs(args, types, rng):
+def host_inputs(args, types, rng, batch=None):
+    """Features and edge types per graph of the batch (per-sample, like LDPC's); index tables once ([1,M,K]:
+    the batch sees them through a stride-0 expand, as identical tables collated by the reference's DataLoader)."""
     C, T = args.dim, args.edge_types
-    x_v = rng.random((1, types[0].n_vars, C), dtype=np.float32)              # node-major [B,N,C]
-    x_f = [np.abs(rng.standard_normal((1, t.n_factors, C))).astype(np.float32) for t in types]
-    et_v2f = [rng.standard_normal((1, T, t.n_factors, t.order)).astype(np.float32) for t in types]
+    B = args.batch if batch is None else batch
+    x_v = rng.random((B, types[0].n_vars, C), dtype=np.float32)              # node-major [B,N,C]
+    x_f = [np.abs(rng.standard_normal((B, t.n_factors, C), dtype=np.float32)) for t in types]
+    et_v2f = [rng.standard_normal((B, T, t.n_factors, t.order), dtype=np.float32) for t in types]
     et_f2v = []
     for t in types:
-        e = rng.standard_normal((1, T, t.n_vars, t.kv)).astype(np.float32)
+        e = rng.standard_normal((B, T, t.n_vars, t.kv), dtype=np.float32)
         e[np.broadcast_to(t.pad_f2v[None, None], e.shape)] = 0.0               # reference padding: etype = 0
         et_f2v.append(e)
     return dict(x_v=x_v, x_f=x_f, et_v2f=et_v2f, et_f2v=et_f2v,
@@ -141,10 +164,13 @@ def algorithmic_bytes_per_layer(args, types):
     for t in types:
         total += 4 * t.n_factors * t.order + s * T * t.n_factors * t.order + s * C * t.n_vars + s * O * t.n_factors
         total += 4 * t.n_vars * t.kv + s * T * t.n_vars * t.kv + s * C * t.n_factors + s * O * t.n_vars
-    return total
+    return total * args.batch
 
 
 def workload_name(args):
+    if args.config == "cfg3":
+        return (f"LDPC 96.3.963 decoding graph (96 variables, 48 check factors of order 6), batch {args.batch} codewords, "
+                f"{args.layers} message-passing iterations, C=O={args.dim}, T={args.edge_types}, fp32")
     return (f"synthetic MAP inference: {args.vars} vars, {args.pairwise} pairwise + {args.high} order-{args.high_order} "
             f"factors, {args.layers} FGNN layers, C=O={args.dim}, T={args.edge_types}, {'bf16 I/O' if args.dtype == 'bf16' else 'fp32'}, "
             f"{'uniform-random' if not args.local_band else f'band-{args.local_band}'} incidence")
@@ -163,8 +189,10 @@ def host_threads():
 
 
 def cpu_layer_pass(args, types, inp, weights, threads=0):
-    """One FGNN layer (all types, both directions) on the CPU oracle; returns seconds."""
+    """One FGNN layer (all types, both directions) on the C restatement of the reference; returns seconds."""
     from oracle import fgnn_oracle as orc
+    B = inp["x_v"].shape[0]
+    rep = lambda a: np.broadcast_to(a, (B,) + a.shape[1:])
     t0 = time.perf_counter()
     x_v = np.ascontiguousarray(inp["x_v"].transpose(0, 2, 1))[..., None]
     for j, ty in enumerate(types):
@@ -174,61 +202,149 @@ def cpu_layer_pass(args, types, inp, weights, threads=0):
                                       ("f2v", x_f, inp["idx_f2v"][j], inp["et_f2v"][j])):
             p = w[direction]
             bn = dict(weight=np.ones_like(p["rv"]), bias=np.zeros_like(p["rv"]), running_mean=p["rm"], running_var=p["rv"])
-            orc.mp_conv_forward_c(x, idx, et, p["filters"], p["bias"], bn, extension=0, aggregator="max",
-                                  threads=threads)
+            orc.mp_conv_forward_c(x, np.ascontiguousarray(rep(idx)), et, p["filters"], p["bias"], bn, extension=0,
+                                  aggregator="max", threads=threads)
     return time.perf_counter() - t0
 
 
-def cpu_baseline(args, passes=5):
+def torch_layer_pass(args, types, inp, weights, device="cpu", chunk_bytes=2 << 30, reps=1):
+    """One FGNN layer through the reference's own op chain (oracle/fgnn_oracle_torch.py: permute -> mm -> int64 index
+    repeat -> gather -> bmm -> max -> bias -> eval BatchNorm -> ReLU, mp_nn.py:115-175) in PyTorch on `device`.
+    Destinations are evaluated in slices so that the O*T-wide int64 index + gathered rows of a slice stay below
+    `chunk_bytes` (bit-identical in eval mode).  Returns seconds per pass (mean of `reps` after 1 warm-up)."""
+    import torch
+    from oracle import fgnn_oracle_torch as orct
+    dev = torch.device(device)
+    B = inp["x_v"].shape[0]
+    OT = args.dim * args.edge_types
+    calls = []
+    x_v = torch.from_numpy(np.ascontiguousarray(inp["x_v"].transpose(0, 2, 1))[..., None]).to(dev)
+    for j, ty in enumerate(types):
+        x_f = torch.from_numpy(np.ascontiguousarray(inp["x_f"][j].transpose(0, 2, 1))[..., None]).to(dev)
+        for direction, x, idx, et in (("v2f", x_v, inp["idx_v2f"][j], inp["et_v2f"][j]),
+                                      ("f2v", x_f, inp["idx_f2v"][j], inp["et_f2v"][j])):
+            p = weights[j][direction]
+            bn = {k: torch.from_numpy(v).to(dev) for k, v in dict(weight=np.ones_like(p["rv"]), bias=np.zeros_like(p["rv"]),
+                                                                   running_mean=p["rm"], running_var=p["rv"]).items()}
+            K = idx.shape[2]
+            rows = max(1, int(chunk_bytes // (12 * B * K * OT)))       # 8-byte index + 4-byte value per gathered element
+            calls.append((x, torch.from_numpy(np.array(np.broadcast_to(idx, (B,) + idx.shape[1:]))).to(dev),
+                          torch.from_numpy(et).to(dev), torch.from_numpy(p["filters"]).to(dev),
+                          torch.from_numpy(p["bias"]).to(dev), bn, rows))
+
+    def one_pass():
+        with torch.no_grad():
+            for x, idx, et, W, bias, bn, rows in calls:
+                orct.mp_conv_forward_torch(x, idx, et, W, bias, bn, extension=0, aggregator="max", chunk_rows=rows)
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+    one_pass()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        one_pass()
+    return (time.perf_counter() - t0) / reps
+
+
+def cpu_baseline(args, budget_s=20.0):
+    """The reference's CPU path beside the GPU number (rank 0, N = 1): its own ATen op chain on PyTorch CPU with all
+    host threads (`kind: port-torch`; /root/reference itself does not exist on the GPU box), on a BOUNDED sample --
+    one FGNN layer on a 1/scale instance of the workload, scale chosen so that the leg takes about `budget_s`.  The
+    C/OpenMP restatement (the `--impl reference` arm) is timed on the same sample for comparison."""
+    import torch
     from oracle import fgnn_oracle as orc
     orc.build_c()
-    scale = args.cpu_sample_scale
-    rng = np.random.default_rng(args.seed + 1)
-    types = build_graph(args, scale)
-    inp = host_inputs(args, types, rng)
-    weights = layer_weights(args, len(types), rng)[0]
     cores = host_threads()
+    torch.set_num_threads(cores)
+    rng = np.random.default_rng(args.seed + 1)
+    # survey probe: ~0.2 M messages/s for the ATen chain at T=16 on 8 threads -> pick the sample for ~budget/4 per pass
+    full_msgs = None
+    scale, batch = 1, args.batch
+    while True:
+        types = build_graph(args, scale)
+        msgs = sum(t.real_messages for t in types) * batch
+        if full_msgs is None:
+            full_msgs = msgs
+        if msgs <= 0.2e6 * cores / 8 * budget_s / 4 or (scale >= 64 and batch <= 8):
+            break
+        if args.config == "cfg3":
+            batch = max(8, batch // 2)
+            if batch == 8:
+                break
+        else:
+            scale *= 2
+    inp = host_inputs(args, types, rng, batch)
+    weights = layer_weights(args, len(types), rng)[0]
+    t_torch = torch_layer_pass(args, types, inp, weights, "cpu", reps=2)
     cpu_layer_pass(args, types, inp, weights, cores)          # warm-up
-    times = [cpu_layer_pass(args, types, inp, weights, cores) for _ in range(passes)]
-    msgs = sum(t.real_messages for t in types)
-    return dict(value=msgs / (sum(times) / len(times)), unit=UNIT, cores=cores, kind="port",
-                sample=(f"1 FGNN layer on a 1/{scale}-scale instance of the workload ({types[0].n_vars} vars, "
-                        f"{msgs} messages), oracle/fgnn_oracle.c (C restatement of mp_nn.py:115-175, OpenMP, "
-                        f"{cores} threads), mean of {passes} passes after 1 warm-up")), sum(times)
+    t_c = min(cpu_layer_pass(args, types, inp, weights, cores) for _ in range(3))
+    what = (f"1 FGNN layer on {'a batch of %d of the %d codewords' % (batch, args.batch) if args.config == 'cfg3' else 'a 1/%d-scale instance of the workload' % scale} "
+            f"({types[0].n_vars} vars, {msgs} messages)")
+    return dict(value=msgs / t_torch, unit=UNIT, cores=cores, kind="port-torch",
+                sample=(f"{what}: oracle/fgnn_oracle_torch.py = the reference's op chain (mp_nn.py:115-175: mm -> int64 index "
+                        f"repeat -> gather -> bmm -> max -> BN -> ReLU) on PyTorch CPU, {cores} threads, mean of 2 passes after 1 warm-up"),
+                c_port={"value": msgs / t_c, "unit": UNIT, "kind": "port",
+                        "what": "oracle/fgnn_oracle.c (C restatement, OpenMP, same threads) on the same sample, best of 3"})
+
+
+def gpu_aten_baseline(args, types, inp, weights):
+    """The reference's unmodified op chain on the SAME B200: PyTorch/ATen CUDA kernels, fp32,
+    one FGNN layer of the full workload (destinations sliced to bound the O*T-wide intermediates)."""
+    import torch
+    try:
+        t = torch_layer_pass(args, types, inp, weights, "cuda", chunk_bytes=8 << 30, reps=3)
+    except Exception as e:  # noqa: BLE001  (out of memory on a shared box: report, do not fail the bench)
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:120]}"}
+    finally:
+        torch.cuda.empty_cache()
+    msgs = sum(t_.real_messages for t_ in types) * args.batch
+    return {"value": msgs / t, "unit": UNIT, "ms_per_layer": t * 1e3,
+            "what": "oracle/fgnn_oracle_torch.py (the reference's op chain, mp_nn.py:115-175) on this GPU through ATen's CUDA "
+                    "kernels, fp32, full workload, mean of 3 layer passes after 1 warm-up, wall clock around a device sync"}
 
 
 def run_reference(args):
-    """--impl reference: the reference's algorithm on the host cores (the oracle port; the reference
-    itself is Python-over-ATen and /root/reference does not exist on the GPU box)."""
+    """--impl reference: the reference's algorithm on the host cores -- the C/OpenMP restatement (oracle/fgnn_oracle.c;
+    the reference itself is Python-over-ATen and /root/reference does not exist on the GPU box) with all host
+    threads, on the arm's own workload at FULL scale, `--warmup` + `--steps` steps as asked.  Only if that would
+    take more than ~4 minutes is every step cut to a 1/scale instance (said in `config.sample`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import fgnn_oracle as orc
     orc.build_c()
-    scale = args.cpu_sample_scale
-    rng = np.random.default_rng(args.seed + 1)
-    types = build_graph(args, scale)
-    inp = host_inputs(args, types, rng)
-    weights = layer_weights(args, len(types), rng)
-    msgs = sum(t.real_messages for t in types)
-    steps = max(1, min(args.steps, 3))
-    warm = 1
     cores = host_threads()
-    for _ in range(warm):
-        cpu_layer_pass(args, types, inp, weights[0], cores)
+    rng = np.random.default_rng(args.seed + 1)
+    scale, batch = 1, args.batch
+    while True:
+        types = build_graph(args, scale)
+        inp = host_inputs(args, types, rng, batch)
+        weights = layer_weights(args, len(types), rng)
+        cpu_layer_pass(args, types, inp, weights[0], cores)                       # first touch
+        t1 = cpu_layer_pass(args, types, inp, weights[0], cores)
+        if t1 * args.layers * (args.steps + args.warmup) <= 240.0 or scale >= 64 or batch <= 8:
+            break
+        if args.config == "cfg3":
+            batch = max(8, batch // 2)
+        else:
+            scale *= 2
+    msgs = sum(t.real_messages for t in types) * batch
+    for _ in range(args.warmup):
+        for l in range(args.layers):
+            cpu_layer_pass(args, types, inp, weights[l], cores)
     t0 = time.perf_counter()
-    for s in range(steps):
+    for s in range(args.steps):
         for l in range(args.layers):
             cpu_layer_pass(args, types, inp, weights[l], cores)
     dt = time.perf_counter() - t0
-    value = msgs * args.layers * steps / dt
-    sample = (f"each step = {args.layers} FGNN layers on a 1/{scale}-scale instance of the workload "
-              f"({types[0].n_vars} vars, {msgs} messages/layer)")
+    value = msgs * args.layers * args.steps / dt
+    full = scale == 1 and batch == args.batch
+    sample = (f"each step = {args.layers} FGNN layers on {'the full workload' if full else ('a 1/%d-scale instance' % scale if args.config != 'cfg3' else 'a batch of %d' % batch)} "
+              f"({types[0].n_vars} vars, {msgs} messages/layer), oracle/fgnn_oracle.c (C restatement of mp_nn.py:115-175, OpenMP, {cores} threads)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "sample": sample},
+        "config": {"workload": workload_name(args), "sample": sample, "full_scale": full},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -324,9 +440,19 @@ def run_native(args):
     types = build_graph(args)
     inp = host_inputs(args, types, rng)
     weights = layer_weights(args, len(types), rng)
-    msgs_layer = sum(t.real_messages for t in types)
+    msgs_layer = sum(t.real_messages for t in types) * args.batch
     bytes_layer = algorithmic_bytes_per_layer(args, types)
     J, L, C = len(types), args.layers, args.dim
+    # independent graphs (cfg3: codewords) shard by BATCH: replicas, no collective
+    batch_sharded = world > 1 and args.batch >= world
+    if batch_sharded:
+        from fgnn_b200.parallel import shard_range
+        b0, b1 = shard_range(args.batch, rank, world)
+        for k in ("x_v",):
+            inp[k] = inp[k][b0:b1]
+        for k in ("x_f", "et_v2f", "et_f2v"):
+            inp[k] = [a[b0:b1] for a in inp[k]]
+    B_loc = inp["x_v"].shape[0]
 
     def to_dev(a, pin=False):
         t = torch.from_numpy(np.ascontiguousarray(a))
@@ -348,8 +474,9 @@ def run_native(args):
     fdev = (lambda a: to_dev(a).to(torch.bfloat16)) if bf16 else to_dev
     d_in = dict(x_v=fdev(inp["x_v"]), x_f=[fdev(a) for a in inp["x_f"]],
                 et_v2f=[fdev(a) for a in inp["et_v2f"]], et_f2v=[fdev(a) for a in inp["et_f2v"]],
-                idx_v2f=[to_dev(a) for a in inp["idx_v2f"]], idx_f2v=[to_dev(a) for a in inp["idx_f2v"]])
-    if world > 1:
+                idx_v2f=[to_dev(a).expand(B_loc, -1, -1) for a in inp["idx_v2f"]],
+                idx_f2v=[to_dev(a).expand(B_loc, -1, -1) for a in inp["idx_f2v"]])
+    if world > 1 and not batch_sharded:
         # factor-sharded: this rank keeps its factor ranges, the compacted F->V tables and their edge types
         from fgnn_b200 import parallel
         plan = parallel.ShardedLayerPlan(types, rank, world, dev, exchange=args.exchange, exchange_ctas=args.exchange_ctas)
@@ -369,7 +496,7 @@ def run_native(args):
         rule = fgnn_b200.mp_conv_v2.AUTO_FAN_OUT[args.edge_types]
         for j, ty in enumerate(types):
             for name, idx, n_src in (("v2f%d" % j, d_in["idx_v2f"][j], ty.n_vars), ("f2v%d" % j, d_in["idx_f2v"][j], ty.n_factors)):
-                fan = idx.numel() / n_src
+                fan = idx.numel() / (n_src * B_loc)
                 if (args.src_calls == "auto" and fan >= rule) or name in args.src_calls.split(","):
                     sp = fgnn_b200.SourcePlan(idx, n_src)
                     if args.src_calls != "auto" or sp.n_rows * 1.25 <= idx.numel():
@@ -381,7 +508,7 @@ def run_native(args):
                              accumulate=accumulate, workspace=wsb, filters_version=ver, plan=plans.get(name))
 
     peer_xv = plan.peer_buffers(J, C) if (plan is not None and args.exchange == "peer") else None
-    side = [torch.cuda.Stream(device=dev) for _ in range(2)] if (world == 1 and args.concurrent_layer) else None
+    side = [torch.cuda.Stream(device=dev) for _ in range(2)] if (plan is None and args.concurrent_layer) else None
 
     def step(src):
         """src: dict of device tensors (x_v, x_f, tables).  Returns the final variable features."""
@@ -431,10 +558,19 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def checksum_of(t):
+        """Exact, order-independent fingerprint of a float tensor: the integer sum of its bit patterns."""
+        return int(t.contiguous().view(torch.int16 if t.dtype == torch.bfloat16 else torch.int32).to(torch.int64).sum().item())
+
     # ---- device-resident timing -----------------------------------------------------------
     for _ in range(2):
-        step(d_in)
+        final = step(d_in)
     barrier()
+    checksum = checksum_of(final)
+    if batch_sharded:                            # every rank holds its own codewords: the job's fingerprint is the sum
+        cs = torch.tensor([checksum], dtype=torch.int64, device=dev)
+        dist.all_reduce(cs)
+        checksum = int(cs.item())
     # The step is launch-bound from Python once the kernels are short (20-30 launches of 20-150 us, more so when
     # sharded): capture it once -- streams, events, programmatic launch edges and all -- and replay the graph.
     run_step, graphed, launches_per_step = (lambda: step(d_in)), False, None
@@ -478,6 +614,31 @@ def run_native(args):
     ms_step = ms / args.steps
     value = msgs_layer * L / (ms_step * 1e-3)
 
+    # ---- the same step back to back for a few seconds: the sustained (power-capped) condition ----------
+    sustained = None
+    if args.sustain_seconds > 0:
+        n_sus = max(args.steps, int(args.sustain_seconds / max(ms_step * 1e-3, 1e-6)) + 1)
+        if world > 1:
+            tn = torch.tensor([n_sus], device=dev)
+            dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+            n_sus = int(tn.item())
+        sampler2 = ClockSampler(local)
+        if rank == 0:
+            sampler2.start()
+        barrier()
+        ev0.record()
+        for _ in range(n_sus):
+            run_step()
+        ev1.record()
+        barrier()
+        ms_sus = ev0.elapsed_time(ev1)
+        if world > 1:
+            tt = torch.tensor([ms_sus], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_sus = float(tt.item())
+        sustained = {"value": msgs_layer * L * n_sus / (ms_sus * 1e-3), "unit": UNIT, "steps": n_sus, "seconds": ms_sus * 1e-3,
+                     "ms_per_step": ms_sus / n_sus, "clocks": sampler2.stop() if rank == 0 else None}
+
     # ---- end to end through the module API with host buffers --------------------------------
     e2e = None
     if not args.no_e2e and world == 1 and not bf16:
@@ -502,7 +663,7 @@ def run_native(args):
         pinned = dict(x_v=to_dev(inp["x_v"], True), x_f=[to_dev(a, True) for a in inp["x_f"]],
                       et_v2f=[to_dev(a, True) for a in inp["et_v2f"]], et_f2v=[to_dev(a, True) for a in inp["et_f2v"]],
                       idx_v2f=[to_dev(a, True) for a in inp["idx_v2f"]], idx_f2v=[to_dev(a, True) for a in inp["idx_f2v"]])
-        host_out = torch.empty((1, types[0].n_vars, C), dtype=torch.float32).pin_memory()
+        host_out = torch.empty((B_loc, types[0].n_vars, C), dtype=torch.float32).pin_memory()
         h2d = sum(t.numel() * t.element_size() for v in pinned.values() for t in (v if isinstance(v, list) else [v]))
         d2h = host_out.numel() * 4
 
@@ -546,11 +707,11 @@ def run_native(args):
                     for j in range(J):
                         if l == 0:
                             need(("idx_v2f", j), ("et_v2f", j))
-                        nf.append(mods[l][j]["v2f"](x_v, src["idx_v2f"][j], src["et_v2f"][j]))
+                        nf.append(mods[l][j]["v2f"](x_v, src["idx_v2f"][j].expand(B_loc, -1, -1), src["et_v2f"][j]))
                         if l == 0:
                             need(("x_f", j), ("idx_f2v", j), ("et_f2v", j))
                             x_f[j] = nm(src["x_f"][j])
-                        y = mods[l][j]["f2v"](x_f[j], src["idx_f2v"][j], src["et_f2v"][j])
+                        y = mods[l][j]["f2v"](x_f[j], src["idx_f2v"][j].expand(B_loc, -1, -1), src["et_f2v"][j])
                         nv = y if nv is None else nv + y
                     x_v, x_f = nv, nf
             done = torch.cuda.Event()
@@ -596,45 +757,68 @@ def run_native(args):
             dist.destroy_process_group()
         return
     peak, peak_src = hbm_peak()
-    achieved = bytes_layer * L / (ms_step * 1e-3) / 1e9
+    # roofline fractions are PER GPU: the job's algorithmic bytes (or flops) over N GPUs' worth of peak
+    achieved = bytes_layer * L / (ms_step * 1e-3) / 1e9 / world
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath) and args.edge_types == 16 and world == 1 and args.vars == 100_000 and args.src_calls == "auto":
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(tpath) and args.edge_types == 16 and world == 1 and args.config in (None, "cfg2") and args.src_calls == "auto" \
+            and args.vars == 100_000 and not bf16:
         traffic = json.load(open(tpath))["traffic_bytes_per_launch_avg"]     # ncu --set full of this very workload
     tpeak, tpeak_src = tensor_peak()
-    mma_flops = executed_mma_flops_per_layer(args, types, plans) if args.kernel != "simt" else 0
+    executed_rows_plans = plans if plan is None else {}
+    mma_flops = (executed_mma_flops_per_layer(args, types, executed_rows_plans) * args.batch) if args.kernel != "simt" else 0
+    exec_tflops = mma_flops * L / (ms_step * 1e-3) / 1e12 / world
+    n_calls = 2 * J * L
+    if batch_sharded:
+        par = "batch-sharded x%d: every rank runs its own codewords, no collective (replicas)" % world
+    elif world > 1:
+        par = "factor-sharded x%d + %s per layer" % (world, "fused max-reduce/epilogue/broadcast kernel over NVLink peer memory"
+                                                      if args.exchange == "peer" else "NCCL max-all-reduce")
+    else:
+        par = "single GPU"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
-        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong",                # the workload is the same graph (or batch) whatever N is
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "checksum": checksum,
         "config": {"workload": workload_name(args), "messages_per_layer": msgs_layer, "layers": L,
                    "kernel": args.kernel, "source_stationary_calls": sorted(plans),
                    "launch": ("CUDA graph of the step, replayed" if graphed else "from Python, call by call") +
-                             ("" if side is None else "; the V->F calls of a layer on their own streams beside the F->V chain"), "l2": "per-step working set (~%d MB/layer) exceeds the 126 MB L2; no explicit flush"
-                   % (bytes_layer // 1_000_000), "parallelism": ("factor-sharded x%d + %s per layer" % (world, "fused max-reduce/epilogue/broadcast kernel over NVLink peer memory"
-                                                                         if args.exchange == "peer" else "NCCL max-all-reduce"))
-                   if world > 1 else "single GPU"},
+                             ("" if side is None else "; the V->F calls of a layer on their own streams beside the F->V chain"),
+                   "l2": "per-step working set (~%d MB/layer) exceeds the 126 MB L2; no explicit flush" % (bytes_layer // 1_000_000),
+                   "gather": "cp.async row gather (TMA tile::gather4 measured slower: 64 requests of 512 B per item are "
+                             "request-rate bound, profiles/r01_early/r01_tc_gather4_variant_full.txt); edge types of a "
+                             "source-stationary tile by one TMA bulk copy",
+                   "parallelism": par},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic,
-                     "traffic_note": ("DRAM bytes per core call from ncu (profiles/r01_traffic.json). Above the algorithmic bytes on purpose: the "
-                                      "source-stationary calls write and re-read one O-wide message per edge (2*4*O bytes) to cut the tensor "
-                                      "work, which is what bounds this path; --src-calls none: 90.9 MB per call, 4 % slower") if traffic else None,
+                     "per_gpu": True, "traffic": traffic,
+                     "traffic_note": ("DRAM bytes per core call from ncu --set full (profiles/r02_traffic.json). Above the algorithmic bytes on "
+                                      "purpose: the source-stationary calls write and re-read one O-wide message per edge (2*4*O bytes) to "
+                                      "cut the tensor work") if traffic else None,
                      "peak_source": peak_src,
-                     "kernel": ("mp_tc_kernel / mp_src_kernel + mp_reduce_kernel (tcgen05; average over the step's %d core calls, "
-                                "a source-stationary call being two launches)" % (2 * J * L))
+                     "kernel": ("mp_src_kernel + mp_reduce_kernel / mp_tc_kernel (tcgen05; average over the step's %d core calls, "
+                                "a source-stationary call being two launches)" % n_calls)
                      if args.kernel != "simt" else "mp_simt_kernel",
-                     "algorithmic_bytes_per_launch": bytes_layer * L / (2 * J * L),
-                     "avg_launch_us": ms_step * 1e3 / (2 * J * L),
-                     "tensor": {"executed_tflops": mma_flops * L / (ms_step * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
-                                "frac": mma_flops * L / (ms_step * 1e-3) / 1e12 / tpeak if tpeak else None, "peak_source": tpeak_src,
-                                "note": "bf16 MMA flops actually issued (3 split-bf16 terms for fp32 parity) against the sustained "
-                                        "cuBLAS bf16 rate: at T=16 the tensor pipe, not HBM, bounds this path (DESIGN.md 3)"}},
+                     "algorithmic_bytes_per_launch": bytes_layer * L / n_calls / world,
+                     "avg_launch_us": ms_step * 1e3 / n_calls,
+                     "tensor": {"executed_tflops": exec_tflops, "peak": tpeak, "unit": "TFLOP/s",
+                                "frac": exec_tflops / tpeak if tpeak else None, "peak_source": tpeak_src, "per_gpu": True,
+                                "note": "bf16 MMA flops actually issued per GPU (3 split-bf16 terms for fp32 parity; one row-product per "
+                                        "virtual source row in source-stationary calls, per slot otherwise) against the sustained cuBLAS "
+                                        "bf16 rate: at T=16 the tensor pipe and tensor-memory reads, not HBM, bound pass 1 (DESIGN.md 3)"}},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    if sustained is not None:
+        sustained["roofline_frac"] = bytes_layer * L / (sustained["ms_per_step"] * 1e-3) / 1e9 / world / peak
+        line["sustained"] = sustained
+    if plan is not None and getattr(plan, "exchange_stats", None):
+        line["exchange"] = plan.exchange_stats
     if e2e is not None:
         line["e2e"] = e2e
+    if world == 1 and not args.no_aten_baseline and not bf16:
+        line["gpu_aten_baseline"] = gpu_aten_baseline(args, types, inp, weights[0])
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"], _ = cpu_baseline(args)
+        line["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -21,6 +21,28 @@ def test_unit_cases(case, impl):
     assert_close(got, case["out"], ORACLE_RTOL, m["name"])
 
 
+@pytest.mark.parametrize("case", CASES, ids=[c["meta"]["name"] for c in CASES])
+@pytest.mark.parametrize("chunk", [0, 3])
+def test_torch_port_unit_cases(case, chunk):
+    """The PyTorch restatement in the reference's op order (the `port-torch` CPU baseline and the ATen-on-GPU
+    baseline of bench.py) against the same reference outputs; chunking over destinations is bit-identical."""
+    import torch
+    from oracle import fgnn_oracle_torch as orct
+    m, sd = case["meta"], case["sd"]
+    t = torch.from_numpy
+    bn = bn_of(sd)
+    bn = {k: t(v) for k, v in bn.items()} if bn is not None else None
+    got = orct.mp_conv_forward_torch(t(case["x"]), t(case["idx"]), t(case["etype"]), t(sd["filters"]),
+                                     t(sd["bias"]) if "bias" in sd else None, bn, extension=m["ext"], aggregator=m["agg"],
+                                     activation=m.get("act", "relu"), chunk_rows=chunk)
+    assert_close(got.numpy(), case["out"], 1e-6, m["name"])
+    if chunk:
+        whole = orct.mp_conv_forward_torch(t(case["x"]), t(case["idx"]), t(case["etype"]), t(sd["filters"]),
+                                           t(sd["bias"]) if "bias" in sd else None, bn, extension=m["ext"],
+                                           aggregator=m["agg"], activation=m.get("act", "relu"))
+        assert torch.equal(got, whole)
+
+
 def test_out_of_range_index_raises():
     c = CASES[0]
     bad = c["idx"].copy()
