@@ -13,7 +13,7 @@ from ._lib import FgnnError
 from .build import build
 from .mp_nn import (SourcePlan, base_mp_nn, check_async_errors, clear_table_cache, invalidate_caches, mp_conv_residual, mp_conv_type,
                     mp_conv_v2, mp_forward)
-from .factor_nn import (FactorNN, FVModule, iid_mapping, iid_mapping_bn, iid_mapping_in,
+from .factor_nn import (FactorNN, FVModule, factor_mpnn, iid_mapping, iid_mapping_bn, iid_mapping_in,
                         mp_sequential)
 
 __version__ = "0.1.0"

@@ -65,7 +65,9 @@ namespace fgnn {
 // 16-byte chunks XOR-swizzled with row % 8): image[part][n][c], n = column o*T+t; part 0 = bf16(W)
 // (all the bf16-I/O kernel uses), part 1 = bf16(W - part 0).
 // ---------------------------------------------------------------------------------------------
-__global__ void w_split_kernel(const float* __restrict__ W, uint8_t* __restrict__ ws, int C, int OT, int64_t version) {
+// diff != 0 (ORIG_WITH_DIFF, C = 2 x 64 filter rows): the image holds [W_top + W_bot ; -W_bot], so that
+// [x_i || x_j] . image == [x_i || x_i - x_j] . W  (mp_nn.py:136-159 evaluated as x_i (W_top + W_bot) - x_j W_bot).
+__global__ void w_split_kernel(const float* __restrict__ W, uint8_t* __restrict__ ws, int C, int OT, int64_t version, int diff) {
   tc::Header* h = reinterpret_cast<tc::Header*>(ws);
   if (version != 0 && h->version == version && h->filters == W && h->C == C && h->OT == OT) return;
   uint8_t* img = ws + tc::kHeaderBytes;
@@ -76,7 +78,12 @@ __global__ void w_split_kernel(const float* __restrict__ W, uint8_t* __restrict_
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float a = W[(int64_t)(chunk * 8 + 2 * j) * OT + n], b = W[(int64_t)(chunk * 8 + 2 * j + 1) * OT + n];
+      float a = W[(int64_t)(chunk * 8 + 2 * j) * OT + n], b = W[(int64_t)(chunk * 8 + 2 * j + 1) * OT + n];
+      if (diff) {
+        const int c0 = chunk * 8 + 2 * j, half = C / 2;
+        if (c0 < half) { a += W[(int64_t)(c0 + half) * OT + n]; b += W[(int64_t)(c0 + 1 + half) * OT + n]; }
+        else { a = -a; b = -b; }
+      }
       const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
       const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
       const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
@@ -503,6 +510,11 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     };
     const uint8_t* xq = reinterpret_cast<const uint8_t*>(p.x) + q * 16;
     const uint32_t sA_u = smem_u32(sA);
+    // Extension modes (mp_nn.py:136-159; KA == 2 with C = 64): the 512-byte A row of slot (m, k) is [x_m || x_idx] --
+    // K atom 0 = the destination's own row (M == N: row g of x), K atom 1 = the gathered neighbour; the filter image
+    // carries the NEIGHBOR / DIFF algebra (w_split_kernel).  Source rows are then 256 bytes apart.
+    const bool two_src = KA == 2 && p.ext != 0;
+    const uint32_t src_rowb = two_src ? (uint32_t)(ROWB / 2) : (uint32_t)ROWB;
     // Warp instruction u (of NIT per item) copies chunk q of the RPW rows RPW*u + sub of this warp's 64:
     // chunk q of tile row rr lands at position q ^ (rr & (LPR-1)) (the converter's per-row reads are then
     // conflict-free).  The swizzle term repeats every NDO instructions, so the shared-memory offset is one
@@ -520,6 +532,8 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     pdl_wait();                                              // x is the preceding launch's output: order behind it
     for (uint32_t i = 0; it.tile < n_tiles; ++i) {
       const uint32_t st = i % NST, use = i / NST;
+      const int cur_tile = it.tile;
+      (void)cur_tile;
       next_item(it);
       index_of(it, nxt);                                     // index loads of the next item: in flight during this one
       mbar_wait(raw_empty(st), (use & 1) ^ 1);
@@ -529,8 +543,9 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
       uint32_t off[IPL];
 #pragma unroll
       for (int j = 0; j < IPL; ++j)
-        off[j] = (cur.base[j] >= 0 && cur.n[j] >= 0 && cur.n[j] < p.N) ? (uint32_t)(cur.base[j] + (int32_t)cur.n[j]) * ROWB
+        off[j] = (cur.base[j] >= 0 && cur.n[j] >= 0 && cur.n[j] < p.N) ? (uint32_t)(cur.base[j] + (int32_t)cur.n[j]) * src_rowb
                                                                        : 0xffffffffu;
+
       const uint32_t stage = sA_u + st * STAGEB;
 #pragma unroll
       for (int u0 = 0; u0 < NIT; u0 += 8) {                  // batches of 8: all shuffles first, then the copies
@@ -545,7 +560,14 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
                                        : stage + (uint32_t)(pw * ROWS_W + u) * ROWB +
                                              (uint32_t)(((q & ~SWZ) | ((q ^ u) & SWZ)) * 16);
           const bool ok = o[j] != 0xffffffffu;
-          cp_async16(dst, xq + (ok ? o[j] : 0u), ok ? 16u : 0u);
+          if (KA == 2 && two_src) {
+            // lanes 0-15: chunk q of the destination's own row; lanes 16-31: chunk q-16 of the neighbour
+            const uint32_t g_self = (uint32_t)cur_tile * kTileM + (uint32_t)(pw * ROWS_W + u);
+            const uint32_t so = (q < 16 ? g_self * src_rowb : o[j]) + (uint32_t)(q & 15) * 16u;
+            cp_async16(dst, reinterpret_cast<const uint8_t*>(p.x) + (ok ? so : 0u), ok ? 16u : 0u);
+          } else {
+            cp_async16(dst, xq + (ok ? o[j] : 0u), ok ? 16u : 0u);
+          }
         }
       }
       cp_async_arrive_noinc(raw_full(st));
@@ -709,7 +731,8 @@ extern "C" int fgnn_debug_trace_read(unsigned long long* host, size_t count) {
 // The bf16 image of `W` in `ws` is rebuilt unless this workspace is known to hold the image of exactly these
 // filters (pointer + caller-supplied version).  Host-side mirror of the device header: a cached image costs
 // no launch at all.  version == 0 always rebuilds.
-int tc_prepare_weights(const float* W, uint8_t* ws, int C, int OT, int64_t version, cudaStream_t stream) {
+int tc_prepare_weights(const float* W, uint8_t* ws, int C, int OT, int64_t version, cudaStream_t stream, int diff) {
+  if (version != 0) version = version * 2 + (diff ? 1 : 0);                 // the image depends on the transform
   static std::mutex mu;
   static std::unordered_map<const void*, tc::Header> known;
   bool fresh = false;
@@ -727,7 +750,7 @@ int tc_prepare_weights(const float* W, uint8_t* ws, int C, int OT, int64_t versi
     known.erase(ws);
   }
   if (!fresh) {
-    w_split_kernel<<<(OT * (C / 8) + 255) / 256, 256, 0, stream>>>(W, ws, C, OT, 0);
+    w_split_kernel<<<(OT * (C / 8) + 255) / 256, 256, 0, stream>>>(W, ws, C, OT, 0, diff);
     count_launch();
     if (cudaGetLastError() != cudaSuccess) return FGNN_ERR_CUDA;
   }
@@ -747,12 +770,19 @@ int tc_num_sms() {
 
 bool tc_pdl_enabled() { return g_pdl; }
 
+// K atoms of the A operand: C / 64, or two for the extension modes at C = 64 ([x_m || x_idx])
+static int tc_k_atoms(const fgnn_mp_args* a) { return a->extension != FGNN_NO_EXTENSION ? 2 : a->C / tc::kC; }
+
 bool tc_supported(const fgnn_mp_args* a) {
-  if (a->extension != FGNN_NO_EXTENSION) return false;
   if (a->dtype != FGNN_F32 && a->dtype != FGNN_BF16) return false;
   const bool xb = a->dtype == FGNN_BF16;
-  if (a->C != tc::kC && !(a->C == 2 * tc::kC && !xb)) return false;        // C = 128: fp32 I/O only
-  const int ka = a->C / tc::kC;
+  if (a->extension != FGNN_NO_EXTENSION) {
+    // NEIGHBOR / DIFF (mp_nn.py:136-159) as a two-atom row [x_m || x_idx] against a transformed filter image
+    if (a->C != tc::kC || xb || a->M != a->N || a->tile_slots || a->out_rows) return false;
+  } else if (a->C != tc::kC && !(a->C == 2 * tc::kC && !xb)) {
+    return false;                                                           // C = 128: fp32 I/O only
+  }
+  const int ka = tc_k_atoms(a);
   if (a->aggregator == FGNN_AGG_NONE) return false;
   if (a->x_sc != 1 || a->x_sn != a->C) return false;                              // node-major rows
   if (a->B > 1 && a->x_sb != (int64_t)a->N * a->C) return false;                  // batch-contiguous
@@ -770,18 +800,18 @@ bool tc_supported(const fgnn_mp_args* a) {
 }
 
 size_t tc_workspace_bytes(const fgnn_mp_args* a) {
-  return tc::kHeaderBytes + (size_t)2 * (a->C > tc::kC ? 2 : 1) * a->O * a->T * 128;
+  return tc::kHeaderBytes + (size_t)2 * tc_k_atoms(a) * a->O * a->T * 128;
 }
 
 int launch_mp_tc(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream) {
   const bool xb = a->dtype == FGNN_BF16;
-  const int ka = p.C / tc::kC;
+  const int ka = tc_k_atoms(a);
   TcConfig c = pick_config(p.T, p.agg, p.O * p.T, xb, ka);
   if (!c.ok) return FGNN_ERR_UNSUPPORTED;
   uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
   if (reinterpret_cast<uintptr_t>(ws) & 255) return FGNN_ERR_WORKSPACE;
   const int OT = p.O * p.T;
-  const int wrc = tc_prepare_weights(p.W, ws, p.C, OT, a->filters_version, stream);
+  const int wrc = tc_prepare_weights(p.W, ws, ka * tc::kC, OT, a->filters_version, stream, p.ext == FGNN_ORIG_WITH_DIFF);
   if (wrc != FGNN_OK) return wrc;
 
   const int num_sms = tc_num_sms();

@@ -219,3 +219,75 @@ class FactorNN(torch.nn.Module):
         if self.final_filter is not None:
             res = self.final_filter(res, node_feature)
         return (res, x_f) if self.ret_high else res
+
+
+class factor_mpnn(torch.nn.Module):
+    """Stacked FGNN over MERGED tables (factor_mpnn.py:8-133; train_syn_pw_factor.py / train_syn_hop_factor.py): per
+    layer and factor type the variable and factor features are concatenated along the node axis and ONE core call
+    does the Variable->Factor and the Factor->Variable step together (`nn_idx [B, N+F, K]`: the first N rows name
+    factor rows, the last F rows variable rows); the per-type variable features are concatenated along channels and
+    merged by a 1x1 map.  Same constructor arguments, forward signature and state_dict keys as the reference; the
+    cores are fgnn_b200 modules (ORIG_WITH_DIFF, which runs on the tensor-core kernel through the two-atom row
+    [x_m || x_idx] against a transformed filter image)."""
+
+    def __init__(self, node_feature_dim, factor_feature_dim_list, dim_mapping_list, netype_list,
+                 gnn_immediate_dim=64, max_mpnn_dim=64, final_filter=None, skip_link={}):
+        super().__init__()
+        self.node_feature_dim = node_feature_dim
+        self.map_dim = dim_mapping_list[0]
+        self.mapping_modules = [iid_mapping(node_feature_dim, self.map_dim)]
+        self.nfactor_types = len(factor_feature_dim_list)
+        for dim in factor_feature_dim_list:
+            self.mapping_modules.append(iid_mapping(dim, self.map_dim))
+        for i, m in enumerate(self.mapping_modules):
+            self.add_module('mapping_modules_{}'.format(i), m)
+        self.mp_nn_modules, self.mp_merge_modules = [], []
+        self.final_filter = final_filter
+        for i in range(len(dim_mapping_list) - 1):
+            nin, nout = dim_mapping_list[i], dim_mapping_list[i + 1]
+            row = []
+            for j in range(self.nfactor_types):
+                if nin == nout:                                            # factor_mpnn.py:55-57
+                    m = mp_conv_residual(nin, gnn_immediate_dim, netype_list[j])
+                elif nin <= max_mpnn_dim and nout <= max_mpnn_dim:         # :59-60
+                    m = mp_conv_v2(nin, nout, netype_list[j])
+                else:                                                      # :62-65
+                    m = torch.nn.Sequential(torch.nn.Conv2d(nin, nout, 1), torch.nn.InstanceNorm2d(nout),
+                                            torch.nn.ReLU(inplace=True))
+                self.add_module('mp_nn_{}_{}'.format(i, j), m)
+                row.append(m)
+            self.mp_nn_modules.append(row)
+            if i < len(dim_mapping_list) - 2:
+                merge = iid_mapping_bn(nout * self.nfactor_types, nout)
+            else:
+                merge = torch.nn.Sequential(
+                    torch.nn.Conv2d(nout * self.nfactor_types, 256, 1, bias=True), torch.nn.BatchNorm2d(256),
+                    torch.nn.LeakyReLU(), torch.nn.Conv2d(256, 256, 1, bias=True), torch.nn.LeakyReLU(),
+                    torch.nn.Conv2d(256, nout, 1, bias=True))
+            self.add_module('merge_module_{}'.format(i), merge)
+            self.mp_merge_modules.append(merge)
+        self.skip_link = skip_link
+
+    def forward(self, node_features, factor_features, graph_structures):
+        nnode = node_features.shape[2]
+        x_v = self.mapping_modules[0](node_features)
+        x_f = [m(f) for f, m in zip(factor_features, self.mapping_modules[1:])]
+        history = []
+        for i, modules in enumerate(self.mp_nn_modules):
+            per_type_v, new_f = [], []
+            for j, (f, m) in enumerate(zip(x_f, modules)):
+                merged = torch.cat([x_v, f], dim=2)
+                nn_idx, etype = graph_structures[j]
+                merged = m(merged, nn_idx, etype) if isinstance(m, base_mp_nn) else m(merged.contiguous())
+                per_type_v.append(merged[:, :, :nnode, :])
+                new_f.append(merged[:, :, nnode:, :])
+            x_v = self.mp_merge_modules[i](torch.cat(per_type_v, dim=1))
+            x_f = new_f
+            if i in self.skip_link.keys():
+                old_v, old_f = history[self.skip_link[i]]
+                x_v = x_v + old_v
+                x_f = [a + b for a, b in zip(x_f, old_f)]
+            history.append([x_v, x_f])
+        if self.final_filter is not None:
+            x_v = self.final_filter(x_v, node_features)
+        return x_v, x_f

@@ -307,7 +307,8 @@ def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=Non
     # tensor returns; the reference permutes it itself, mp_nn.py:125) is brought to node-major memory with one
     # pass of the library's own transpose when the call otherwise qualifies for them -- that pass costs 8 bytes
     # per element, the fp32 CUDA-core kernel it avoids is 10-60x slower.  Results do not depend on the layout.
-    if (extension == 0 and C in (64, 128) and kernel != _lib.KERNEL_SIMT and x3.dtype == torch.float32
+    if (((extension == 0 and C in (64, 128)) or (extension != 0 and C == 64 and M == N))
+            and kernel != _lib.KERNEL_SIMT and x3.dtype == torch.float32
             and aggregator != _lib.AGG_NONE and N > 0 and B * M * K > 0
             and not (x3.stride(1) == 1 and x3.stride(2) == C and (B == 1 or x3.stride(0) == N * C))):
         xt = torch.empty((B, N, C), dtype=torch.float32, device=dev)

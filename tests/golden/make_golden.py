@@ -223,16 +223,63 @@ def ldpc(mpnn):
           float(res.abs().min()), "idx_f2v", idx_f2v.shape, "idx_v2f", idx_v2f.shape)
 
 
+def factor_mpnn_merged(mpnn):
+    """The merged-table path of train_syn_hop_factor.py / train_syn_pw_factor.py: the reference's
+    `factor_mpnn` (lib/model/mpnn/factor_mpnn.py:88-133) on a chain of n = 30 variables with the scripts' own
+    `generate_pw_factor_table(n)` / `generate_high_factor_table(n, 4)` (train_syn_hop_factor.py:112-151) and edge
+    models (:174-179); dims [64, 64, 2]: a residual layer (ORIG_WITH_DIFF cores, max) and the bare
+    mp_conv_v2(64 -> 2) last layer with the default softmax aggregator; B = 4; MAP = argmax over the 2 channels."""
+    gen = torch.Generator().manual_seed(4242)
+    fns = refload.script_functions("train_syn_hop_factor.py", ["generate_pw_factor_table", "generate_high_factor_table"])
+    n, hop = 30, 4
+    idx_pw, ef_pw = fns["generate_pw_factor_table"](n)              # [1, 2n, 2], [1, 3, 2n, 2]
+    idx_hi, ef_hi = fns["generate_high_factor_table"](n, hop)       # [1, 2n, hop], [1, 2, 2n, hop]
+    model = refload.quiet(mpnn.factor_mpnn, 2, [4, hop], [64, 64, 2], [16, 16])
+    em_pw = torch.nn.Sequential(torch.nn.Conv2d(3, 64, 1), torch.nn.ReLU(inplace=True), torch.nn.Conv2d(64, 16, 1))
+    em_hi = torch.nn.Sequential(torch.nn.Conv2d(2, 64, 1), torch.nn.ReLU(inplace=True), torch.nn.Conv2d(64, 16, 1))
+    randomise(model, gen, filt_scale=0.25)
+    randomise(em_pw, gen)
+    randomise(em_hi, gen)
+    B = 4
+    node = torch.rand(B, 2, n, 1, generator=gen)
+    f_pw = torch.rand(B, 4, n, 1, generator=gen)
+    f_hi = torch.rand(B, hop, n, 1, generator=gen)
+    with torch.no_grad():
+        et_pw = em_pw(ef_pw).repeat(B, 1, 1, 1)
+        et_hi = em_hi(ef_hi).repeat(B, 1, 1, 1)
+        i_pw, i_hi = idx_pw.repeat(B, 1, 1), idx_hi.repeat(B, 1, 1)
+        out_v, out_f = model(node, [f_pw, f_hi], [[i_pw, et_pw], [i_hi, et_hi]])
+        # centre the two logits (random weights leave the output bias-dominated: every label equal, SURVEY 7 hard
+        # part 3) so that the MAP check is not vacuous
+        d = torch.sort((out_v[:, 0] - out_v[:, 1]).reshape(-1)).values
+        mid = slice(d.numel() // 3, 2 * d.numel() // 3)
+        gap = int(torch.argmax(d[mid][1:] - d[mid][:-1])) + mid.start        # the widest gap near the median: decisions keep a margin
+        model.mp_merge_modules[-1][-1].bias.data[0] -= 0.5 * (d[gap] + d[gap + 1])
+        out_v, out_f = model(node, [f_pw, f_hi], [[i_pw, et_pw], [i_hi, et_hi]])
+    labels = out_v.squeeze(-1).argmax(dim=1)
+    margin = (out_v[:, 0] - out_v[:, 1]).abs().min().item()
+    out = dict(node=node.numpy(), f_pw=f_pw.numpy(), f_hi=f_hi.numpy(), idx_pw=idx_pw.numpy(), idx_hi=idx_hi.numpy(),
+               et_pw=et_pw.numpy(), et_hi=et_hi.numpy(), out_v=out_v.numpy(), out_f0=out_f[0].numpy(), out_f1=out_f[1].numpy(),
+               labels=labels.numpy(), min_margin=np.float32(margin))
+    out.update(sd_np(model, "model/"))
+    np.savez_compressed(os.path.join(HERE, "factor_mpnn_merged.npz"), **out)
+    print("factor_mpnn_merged.npz: labels ones =", int(labels.sum()), "of", labels.numel(), "min |margin| =", margin)
+
+
 def main():
     if not refload.available():
         raise SystemExit("reference tree not found; golden vectors can only be regenerated in the build container")
     mpnn = refload.load()
     torch.manual_seed(0)
     np.random.seed(23456)
+    if len(sys.argv) > 1 and sys.argv[1] == "factor_mpnn":
+        factor_mpnn_merged(mpnn)
+        return
     unit_cases(mpnn)
     cfg1_simple_gnn(mpnn)
     cfg1_factornn(mpnn)
     ldpc(mpnn)
+    factor_mpnn_merged(mpnn)
 
 
 if __name__ == "__main__":

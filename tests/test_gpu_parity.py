@@ -204,6 +204,54 @@ def test_ldpc_factornn_hard_decisions_bit_exact():
     assert np.array_equal((res >= 0).cpu().numpy(), g["hard"])
 
 
+def test_factor_mpnn_merged_tables_labels_bit_exact():
+    """The merged-table model of train_syn_hop_factor.py / train_syn_pw_factor.py (factor_mpnn.py:88-133): golden from
+    the real reference.  Its ORIG_WITH_DIFF residual cores (C = 64) run on the tensor-core kernel."""
+    g = load_npz("factor_mpnn_merged.npz")
+    model = fgnn_b200.factor_mpnn(2, [4, 4], [64, 64, 2], [16, 16])
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sub_sd(g, "model").items()})
+    model = model.to(DEV).eval()
+    B = g["node"].shape[0]
+    before = fgnn_b200.launch_count()
+    with torch.no_grad():
+        out_v, out_f = model(t(g["node"]), [t(g["f_pw"]), t(g["f_hi"])],
+                             [[t(g["idx_pw"]).repeat(B, 1, 1), t(g["et_pw"])], [t(g["idx_hi"]).repeat(B, 1, 1), t(g["et_hi"])]])
+    assert fgnn_b200.launch_count() > before
+    assert_close(out_v.cpu().numpy(), g["out_v"], RTOL, "out_v")
+    assert_close(out_f[0].cpu().numpy(), g["out_f0"], RTOL, "out_f0")
+    assert_close(out_f[1].cpu().numpy(), g["out_f1"], RTOL, "out_f1")
+    labels = out_v.squeeze(-1).argmax(1).cpu().numpy()
+    assert np.array_equal(labels, g["labels"]) and 0 < labels.sum() < labels.size
+
+
+@pytest.mark.parametrize("ext", [1, 2])
+@pytest.mark.parametrize("agg", ["max", "softmax", "mean"])
+@pytest.mark.parametrize("shape", [dict(B=2, N=300, K=4, O=64, T=16), dict(B=8, N=128, K=4, O=64, T=16),
+                                   dict(B=32, N=60, K=9, O=64, T=16), dict(B=1, N=1000, K=3, O=128, T=4),
+                                   dict(B=3, N=130, K=2, O=32, T=8)],
+                         ids=lambda s: "B{B}_N{N}_K{K}_O{O}_T{T}".format(**s))
+def test_extension_modes_on_tensor_cores(ext, agg, shape):
+    """ORIG_WITH_NEIGHBOR / ORIG_WITH_DIFF (mp_nn.py:136-159) at C = 64 select the tcgen05 kernel: the A row of a
+    slot is [x_m || x_idx] (two K atoms) against the filter image [W_top ; W_bot] resp. [W_top + W_bot ; -W_bot].
+    Shapes: cfg 1 (N = 128, K = 4, B = 8) and the factor_mpnn scripts (N + F = 60, K = 2 / 9, B = 32)."""
+    rng = np.random.default_rng(ext * 100 + shape["N"])
+    B, N, K, O, T = (shape[k] for k in "BNKOT")
+    x, idx, et, W0, bias, bn = _random_call(rng, B=B, N=N, M=N, K=K, C=64, O=O, T=T)
+    W = (rng.uniform(-1, 1, (128, O * T)) * 0.1).astype(np.float32)
+    code = {"max": 0, "softmax": 1, "mean": 2}[agg]
+    a = _lib.MpArgs()
+    a.x = a.idx = a.etype = a.filters = a.out = 4096
+    a.B, a.N, a.M, a.K, a.C, a.O, a.T = B, N, N, K, 64, O, T
+    a.x_sc, a.x_sn, a.x_sb, a.out_so, a.out_sm, a.out_sb, a.out_sk = 1, 64, N * 64, 1, O, N * O, 1
+    a.extension, a.aggregator = ext, code
+    assert _lib.lib().fgnn_mp_select_kernel(ctypes.byref(a)) == _lib.KERNEL_TCGEN05
+    y = _native(x, idx, et, W, bias, bn, agg=code, extension=ext)
+    y_simt = _native(x, idx, et, W, bias, bn, agg=code, extension=ext, kernel=_lib.KERNEL_SIMT)
+    ref = orc.mp_conv_forward_c(x, idx, et, W, bias, bn, extension=ext, aggregator=agg)
+    assert_close(y.cpu().numpy(), ref, RTOL, f"ext {ext} {agg} tensor cores")
+    assert_close(y_simt.cpu().numpy(), ref, RTOL, f"ext {ext} {agg} simt")
+
+
 # ---------------------------------------------------------------------------------------------
 # seeded inputs vs the CPU oracle at sizes it finishes in seconds; properties at full size
 # ---------------------------------------------------------------------------------------------
@@ -221,12 +269,12 @@ def _random_call(rng, B, N, M, K, C, O, T, pad_frac=0.1):
     return x, idx, et, W, bias, bn
 
 
-def _native(x, idx, et, W, bias, bn, agg=_lib.AGG_MAX, kernel=_lib.KERNEL_AUTO, **kw):
+def _native(x, idx, et, W, bias, bn, agg=_lib.AGG_MAX, kernel=_lib.KERNEL_AUTO, extension=0, **kw):
     scale = bn["weight"] / np.sqrt(bn["running_var"] + 1e-5)
     shift = bn["bias"] - bn["running_mean"] * scale
     xt = t(x).contiguous(memory_format=torch.channels_last)
     y = fgnn_b200.mp_forward(xt, t(idx), t(et), t(W), t(bias), t(scale.astype(np.float32)),
-                             t(shift.astype(np.float32)), extension=0, aggregator=agg, kernel=kernel, **kw)
+                             t(shift.astype(np.float32)), extension=extension, aggregator=agg, kernel=kernel, **kw)
     return y
 
 

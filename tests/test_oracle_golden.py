@@ -100,3 +100,19 @@ def test_ldpc_factornn():
     assert_close(res, g["res"], 5e-5, "res")
     assert_close(nhops[0], g["nhop0"], 5e-5, "nhop0")
     assert np.array_equal(res >= 0, g["hard"])
+
+
+def test_factor_mpnn_merged_tables():
+    """The merged-table model of train_syn_hop_factor.py (factor_mpnn.py:88-133): ORIG_WITH_DIFF residual cores and
+    the bare 64 -> 2 last layer with the default softmax aggregator; MAP labels bit-exact."""
+    g = load_npz("factor_mpnn_merged.npz")
+    sd = sub_sd(g, "model")
+    B = g["node"].shape[0]
+    rep = lambda a: np.repeat(a, B, 0)
+    out_v, out_f = orc.factor_mpnn_forward(sd, g["node"], [g["f_pw"], g["f_hi"]],
+                                           [(rep(g["idx_pw"]), g["et_pw"]), (rep(g["idx_hi"]), g["et_hi"])], [64, 64, 2])
+    assert_close(out_v, g["out_v"], 5e-5, "out_v")
+    assert_close(out_f[0], g["out_f0"], 5e-5, "out_f0")
+    assert_close(out_f[1], g["out_f1"], 5e-5, "out_f1")
+    labels = out_v[..., 0].argmax(1)
+    assert np.array_equal(labels, g["labels"]) and 0 < labels.sum() < labels.size
