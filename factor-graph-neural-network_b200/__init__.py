@@ -11,7 +11,7 @@ file by path.  Public surface = the reference's `lib.model.mpnn` names for this 
 from . import _lib
 from ._lib import FgnnError
 from .build import build
-from .mp_nn import (SourcePlan, base_mp_nn, check_async_errors, clear_table_cache, invalidate_caches, mp_conv_residual, mp_conv_type,
+from .mp_nn import (SourcePlan, base_mp_nn, check_async_errors, clear_table_cache, emodel_forward, invalidate_caches, mp_conv_residual, mp_conv_type,
                     mp_conv_v2, mp_forward)
 from .factor_nn import (FactorNN, FVModule, factor_mpnn, iid_mapping, iid_mapping_bn, iid_mapping_in,
                         mp_sequential)

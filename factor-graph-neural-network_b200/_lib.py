@@ -93,6 +93,10 @@ EXPORTS = {
     "fgnn_src_permute_etype": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                               ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
                                               ctypes.c_void_p]),
+    "fgnn_emodel_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                           ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                           ctypes.c_int32, ctypes.c_void_p]),
     "fgnn_comm_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
     "fgnn_comm_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
     "fgnn_comm_close": (ctypes.c_int, [ctypes.c_void_p]),

@@ -432,6 +432,45 @@ def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=Non
     return out
 
 
+def emodel_forward(emodel, efeature, plan=None):
+    """The scripts' edge model `Sequential(Conv2d(Fe, 64, 1), ReLU, Conv2d(64, T, 1))` (train_ldpc.py:32-38;
+    train_syn_hop_factor.py:174-179) as ONE kernel (`fgnn_emodel_forward`): the 64-channel hidden tensor never reaches
+    HBM.  efeature [B,Fe,M,K] fp32 CUDA.  Returns etype [B,T,M,K]; with `plan` (a SourcePlan of the table these edge
+    types belong to) the plan's edge-type image is produced as well and attached to the plan for this etype object,
+    so the first source-stationary call skips its permute pass."""
+    mods = list(emodel)
+    if not (len(mods) == 3 and isinstance(mods[0], torch.nn.Conv2d) and isinstance(mods[1], torch.nn.ReLU)
+            and isinstance(mods[2], torch.nn.Conv2d) and mods[0].kernel_size == (1, 1) and mods[2].kernel_size == (1, 1)
+            and mods[0].out_channels == 64 and mods[2].in_channels == 64):
+        raise ValueError("emodel_forward expects Sequential(Conv2d(Fe, 64, 1), ReLU, Conv2d(64, T, 1))")
+    if not efeature.is_cuda or efeature.dtype != torch.float32 or efeature.dim() != 4:
+        raise RuntimeError("fgnn_b200: emodel_forward needs a float32 CUDA tensor [B,Fe,M,K]")
+    B, Fe, M, K = efeature.shape
+    T = mods[2].out_channels
+    if Fe != mods[0].in_channels:
+        raise ValueError("efeature has %d channels, the edge model takes %d" % (Fe, mods[0].in_channels))
+    ef = efeature if (efeature.stride(3) == 1 and efeature.stride(2) == K and efeature.stride(1) == M * K) else efeature.contiguous()
+    ef_sb = ef.stride(0) if B > 1 else Fe * M * K
+    w1 = mods[0].weight.detach().reshape(64, Fe).contiguous()
+    w2 = mods[2].weight.detach().reshape(T, 64).contiguous()
+    b1 = mods[0].bias.detach().contiguous() if mods[0].bias is not None else None
+    b2 = mods[2].bias.detach().contiguous() if mods[2].bias is not None else None
+    out = torch.empty((B, T, M, K), dtype=torch.float32, device=ef.device)
+    lib = _lib.lib()
+    with torch.cuda.device(ef.device):
+        st = ctypes.c_void_p(torch.cuda.current_stream(ef.device).cuda_stream)
+        _lib.check(lib.fgnn_emodel_forward(_ptr(ef), ef_sb, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(out), T * M * K, None, 0,
+                                           B, Fe, 64, T, M, K, st), "emodel_forward")
+        if plan is not None:
+            if (plan.B, plan.M, plan.K) != (B, M, K):
+                raise ValueError("plan was built for another index table")
+            img = torch.empty((max(1, plan.n_edges), T), dtype=torch.float32, device=ef.device)
+            _lib.check(lib.fgnn_emodel_forward(_ptr(ef), ef_sb, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(img), 0,
+                                               _ptr(plan.edge_slot), plan.n_edges, B, Fe, 64, T, M, K, st), "emodel_forward")
+            plan._et = (weakref.ref(out), out._version, out.data_ptr(), img)
+    return out
+
+
 class mp_conv_v2(base_mp_nn):
     """Message passing layer (VF and FV module of FGNN); reference mp_nn.py:13-175.
 

@@ -165,10 +165,22 @@ int fgnn_mp_forward_host(const fgnn_mp_args* host_args);
 /* 1 if `args` (with its source-stationary plan fields set) qualifies for the source-stationary path, else 0. */
 int fgnn_mp_src_supported(const fgnn_mp_args* args);
 
-/* etype [B,T,M,K] (reference layout, batch stride et_sb elements) -> edge-major [E,T] in the plan's edge order:
- * out[e, t] = etype[b, t, m, k] for edge e = slot (b*M + m)*K + k = edge_slot[e].  Asynchronous on `stream`. */
+/* etype [B,T,M,K] (reference layout, batch stride et_sb elements) -> the plan's edge-type image: edge-major [E,T] in
+ * the plan's edge order (edge e = slot (b*M + m)*K + k = edge_slot[e]), with the T/4 16-byte pieces of edge e stored
+ * at piece position j ^ key(e), key(e) = (e / (8 / (T/4))) & (T/4 - 1) -- a tile's block is staged in shared memory
+ * by one bulk copy and read row-per-thread; the key spreads those reads over the banks.  Asynchronous on `stream`. */
 int fgnn_src_permute_etype(const float* etype, int64_t et_sb, const int32_t* edge_slot, float* out, int32_t T,
                            int32_t M, int32_t K, int64_t n_edges, void* stream);
+
+/* The scripts' edge model as ONE kernel: etype = Conv1x1(H -> T)(ReLU(Conv1x1(Fe -> H)(efeature))) with H = 64
+ * (reference train_ldpc.py:32-38,68-69; train_syn_hop_factor.py:174-179): the H-channel hidden tensor never reaches
+ * HBM.  efeature logical [B,Fe,M,K] (batch stride ef_sb elements, the rest contiguous), w1 [H,Fe], b1 [H] or NULL,
+ * w2 [T,H], b2 [T] or NULL.  edge_slot == NULL: out = etype [B,T,M,K] (batch stride out_sb).  edge_slot != NULL
+ * ([n_edges] slot of every edge of a source-stationary plan): out = the plan's edge-type image [n_edges, T], i.e.
+ * what fgnn_src_permute_etype would produce from the etype -- that pass is fused too.  Fe <= 8, T <= 16. */
+int fgnn_emodel_forward(const float* efeature, int64_t ef_sb, const float* w1, const float* b1, const float* w2,
+                        const float* b2, float* out, int64_t out_sb, const int32_t* edge_slot, int64_t n_edges,
+                        int32_t B, int32_t Fe, int32_t H, int32_t T, int32_t M, int32_t K, void* stream);
 
 /* Index validation the reference gets for free from ATen's gather (mp_nn.py:111): returns
  * FGNN_ERR_INDEX_RANGE if any entry of idx[count] is outside [lo, N).  Synchronises `stream`.

@@ -204,6 +204,35 @@ def test_ldpc_factornn_hard_decisions_bit_exact():
     assert np.array_equal((res >= 0).cpu().numpy(), g["hard"])
 
 
+@pytest.mark.parametrize("fe,T,M,K,B", [(7, 4, 96, 3, 5), (7, 4, 48, 6, 5), (3, 16, 60, 2, 4), (2, 16, 1000, 9, 1), (1, 16, 128, 4, 1)])
+def test_fused_edge_model_matches_torch_sequential(fe, T, M, K, B):
+    """`emodel_forward` (one kernel, hidden vector in registers) == the scripts' Sequential(Conv2d(Fe,64,1), ReLU,
+    Conv2d(64,T,1)) (train_ldpc.py:32-38, train_syn_hop_factor.py:174-179); with a plan it also leaves the plan's
+    edge-type image, bit-identical to fgnn_src_permute_etype of its own output."""
+    torch.manual_seed(fe * 100 + T)
+    em = torch.nn.Sequential(torch.nn.Conv2d(fe, 64, 1), torch.nn.ReLU(inplace=True), torch.nn.Conv2d(64, T, 1)).to(DEV).eval()
+    ef = torch.randn(B, fe, M, K, device=DEV)
+    with torch.no_grad():
+        want = em(ef.clone())
+    idx = torch.randint(0, 37, (B, M, K), device=DEV)
+    plan = fgnn_b200.SourcePlan(idx, 37) if T % 4 == 0 else None
+    got = fgnn_b200.emodel_forward(em, ef, plan=plan)
+    assert_close(got.cpu().numpy(), want.cpu().numpy(), 1e-5, "fused edge model")
+    if plan is not None:
+        img = plan._et[3].clone()
+        plan._et = None
+        ref_img = plan.etype_edges(got, got.stride(0) if B > 1 else T * M * K)
+        assert torch.equal(img, ref_img)
+
+
+def test_fused_edge_model_cfg1_golden():
+    g = load_npz("cfg1_simple_gnn.npz")
+    emodel = torch.nn.Sequential(torch.nn.Conv2d(1, 64, 1), torch.nn.ReLU(inplace=True), torch.nn.Conv2d(64, 16, 1))
+    emodel.load_state_dict({k: torch.from_numpy(v) for k, v in sub_sd(g, "emodel").items()})
+    got = fgnn_b200.emodel_forward(emodel.to(DEV).eval(), t(g["efeature"]))
+    assert_close(got.cpu().numpy(), g["etype"], 1e-5, "cfg1 etype")
+
+
 def test_factor_mpnn_merged_tables_labels_bit_exact():
     """The merged-table model of train_syn_hop_factor.py / train_syn_pw_factor.py (factor_mpnn.py:88-133): golden from
     the real reference.  Its ORIG_WITH_DIFF residual cores (C = 64) run on the tensor-core kernel."""
