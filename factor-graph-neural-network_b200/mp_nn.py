@@ -9,9 +9,9 @@ marshals raw device pointers and the current CUDA stream into ONE C-ABI call
 permute -> mm -> repeat -> gather -> bmm -> max -> bias -> BN -> ReLU.
 
 There is no CPU or PyTorch fallback: a CPU tensor, a missing library or a failing call raises.
-Autograd and train-mode BatchNorm statistics are not part of this boundary:
-forward under `torch.no_grad()` / `.eval()` is the contract; train-mode BN is served by running
-the kernel up to the bias add and handing the result to the module's own `bn`.
+Training: in train mode with gradients enabled the aggregate runs on the same kernel inside
+`_MpCore` (an autograd.Function whose backward is csrc/backward.cu + three plain GEMMs) and bias / batch-statistics
+BatchNorm / activation are PyTorch ops, so the scripts' `loss.backward()` works on installed modules.
 """
 import ctypes
 import os
@@ -432,6 +432,83 @@ def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=Non
     return out
 
 
+class _MpCore(torch.autograd.Function):
+    """The aggregate y = AGG_k sum_t etype * (xin . filters) (no bias / BN / activation) with a native backward
+    (csrc/backward.cu + three plain GEMMs): gradients for x, etype and filters.  Forward = the same sm_100a kernel as
+    inference.  Destinations are processed in chunks so the O*T-wide intermediates stay below `CHUNK_BYTES`."""
+    CHUNK_BYTES = 256 << 20
+
+    @staticmethod
+    def forward(ctx, x, etype, filters, nn_idx, ext, agg, gamma, kernel):
+        with torch.no_grad():
+            y = mp_forward(x, nn_idx, etype, filters, None, None, None, extension=ext, aggregator=agg,
+                           activation=_lib.ACT_NONE, gamma=gamma, kernel=kernel)
+        ctx.save_for_backward(x, etype, filters, nn_idx)
+        ctx.opts = (ext, agg, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, etype, filters, nn_idx = ctx.saved_tensors
+        ext, agg, gamma = ctx.opts
+        lib = _lib.lib()
+        dev = x.device
+        x3 = (x[..., 0] if x.dim() == 4 else x).detach().float()
+        B, C, N = x3.shape
+        _, M, K = nn_idx.shape
+        T = etype.shape[1]
+        W = filters.detach().float().contiguous()
+        Cin, OT = W.shape
+        O = OT // T
+        idx = nn_idx if nn_idx.dtype in (torch.int64, torch.int32) else nn_idx.long()
+        if idx.stride(2) != 1 or idx.stride(1) != K or (B > 1 and idx.stride(0) not in (0, M * K)):
+            idx = idx.contiguous()
+        et = etype.detach().float()
+        if et.stride(3) != 1 or et.stride(2) != K or et.stride(1) != M * K:
+            et = et.contiguous()
+        g = g.detach().float()
+        a = _lib.MpArgs()
+        a.x, a.idx, a.etype, a.filters, a.out = x3.data_ptr(), idx.data_ptr(), et.data_ptr(), W.data_ptr(), g.data_ptr()
+        a.x_sb, a.x_sc, a.x_sn = x3.stride(0), x3.stride(1), x3.stride(2)
+        a.idx_sb = idx.stride(0) if B > 1 else M * K
+        a.et_sb = et.stride(0) if B > 1 else T * M * K
+        a.B, a.N, a.M, a.K, a.C, a.O, a.T = B, N, M, K, C, O, T
+        a.extension, a.aggregator, a.activation = int(ext), int(agg), _lib.ACT_NONE
+        a.dtype, a.idx_dtype, a.gamma = _lib.F32, (_lib.I64 if idx.dtype == torch.int64 else _lib.I32), float(gamma)
+        need_x, need_et, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        dx = torch.zeros((B, N, C), dtype=torch.float32, device=dev) if need_x else None
+        d_et = torch.empty((B, T, M, K), dtype=torch.float32, device=dev) if need_et else None
+        dW = torch.zeros_like(W) if need_w else None
+        mc = max(1, min(M, int(_MpCore.CHUNK_BYTES // max(1, 4 * B * K * OT))))
+        gk = g.stride(3) if g.dim() == 4 else 0
+        with torch.cuda.device(dev):
+            st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            for m0 in range(0, M, mc):
+                m1 = min(M, m0 + mc)
+                S = B * (m1 - m0) * K
+                xin = torch.empty((S, Cin), dtype=torch.float32, device=dev)
+                _lib.check(lib.fgnn_bwd_gather(ctypes.byref(a), _ptr(xin), m0, m1 - m0, st), "bwd_gather")
+                H = xin @ W                                                       # [S, O*T]
+                e = torch.empty((S, O), dtype=torch.float32, device=dev)
+                _lib.check(lib.fgnn_bwd_slot_values(ctypes.byref(a), _ptr(H), _ptr(e), m0, m1 - m0, st), "bwd_slot_values")
+                ge = torch.empty((S, O), dtype=torch.float32, device=dev)
+                _lib.check(lib.fgnn_bwd_aggregate(ctypes.byref(a), _ptr(e), _ptr(g), g.stride(0), g.stride(1), g.stride(2), gk,
+                                                  _ptr(ge), m0, m1 - m0, st), "bwd_aggregate")
+                _lib.check(lib.fgnn_bwd_outer(ctypes.byref(a), _ptr(H), _ptr(ge), _ptr(d_et), T * M * K, m0, m1 - m0, st),
+                           "bwd_outer")                                            # H now holds Z
+                if need_w:
+                    dW.addmm_(xin.t(), H)
+                if need_x:
+                    dxin = H @ W.t()
+                    _lib.check(lib.fgnn_bwd_scatter(ctypes.byref(a), _ptr(dxin), _ptr(dx), m0, m1 - m0, st), "bwd_scatter")
+        gx = None
+        if need_x:
+            gx = dx.permute(0, 2, 1)
+            gx = gx.unsqueeze(-1) if x.dim() == 4 else gx
+            gx = gx.to(x.dtype)
+        return gx, (d_et.to(etype.dtype) if need_et else None), (dW.to(filters.dtype) if need_w else None), None, None, None, None, None
+
+
 def emodel_forward(emodel, efeature, plan=None):
     """The scripts' edge model `Sequential(Conv2d(Fe, 64, 1), ReLU, Conv2d(64, T, 1))` (train_ldpc.py:32-38;
     train_syn_hop_factor.py:174-179) as ONE kernel (`fgnn_emodel_forward`): the 64-channel hidden tensor never reaches
@@ -558,11 +635,11 @@ class mp_conv_v2(base_mp_nn):
         aggregtor = self.aggregtor                        # AttributeError for an unknown string
         if self.training and torch.is_grad_enabled() and (
                 self.filters.requires_grad or x.requires_grad or etype.requires_grad):
-            # eval-mode forwards (the scripts' test phases call model.eval() without no_grad, e.g.
-            # train_syn_fixed_pw_hop.py:313) just return a tensor outside the autograd graph
-            raise NotImplementedError(
-                "fgnn_b200.mp_conv_v2 is forward-only (autograd is outside this boundary, SURVEY 8b/8f): "
-                "call .eval() or torch.no_grad(), or use the reference module for training")
+            # training (train_ldpc.py:222-231: loss.backward()): the aggregate runs on the same kernel inside an
+            # autograd.Function with a native backward; bias / batch-statistics BatchNorm / activation are PyTorch ops.
+            # Eval-mode forwards (the scripts' test phases call model.eval() without no_grad, e.g.
+            # train_syn_fixed_pw_hop.py:313) take the fused path below and return a tensor outside the graph.
+            return self._forward_train(x, nn_idx, etype, aggregtor)
         # `install()` leaves the REFERENCE package's enum on .extension (its own isinstance checks see it): any Enum
         # or plain int is accepted here
         ext = int(getattr(self.extension, "value", self.extension))
@@ -595,6 +672,20 @@ class mp_conv_v2(base_mp_nn):
         if self.activation_fn is not None:
             out = self.activation_fn(out)
         return out
+
+    def _forward_train(self, x, nn_idx, etype, aggregtor):
+        ext = int(getattr(self.extension, "value", self.extension))
+        agg = self._agg if self._agg is not None else _lib.AGG_NONE
+        y = _MpCore.apply(x, etype, self.filters, nn_idx, ext, agg, _SOFTMAX_GAMMA, self.kernel)
+        if self._agg is None and aggregtor is not None:
+            y = aggregtor(y)                                  # user callable on [B,O,M,K] (mp_nn.py:162-163)
+        if self.bias is not None:
+            y = y + self.bias.view(1, self.nou, 1, 1)         # mp_nn.py:165-168
+        if self.bn is not None:
+            y = self.bn(y)                                    # mp_nn.py:169-170 (batch statistics in train mode)
+        if self.activation_fn is not None:
+            y = self.activation_fn(y)                         # mp_nn.py:172-173
+        return y
 
     # fan-out (edges per source row) from which the source-stationary path is chosen automatically, by
     # edge-type count (measured on B200, DESIGN.md 6: it pays at T = 16, where the destination-stationary

@@ -182,6 +182,25 @@ int fgnn_emodel_forward(const float* efeature, int64_t ef_sb, const float* w1, c
                         const float* b2, float* out, int64_t out_sb, const int32_t* edge_slot, int64_t n_edges,
                         int32_t B, int32_t Fe, int32_t H, int32_t T, int32_t M, int32_t K, void* stream);
 
+/* ---- backward of the call (training; reference train_ldpc.py:222-231 relies on ATen autograd) ---------------------
+ * With g = dL/dy, a = dAGG/de (one-hot at the first arg-max slot | softmax_k(gamma e) | 1/K), ge = g * a:
+ *     Z[(b,m,k), o*T+t] = ge[.,o] * etype[b,t,m,k]     dXin = Z W^T     dW = Xin^T Z     H = Xin W
+ *     d etype[b,t,m,k] = sum_o ge[.,o] * H[., o*T+t]    dx = scatter-add of dXin through nn_idx (+ the self part)
+ * The three dense products are plain GEMMs run by the caller (mp_nn.py: torch.matmul = cuBLAS); these entry points
+ * are the graph-structured pieces, each over the destination rows m0 .. m0+mc-1 of every batch element (slot order
+ * (b, m - m0, k)), so the O*T-wide intermediates stay bounded.  `a` describes the forward call (x, idx, etype, strides,
+ * shapes, extension, aggregator, gamma, flags); fp32 only.  All asynchronous on `stream`. */
+int fgnn_bwd_gather(const fgnn_mp_args* a, float* xin /* [B*mc*K, C or 2C] */, int32_t m0, int32_t mc, void* stream);
+int fgnn_bwd_slot_values(const fgnn_mp_args* a, const float* H /* [B*mc*K, O*T] */, float* e /* [B*mc*K, O] */, int32_t m0,
+                         int32_t mc, void* stream);
+int fgnn_bwd_aggregate(const fgnn_mp_args* a, const float* e, const float* grad_out, int64_t g_sb, int64_t g_so, int64_t g_sm,
+                       int64_t g_sk, float* ge /* [B*mc*K, O] */, int32_t m0, int32_t mc, void* stream);
+/* d_etype (reference layout [B,T,M,K], batch stride det_sb; may be NULL) from H, then H <- Z in place */
+int fgnn_bwd_outer(const fgnn_mp_args* a, float* H_inout, const float* ge, float* d_etype, int64_t det_sb, int32_t m0, int32_t mc,
+                   void* stream);
+/* dx [B,N,C] node-major, zero-initialised by the caller, += dXin [B*mc*K, C or 2C] (atomic adds) */
+int fgnn_bwd_scatter(const fgnn_mp_args* a, const float* dxin, float* dx, int32_t m0, int32_t mc, void* stream);
+
 /* Index validation the reference gets for free from ATen's gather (mp_nn.py:111): returns
  * FGNN_ERR_INDEX_RANGE if any entry of idx[count] is outside [lo, N).  Synchronises `stream`.
  * `scratch` = 8 bytes of device memory. */

@@ -233,6 +233,70 @@ def test_fused_edge_model_cfg1_golden():
     assert_close(got.cpu().numpy(), g["etype"], 1e-5, "cfg1 etype")
 
 
+@pytest.mark.parametrize("ext", [0, 1, 2])
+@pytest.mark.parametrize("agg", ["max", "softmax", "mean", None])
+def test_training_step_gradients_match_aten_autograd(ext, agg):
+    """Train mode (train_ldpc.py:222-231 calls loss.backward()): forward with batch-statistics
+    BatchNorm and the native backward (csrc/backward.cu + three GEMMs) against ATen's autograd through the reference's
+    own op chain (oracle/fgnn_oracle_torch.py) on the same device: output, d x, d etype, d filters, d bias, d BN."""
+    from oracle import fgnn_oracle_torch as orct
+    torch.manual_seed(10 * ext + len(str(agg)))
+    B, C, O, T, N, K = 3, 64, 64, 4, 50, 3
+    M = N if ext else 70
+    mod = fgnn_b200.mp_conv_v2(C, O, T, extension=fgnn_b200.mp_conv_type(ext), aggregtor=agg).to(DEV).train()
+    with torch.no_grad():
+        mod.filters.uniform_(-0.2, 0.2)
+    x = torch.randn(B, C, N, 1, device=DEV, requires_grad=True)
+    et = torch.randn(B, T, M, K, device=DEV, requires_grad=True)
+    idx = torch.randint(0, N, (B, M, K), device=DEV)
+    probe = torch.randn(B, O, M, K if agg is None else 1, device=DEV)
+    before = fgnn_b200.launch_count()
+    y = mod(x, idx, et)
+    (y * probe).sum().backward()
+    assert fgnn_b200.launch_count() >= before + 6            # forward kernel + the five backward kernels
+    got = [y.detach(), x.grad.clone(), et.grad.clone(), mod.filters.grad.clone(), mod.bias.grad.clone(), mod.bn.weight.grad.clone()]
+    rm, rv = mod.bn.running_mean.clone(), mod.bn.running_var.clone()
+    # reference op chain under ATen autograd, same parameters, fresh BatchNorm in train mode
+    x2, et2 = x.detach().clone().requires_grad_(True), et.detach().clone().requires_grad_(True)
+    W2, b2 = mod.filters.detach().clone().requires_grad_(True), mod.bias.detach().clone().requires_grad_(True)
+    bn2 = torch.nn.BatchNorm2d(O).to(DEV).train()
+    pre = orct.mp_conv_forward_torch(x2, idx, et2, W2, b2, None, extension=ext, aggregator=agg, activation=None)
+    y2 = torch.relu(bn2(pre))
+    (y2 * probe).sum().backward()
+    want = [y2.detach(), x2.grad, et2.grad, W2.grad, b2.grad, bn2.weight.grad]
+    for name, a, b in zip(["y", "dx", "d_etype", "d_filters", "d_bias", "d_bn_weight"], got, want):
+        if name == "d_bias":          # batch-statistics BN removes the mean: the bias gradient is zero up to round-off
+            assert float(a.abs().max()) < 1e-4 and float(b.abs().max()) < 1e-4
+            continue
+        assert_close(a.cpu().numpy(), b.cpu().numpy(), 2e-4, f"ext {ext} agg {agg}: {name}")
+    assert torch.allclose(rm, bn2.running_mean, rtol=1e-4, atol=1e-6) and torch.allclose(rv, bn2.running_var, rtol=1e-4, atol=1e-6)
+
+
+def test_training_step_through_factornn_and_residual_wrappers():
+    """loss.backward() through FactorNN (mp_conv_residual cores, InstanceNorm maps) in train mode: every parameter gets
+    a finite gradient and one SGD step lowers the loss (the scripts' training loops run on the native core)."""
+    torch.manual_seed(5)
+    g = load_npz("cfg1_factornn.npz")
+    model = fgnn_b200.FactorNN(2, [4], [64, 64, 64], [16], 2).to(DEV).train()      # two layers: the V->F modules of the first feed the output
+    B = g["node"].shape[0]
+    args = (t(g["node"]), [t(g["hop"])], [t(g["idx_f2v"]).repeat(B, 1, 1)], [t(g["idx_v2f"]).repeat(B, 1, 1)],
+            [t(g["et_f2v"])], [t(g["et_v2f"])])
+    target = (torch.rand(B, 1, 128, 1, device=DEV) > 0.5).float()
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(model(*args), target)
+        loss.backward()
+        for n_, p_ in model.named_parameters():
+            if n_.startswith(("v2f_1_", "f2f_1_")):          # the last layer's factor features are not read by the classifier
+                continue
+            assert p_.grad is not None and torch.isfinite(p_.grad).all(), n_
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert losses[-1] < losses[0]
+
+
 def test_factor_mpnn_merged_tables_labels_bit_exact():
     """The merged-table model of train_syn_hop_factor.py / train_syn_pw_factor.py (factor_mpnn.py:88-133): golden from
     the real reference.  Its ORIG_WITH_DIFF residual cores (C = 64) run on the tensor-core kernel."""

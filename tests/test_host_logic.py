@@ -51,9 +51,10 @@ def test_cpu_tensor_has_no_fallback():
         m(torch.zeros(1, 4, 3, 1), torch.zeros(1, 3, 2, dtype=torch.long), torch.zeros(1, 2, 3, 2))
 
 
-def test_training_forward_is_refused():
+def test_training_forward_needs_cuda_too():
+    """Train mode goes through the autograd.Function around the same kernel: still no CPU fallback."""
     m = fgnn_b200.mp_conv_v2(4, 8, 2).train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(1, 4, 3, 1), torch.zeros(1, 3, 2, dtype=torch.long), torch.zeros(1, 2, 3, 2))
 
 
