@@ -69,9 +69,13 @@ def parse_args():
                     help="which core calls run source-stationary (one row-product per source row, csrc/mp_src.cu): "
                          "'auto' (fan-out rule of mp_conv_v2), 'none', or a comma list of v2f<j>/f2v<j> (j = factor type)")
     ap.add_argument("--cpu-sample-scale", type=int, default=2, help="cpu_baseline runs on 1/scale of the graph")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="multi-GPU: the cross-GPU step as one kernel over NVLink peer memory (csrc/exchange.cu), or "
-                         "NCCL all_reduce(MAX) + epilogue kernel")
+    ap.add_argument("--exchange", default="halo", choices=["halo", "peer", "nccl"],
+                    help="multi-GPU: 'halo' = owner-computes sharding, one NVLink peer-memory kernel pulls the feature halos "
+                         "per layer (parallel.HaloLayerPlan); 'peer' = factor sharding + fused max-reduce/epilogue/broadcast "
+                         "kernel over peer memory; 'nccl' = factor sharding + NCCL all_reduce(MAX) + epilogue kernel")
+    ap.add_argument("--order", default="locality", choices=["locality", "none"],
+                    help="factor numbering before sharding: 'locality' sorts every type's factors by their smallest variable "
+                         "(graphs.locality_order) so contiguous shards cut few edges when the graph has index locality")
     ap.add_argument("--concurrent-layer", action="store_true",
                     help="single GPU: issue the V->F calls of a layer on their own streams beside the F->V chain "
                          "(measured: +2 %% at T=4, nothing at T=16 -- programmatic launch already hides the hand-over)")
@@ -114,8 +118,11 @@ def build_graph(args, scale=1):
         # (lib/data/ldpc_dataset.py:92-106); the tables travel in the committed golden fixture
         z = np.load(os.path.join(ROOT, "tests", "golden", "ldpc_factornn.npz"))
         return [graphs.FactorType(z["idx_v2f"], z["idx_f2v"], np.zeros(z["idx_f2v"].shape, bool), "ldpc-checks")]
-    return graphs.synthetic_map_graph(args.vars // scale, args.pairwise // scale, args.high // scale,
-                                      args.high_order, seed=args.seed, local_band=args.local_band)
+    types = graphs.synthetic_map_graph(args.vars // scale, args.pairwise // scale, args.high // scale,
+                                       args.high_order, seed=args.seed, local_band=args.local_band)
+    if args.order == "locality" and args.local_band:
+        types = graphs.locality_order(types)
+    return types
 
 
 def layer_weights(args, n_types, rng):
@@ -469,22 +476,30 @@ def run_native(args):
         for j in range(J):
             ws[l][j]["ver_v2f"], ws[l][j]["ver_f2v"] = 1 + l * 16 + j * 2, 2 + l * 16 + j * 2
     bf16 = args.dtype == "bf16"
-    if bf16 and world > 1:
-        raise RuntimeError("bench.py: --dtype bf16 is a single-GPU measurement in this round (the sharded layer is fp32)")
     fdev = (lambda a: to_dev(a).to(torch.bfloat16)) if bf16 else to_dev
     d_in = dict(x_v=fdev(inp["x_v"]), x_f=[fdev(a) for a in inp["x_f"]],
                 et_v2f=[fdev(a) for a in inp["et_v2f"]], et_f2v=[fdev(a) for a in inp["et_f2v"]],
                 idx_v2f=[to_dev(a).expand(B_loc, -1, -1) for a in inp["idx_v2f"]],
                 idx_f2v=[to_dev(a).expand(B_loc, -1, -1) for a in inp["idx_f2v"]])
-    if world > 1 and not batch_sharded:
+    plan = halo = None
+    if world > 1 and not batch_sharded and args.exchange == "halo":
+        # owner-computes sharding: this rank keeps its variables, its factors, the renumbered tables, their edge types
+        from fgnn_b200 import parallel
+        halo = parallel.HaloLayerPlan(types, rank, world, dev, torch.bfloat16 if args.dtype == "bf16" else torch.float32, C,
+                                      ctas=args.exchange_ctas)
+        halo.connect_distributed()
+        d_in["et_v2f"], d_in["et_f2v"] = halo.local_etypes(d_in["et_v2f"], d_in["et_f2v"])
+        d_in["idx_v2f"], d_in["idx_f2v"] = halo.idx_v2f, halo.idx_f2v
+        torch.cuda.empty_cache()
+    elif world > 1 and not batch_sharded:
         # factor-sharded: this rank keeps its factor ranges, the compacted F->V tables and their edge types
+        if args.dtype == "bf16":
+            raise RuntimeError("bench.py: --dtype bf16 on several GPUs needs --exchange halo (the raw-aggregate exchanges are fp32)")
         from fgnn_b200 import parallel
         plan = parallel.ShardedLayerPlan(types, rank, world, dev, exchange=args.exchange, exchange_ctas=args.exchange_ctas)
         d_in["x_f"] = plan.local_factor_features(d_in["x_f"])
         d_in["et_v2f"], d_in["et_f2v"] = plan.local_etypes(d_in["et_v2f"], d_in["et_f2v"])
         d_in["idx_v2f"] = d_in["idx_f2v"] = None
-    else:
-        plan = None
     # ping-pong feature buffers, node-major
     buf_v = [torch.empty_like(d_in["x_v"]) for _ in range(2)]
     buf_f = [[torch.empty_like(x) for x in d_in["x_f"]] for _ in range(2)]
@@ -495,7 +510,10 @@ def run_native(args):
     if plan is None and args.src_calls != "none" and kernel != _lib.KERNEL_SIMT and C == 64 and args.edge_types in (4, 8, 16) and not bf16:
         rule = fgnn_b200.mp_conv_v2.AUTO_FAN_OUT[args.edge_types]
         for j, ty in enumerate(types):
-            for name, idx, n_src in (("v2f%d" % j, d_in["idx_v2f"][j], ty.n_vars), ("f2v%d" % j, d_in["idx_f2v"][j], ty.n_factors)):
+            n_v, n_f = (ty.n_vars, ty.n_factors) if halo is None else (halo.rows_v, halo.rows_f[j])
+            for name, idx, n_src in (("v2f%d" % j, d_in["idx_v2f"][j], n_v), ("f2v%d" % j, d_in["idx_f2v"][j], n_f)):
+                if idx.numel() == 0:
+                    continue
                 fan = idx.numel() / (n_src * B_loc)
                 if (args.src_calls == "auto" and fan >= rule) or name in args.src_calls.split(","):
                     sp = fgnn_b200.SourcePlan(idx, n_src)
@@ -513,6 +531,11 @@ def run_native(args):
     def step(src):
         """src: dict of device tensors (x_v, x_f, tables).  Returns the final variable features."""
         x_v, x_f = src["x_v"], src["x_f"]
+        if halo is not None:
+            halo.load_features(src["x_v"], src["x_f"])       # own + halo rows of the step's input features (local gather)
+            for l in range(L):
+                out = halo.layer(l, src["et_v2f"], src["et_f2v"], W[l], kernel, ws[l], last=(l == L - 1), plans=plans)
+            return out
         if peer_xv is not None:
             # the variable features live in the peer-mapped arena: layer l reads buffer l & 1 and the fused
             # exchange kernel leaves the new features in buffer (l + 1) & 1 on every rank
@@ -567,7 +590,7 @@ def run_native(args):
         final = step(d_in)
     barrier()
     checksum = checksum_of(final)
-    if batch_sharded:                            # every rank holds its own codewords: the job's fingerprint is the sum
+    if batch_sharded or halo is not None:        # every rank holds its own codewords / variables: the job's fingerprint is the sum
         cs = torch.tensor([checksum], dtype=torch.int64, device=dev)
         dist.all_reduce(cs)
         checksum = int(cs.item())
@@ -771,6 +794,9 @@ def run_native(args):
     n_calls = 2 * J * L
     if batch_sharded:
         par = "batch-sharded x%d: every rank runs its own codewords, no collective (replicas)" % world
+    elif halo is not None:
+        par = ("owner-computes sharding x%d (contiguous variable / factor ranges%s) + one NVLink peer-memory halo pull per layer"
+               % (world, ", factors ordered by smallest variable" if (args.order == "locality" and args.local_band) else ""))
     elif world > 1:
         par = "factor-sharded x%d + %s per layer" % (world, "fused max-reduce/epilogue/broadcast kernel over NVLink peer memory"
                                                       if args.exchange == "peer" else "NCCL max-all-reduce")
@@ -811,8 +837,10 @@ def run_native(args):
     if sustained is not None:
         sustained["roofline_frac"] = bytes_layer * L / (sustained["ms_per_step"] * 1e-3) / 1e9 / world / peak
         line["sustained"] = sustained
-    if plan is not None and getattr(plan, "exchange_stats", None):
-        line["exchange"] = plan.exchange_stats
+    if halo is not None:
+        line["exchange"] = {"kind": "halo pull", "halo_bytes_per_layer_rank0": int(halo.halo_bytes_per_layer),
+                            "halo_rows_rank0": {"variables": int(len(halo.var_halo)), "factors": [int(len(h)) for h in halo.fac_halo]},
+                            "owned_rows_rank0": {"variables": int(halo.n_own_v), "factors": [int(n) for n in halo.n_own_f]}}
     if e2e is not None:
         line["e2e"] = e2e
     if world == 1 and not args.no_aten_baseline and not bf16:

@@ -62,6 +62,19 @@ class ExchangeArgs(ctypes.Structure):
     ]
 
 
+class HaloJob(ctypes.Structure):
+    """struct fgnn_halo_job"""
+    _fields_ = [("src", ctypes.c_void_p * 8), ("dst", ctypes.c_void_p), ("src_row", ctypes.c_void_p), ("src_rank", ctypes.c_void_p),
+                ("dst_row0", ctypes.c_int64), ("n", ctypes.c_int32), ("row_bytes", ctypes.c_int32)]
+
+
+class HaloArgs(ctypes.Structure):
+    """struct fgnn_halo_args"""
+    _fields_ = [("jobs", HaloJob * 4), ("flags", ctypes.c_void_p * 8), ("counter", ctypes.c_void_p),
+                ("n_jobs", ctypes.c_int32), ("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("epoch", ctypes.c_uint32),
+                ("ctas", ctypes.c_int32), ("reserved_", ctypes.c_int32)]
+
+
 EXPORTS = {
     "fgnn_version": (ctypes.c_int, []),
     "fgnn_strerror": (ctypes.c_char_p, [ctypes.c_int]),
@@ -111,6 +124,7 @@ EXPORTS = {
     "fgnn_comm_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
     "fgnn_comm_close": (ctypes.c_int, [ctypes.c_void_p]),
     "fgnn_comm_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "fgnn_halo_pull": (ctypes.c_int, [ctypes.POINTER(HaloArgs), ctypes.c_void_p]),
     "fgnn_exchange_forward": (ctypes.c_int, [ctypes.POINTER(ExchangeArgs), ctypes.c_void_p]),
     "fgnn_launch_count": (ctypes.c_uint64, []),
     "fgnn_set_programmatic_launch": (ctypes.c_int, [ctypes.c_int]),

@@ -190,6 +190,88 @@ exchange_kernel(const ExParams p) {
   wait_all(p, 1, epoch);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Feature-halo pull for the owner-computes sharding (parallel.py: HaloLayerPlan).  Every rank owns a contiguous
+// range of variables and of each type's factors and evaluates ALL slots of its own destinations (same kernel, same
+// slot order as the single-GPU layer: bit-identical rows); what it lacks are the features of the source rows other
+// ranks own -- its HALO.  After a layer's calls have written the owned rows of the next-layer buffers, this kernel
+// copies every halo row straight out of its owner's buffer over NVLink (16-byte loads, all of a thread's loads in
+// flight before the first store), for up to kMaxJobs buffers (variables + factor types) in one launch.
+// Epoch flags as above: A = "my owned rows are written" (stream order: the producers precede this launch),
+// B = "I have copied everything I need": when the kernel completes on a rank nobody still reads its buffers.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxJobs = 4;
+
+struct HaloJob {
+  const uint8_t* src[kMaxRanks];     // per rank: base of that rank's buffer (owned rows first)
+  uint8_t* dst;                      // this rank's buffer
+  const int32_t* src_row;            // [n] row in the owner's buffer
+  const uint8_t* src_rank;           // [n] owner
+  int64_t dst_row0;                  // first halo row of this rank's buffer
+  int32_t n;                         // halo rows
+  int32_t row_bytes;                 // multiple of 16
+};
+
+struct HaloParams {
+  HaloJob job[kMaxJobs];
+  uint32_t* flags[kMaxRanks];
+  unsigned long long* counter;
+  int n_jobs, world, rank;
+  uint32_t epoch;
+};
+
+__global__ void __launch_bounds__(512, 2)
+halo_kernel(const HaloParams p) {
+  __shared__ uint32_t s_epoch;
+  if (threadIdx.x == 0)
+    s_epoch = p.epoch ? p.epoch : (uint32_t)(*reinterpret_cast<volatile unsigned long long*>(p.counter) / gridDim.x) + 1u;
+  __syncthreads();
+  const uint32_t epoch = s_epoch;
+  ExParams fl;                                         // wait_all only reads flags / rank / world
+  for (int q = 0; q < kMaxRanks; ++q) fl.flags[q] = p.flags[q];
+  fl.rank = p.rank; fl.world = p.world;
+  if (blockIdx.x == 0 && (int)threadIdx.x < p.world) st_release_sys(p.flags[threadIdx.x] + 0 * kMaxRanks + p.rank, epoch);
+  wait_all(fl, 0, epoch);
+  constexpr int U = 4;
+  for (int j = 0; j < p.n_jobs; ++j) {
+    const HaloJob& jb = p.job[j];
+    const int cpr = jb.row_bytes >> 4;                 // 16-byte chunks per row
+    const int64_t total = (int64_t)jb.n * cpr, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < total) {
+          const int64_t r = i / cpr;
+          const int c = (int)(i - r * cpr);
+          const uint8_t* src = jb.src[jb.src_rank[r]] + (int64_t)jb.src_row[r] * jb.row_bytes + c * 16;
+          v[u] = ld_peer_f4(reinterpret_cast<const float*>(src));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < total) {
+          const int64_t r = i / cpr;
+          const int c = (int)(i - r * cpr);
+          *reinterpret_cast<float4*>(jb.dst + (jb.dst_row0 + r) * jb.row_bytes + c * 16) = v[u];
+        }
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long done = atomicAdd(p.counter, 1ull) + 1ull;
+    if (done % gridDim.x == 0) {
+      __threadfence_system();
+      for (int q = 0; q < p.world; ++q) st_release_sys(p.flags[q] + 1 * kMaxRanks + p.rank, epoch);
+    }
+  }
+  wait_all(fl, 1, epoch);
+}
+
 template <int WORLD, int UNROLL, int kJ>
 cudaError_t launch_exchange(const ExParams& p, int ctas, cudaStream_t st) {
   exchange_kernel<WORLD, UNROLL, kJ><<<ctas, 512, 0, st>>>(p);
@@ -233,6 +315,33 @@ int fgnn_comm_close(void* dev_ptr) {
 }
 
 int fgnn_comm_free(void* dev_ptr) { return cudaFree(dev_ptr) == cudaSuccess ? FGNN_OK : FGNN_ERR_CUDA; }
+
+int fgnn_halo_pull(const fgnn_halo_args* a, void* stream_) {
+  if (!a || a->world < 1 || a->world > kMaxRanks || a->rank < 0 || a->rank >= a->world || a->n_jobs < 1 || a->n_jobs > kMaxJobs ||
+      !a->counter)
+    return FGNN_ERR_INVALID_ARG;
+  HaloParams p;
+  memset(&p, 0, sizeof(p));
+  for (int q = 0; q < a->world; ++q) {
+    if (!a->flags[q]) return FGNN_ERR_INVALID_ARG;
+    p.flags[q] = a->flags[q];
+  }
+  for (int j = 0; j < a->n_jobs; ++j) {
+    const fgnn_halo_job& s = a->jobs[j];
+    if (s.n < 0 || s.row_bytes <= 0 || (s.row_bytes & 15) || !s.dst || (s.n > 0 && (!s.src_row || !s.src_rank))) return FGNN_ERR_INVALID_ARG;
+    HaloJob& d = p.job[j];
+    for (int q = 0; q < a->world; ++q) d.src[q] = reinterpret_cast<const uint8_t*>(s.src[q]);
+    d.dst = reinterpret_cast<uint8_t*>(s.dst); d.src_row = s.src_row; d.src_rank = s.src_rank;
+    d.dst_row0 = s.dst_row0; d.n = s.n; d.row_bytes = s.row_bytes;
+  }
+  p.counter = reinterpret_cast<unsigned long long*>(a->counter);
+  p.n_jobs = a->n_jobs; p.world = a->world; p.rank = a->rank; p.epoch = a->epoch;
+  int ctas = a->ctas > 0 ? a->ctas : 32;
+  if (ctas > 128) ctas = 128;
+  halo_kernel<<<ctas, 512, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(p);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? (int)FGNN_OK : (int)FGNN_ERR_CUDA;
+}
 
 int fgnn_exchange_forward(const fgnn_exchange_args* a, void* stream_) {
   if (!a || a->world < 1 || a->world > kMaxRanks || a->rank < 0 || a->rank >= a->world) return FGNN_ERR_INVALID_ARG;

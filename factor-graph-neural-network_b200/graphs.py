@@ -97,6 +97,22 @@ def synthetic_map_graph(n_vars, n_pairwise, n_high, high_order, seed=0, local_ba
     return types
 
 
+def locality_order(types):
+    """Renumber the factors of every type by their smallest variable (stable), so that a contiguous range of factors
+    touches a (nearly) contiguous range of variables when the graph has index locality (banded / chain / kNN
+    graphs): the precondition for halo-sized exchanges under contiguous sharding.  The variable
+    numbering is kept.  Returns new FactorType objects (tables only; features / edge types generated afterwards
+    follow the new numbering)."""
+    out = []
+    for t in types:
+        order = np.argsort(t.idx_v2f.min(1), kind="stable")             # new factor i = old factor order[i]
+        inv = np.empty_like(order)
+        inv[order] = np.arange(order.size)
+        idx_f2v = np.where(t.pad_f2v, 0, inv[t.idx_f2v])                # pads keep pointing at a valid row (0)
+        out.append(FactorType(t.idx_v2f[order], idx_f2v, t.pad_f2v, t.name))
+    return out
+
+
 def chain_knn_table(n, k):
     """Chain-MRF neighbour table with the semantics of the reference's generate_knn_table
     (train_syn_fixed_pw_hop.py:86-101): node i lists its k//2 left neighbours i-k//2..i-1 and its

@@ -175,6 +175,217 @@ class PeerExchange:
                 self.base = 0
 
 
+def owner_of(ids, n, world):
+    """Rank owning each of `ids` under shard_range(n, ., world)."""
+    bounds = np.array([shard_range(n, q, world)[1] for q in range(world)], dtype=np.int64)
+    return np.searchsorted(bounds, np.asarray(ids, dtype=np.int64), side="right")
+
+
+class HaloLayerPlan:
+    """Owner-computes sharding with feature halos (halo-restricted exchange).
+
+    Rank r owns the variables shard_range(N, r, G) and, per type, the factors shard_range(F_j, r, G).  It evaluates
+    ALL slots of its own destinations -- the V->F call of its factors, the F->V calls of its variables -- with the
+    same kernel and the same slot order as the single-GPU layer, so every row is bit-identical to it.  The sources it
+    reads but does not own are its HALO: the feature buffers hold [owned rows | halo rows], the index tables are
+    renumbered into that local order, and after every layer one kernel (`fgnn_halo_pull`, csrc/exchange.cu) copies the
+    halo rows of the new features out of their owners' arenas over NVLink.  What crosses the links is therefore
+    bounded by the graph's cut: with a locality-preserving factor order (`graphs.locality_order`) a banded graph
+    exchanges a few hundred rows per layer; uniform-random incidence still needs most rows (reported as measured).
+
+    Layer l reads buffer set l & 1 and writes set (l + 1) & 1 (owned rows by the calls, halo rows by the pull).
+    """
+    HEADER = 256
+
+    def __init__(self, types, rank, world, device, dtype=torch.float32, C=64, ctas=32):
+        self.types, self.rank, self.world, self.device, self.dtype, self.C, self.ctas = types, rank, world, device, dtype, C, ctas
+        J = len(types)
+        N = types[0].n_vars
+        self.v0, self.v1 = shard_range(N, rank, world)
+        self.fr = [shard_range(t.n_factors, rank, world) for t in types]
+        n_own = self.v1 - self.v0
+        # ---- V->F: my factors read variables; halo = the variables outside my range
+        tv = [np.asarray(t.idx_v2f[f0:f1]) for t, (f0, f1) in zip(types, self.fr)]
+        outside = [a[(a < self.v0) | (a >= self.v1)] for a in tv]
+        self.var_halo = np.unique(np.concatenate(outside)) if outside else np.zeros(0, np.int64)
+
+        def to_local(a, lo, hi, halo, n_owned):
+            a = np.asarray(a, dtype=np.int64)
+            own = (a >= lo) & (a < hi)
+            return np.where(own, a - lo, n_owned + np.searchsorted(halo, a)).astype(np.int64)
+
+        self.idx_v2f = [torch.from_numpy(to_local(a, self.v0, self.v1, self.var_halo, n_own)[None]).to(device) for a in tv]
+        # ---- F->V: my variables read factors of every type; halo = the factors outside my range
+        self.fac_halo, self.idx_f2v = [], []
+        for t, (f0, f1) in zip(types, self.fr):
+            a = np.asarray(t.idx_f2v[self.v0:self.v1])
+            h = np.unique(a[(a < f0) | (a >= f1)])
+            self.fac_halo.append(h)
+            self.idx_f2v.append(torch.from_numpy(to_local(a, f0, f1, h, f1 - f0)[None]).to(device))
+        self.rows_v = n_own + len(self.var_halo)
+        self.rows_f = [(f1 - f0) + len(h) for (f0, f1), h in zip(self.fr, self.fac_halo)]
+        self.n_own_v, self.n_own_f = n_own, [f1 - f0 for f0, f1 in self.fr]
+        # halo sources: owner and row inside the owner's buffer (its owned rows come first)
+        def src_of(halo, n):
+            own = owner_of(halo, n, world)
+            starts = np.array([shard_range(n, q, world)[0] for q in range(world)], dtype=np.int64)
+            return (torch.from_numpy(own.astype(np.uint8)).to(device), torch.from_numpy((halo - starts[own]).astype(np.int32)).to(device))
+        self.src_v = src_of(self.var_halo, N)
+        self.src_f = [src_of(h, t.n_factors) for h, t in zip(self.fac_halo, types)]
+        # ---- arena: header | two sets of [xv, xf_0 .. xf_J-1]
+        esz = 2 if dtype == torch.bfloat16 else 4
+        self.row_bytes = C * esz
+        off, self.off_v, self.off_f = self.HEADER, [], []
+        for _ in range(2):
+            self.off_v.append(off)
+            off = self._align(off + self.rows_v * self.row_bytes)
+            fs = []
+            for r in self.rows_f:
+                fs.append(off)
+                off = self._align(off + max(r, 1) * self.row_bytes)
+            self.off_f.append(fs)
+        self.nbytes = off
+        lib = _lib.lib()
+        ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        with torch.cuda.device(device):
+            _lib.check(lib.fgnn_comm_alloc(self.nbytes, ctypes.byref(ptr), handle), "comm_alloc")
+        self.base, self.handle = ptr.value, bytes(handle.raw)
+        self._opened = []
+        mem = torch.as_tensor(_DevMem(self.base, self.nbytes), device=device)
+        self._mem = mem
+        view = lambda o, rows: mem[o:o + rows * self.row_bytes].view(dtype).view(1, rows, C)
+        self.xv = [view(self.off_v[p], self.rows_v) for p in range(2)]
+        self.xf = [[view(self.off_f[p][j], self.rows_f[j]) for j in range(J)] for p in range(2)]
+        self.peers = None                                     # per rank: (base, off_v, off_f), see connect()
+        self._side = torch.cuda.Stream(device=device)
+        self._halo_v_dev = torch.from_numpy(self.var_halo).to(device)
+        self._halo_f_dev = [torch.from_numpy(h).to(device) for h in self.fac_halo]
+        self.n_sms = torch.cuda.get_device_properties(device).multi_processor_count
+        self.halo_bytes_per_layer = (len(self.var_halo) + sum(len(h) for h in self.fac_halo)) * self.row_bytes
+        self.exchange_stats = None
+
+    @staticmethod
+    def _align(n):
+        return (n + 255) // 256 * 256
+
+    def info(self):
+        """What the other ranks need to address this rank's arena."""
+        return {"handle": self.handle, "base": self.base, "off_v": self.off_v, "off_f": self.off_f}
+
+    def connect(self, infos, same_process=False):
+        """infos[q] = info() of rank q (all_gather_object across processes; passed directly when the ranks live in one
+        process, e.g. the single-device tests)."""
+        lib = _lib.lib()
+        self.peers = []
+        for q, inf in enumerate(infos):
+            if q == self.rank or same_process:
+                base = self.base if q == self.rank else inf["base"]
+            else:
+                pp = ctypes.c_void_p()
+                with torch.cuda.device(self.device):
+                    _lib.check(lib.fgnn_comm_open(inf["handle"], ctypes.byref(pp)), "comm_open")
+                base = pp.value
+                self._opened.append(base)
+            self.peers.append((base, inf["off_v"], inf["off_f"]))
+
+    def connect_distributed(self, group=None):
+        infos = [None] * self.world
+        torch.distributed.all_gather_object(infos, self.info(), group=group)
+        self.connect(infos)
+
+    # -- inputs ------------------------------------------------------------------------------
+    def load_features(self, x_v_full, x_f_full):
+        """Fill buffer set 0 from full (replicated) feature arrays [1,N,C] / [1,F_j,C]: owned rows, then halo rows."""
+        dev = self.device
+        self.xv[0][:, :self.n_own_v].copy_(x_v_full[:, self.v0:self.v1])
+        if len(self.var_halo):
+            torch.index_select(x_v_full, 1, self._halo_v_dev, out=self.xv[0][:, self.n_own_v:])
+        for j, (f0, f1) in enumerate(self.fr):
+            self.xf[0][j][:, :self.n_own_f[j]].copy_(x_f_full[j][:, f0:f1])
+            if len(self.fac_halo[j]):
+                torch.index_select(x_f_full[j], 1, self._halo_f_dev[j], out=self.xf[0][j][:, self.n_own_f[j]:])
+
+    def local_etypes(self, et_v2f_full, et_f2v_full):
+        ev = [e[:, :, f0:f1].contiguous() for e, (f0, f1) in zip(et_v2f_full, self.fr)]
+        ef = [e[:, :, self.v0:self.v1].contiguous() for e in et_f2v_full]
+        return ev, ef
+
+    # -- one layer ---------------------------------------------------------------------------
+    def pull(self, dst_set, stream=None, what=("v", "f")):
+        """Copy the halo rows of buffer set `dst_set` from their owners (asynchronous; all ranks call it alike)."""
+        a = _lib.HaloArgs()
+        jobs = []
+        if "v" in what:
+            jobs.append((self.off_v[dst_set], [pb + ov[dst_set] for pb, ov, _ in self.peers], self.src_v, self.n_own_v))
+        if "f" in what:
+            for j in range(len(self.types)):
+                jobs.append((self.off_f[dst_set][j], [pb + of[dst_set][j] for pb, _, of in self.peers], self.src_f[j], self.n_own_f[j]))
+        for i, (off, srcs, (s_rank, s_row), n_own) in enumerate(jobs):
+            jb = a.jobs[i]
+            for q in range(self.world):
+                jb.src[q] = srcs[q]
+            jb.dst = self.base + off
+            jb.src_row, jb.src_rank = s_row.data_ptr(), s_rank.data_ptr()
+            jb.dst_row0, jb.n, jb.row_bytes = n_own, s_row.numel(), self.row_bytes
+        for q in range(self.world):
+            a.flags[q] = self.peers[q][0]
+        a.counter = self.base + 128
+        a.n_jobs, a.world, a.rank, a.epoch, a.ctas = len(jobs), self.world, self.rank, 0, self.ctas
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().fgnn_halo_pull(ctypes.byref(a), ctypes.c_void_p(st.cuda_stream)), "halo_pull")
+
+    def layer(self, l, et_v2f_local, et_f2v_local, weights, kernel=_lib.KERNEL_AUTO, workspaces=None, last=False, plans=None):
+        """Layer l: reads buffer set l & 1, leaves the new features in set (l + 1) & 1 -- owned rows by the calls, halo
+        rows by the pulls.  Order: the V->F calls, the pull of the new factor halos on a side stream BESIDE the F->V
+        calls (which read the old factor features), then the pull of the new variable halos."""
+        p, q = l & 1, (l + 1) & 1
+        nm = lambda t: t.permute(0, 2, 1).unsqueeze(-1)
+        main = torch.cuda.current_stream(self.device)
+        plans = plans or {}
+        for j in range(len(self.types)):
+            if self.n_own_f[j] == 0:
+                continue
+            w = weights[j]["v2f"]
+            wsj = workspaces[j] if workspaces is not None else {}
+            mp_forward(nm(self.xv[p]), self.idx_v2f[j], et_v2f_local[j], w["filters"], w["bias"], w["scale"], w["shift"],
+                       extension=0, aggregator=_lib.AGG_MAX, activation=_lib.ACT_RELU, kernel=kernel,
+                       out=nm(self.xf[q][j][:, :self.n_own_f[j]]), workspace=wsj.get("v2f"), filters_version=wsj.get("ver_v2f", 0),
+                       plan=plans.get("v2f%d" % j), validate=False)
+        if not last and self.world > 1:
+            ready = torch.cuda.Event()
+            ready.record(main)
+            self._side.wait_event(ready)
+            self.pull(q, stream=self._side, what=("f",))
+            done_f = torch.cuda.Event()
+            done_f.record(self._side)
+        # the F->V calls leave the pull its SMs (two 512-thread CTAs per SM) while it runs beside them
+        sms = self.n_sms - (self.ctas + 1) // 2 if (not last and self.world > 1) else 0
+        for j in range(len(self.types)):
+            w = weights[j]["f2v"]
+            wsj = workspaces[j] if workspaces is not None else {}
+            mp_forward(nm(self.xf[p][j]), self.idx_f2v[j], et_f2v_local[j], w["filters"], w["bias"], w["scale"], w["shift"],
+                       extension=0, aggregator=_lib.AGG_MAX, activation=_lib.ACT_RELU, kernel=kernel,
+                       out=nm(self.xv[q][:, :self.n_own_v]), accumulate=j > 0, workspace=wsj.get("f2v"),
+                       filters_version=wsj.get("ver_f2v", 0), plan=plans.get("f2v%d" % j), sm_limit=sms, validate=False)
+        if not last and self.world > 1:
+            main.wait_event(done_f)
+            self.pull(q, what=("v",))
+        return self.xv[q][:, :self.n_own_v]
+
+    def close(self):
+        lib = _lib.lib()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for pp in self._opened:
+                lib.fgnn_comm_close(ctypes.c_void_p(pp))
+            self._opened = []
+            if self.base:
+                self.xv = self.xf = self._mem = None
+                lib.fgnn_comm_free(ctypes.c_void_p(self.base))
+                self.base = 0
+
+
 class ShardedLayerPlan:
     """Everything rank `rank` of `world` needs to run FGNN layers on its factor shard.
 

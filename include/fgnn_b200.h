@@ -266,6 +266,33 @@ typedef struct fgnn_exchange_args {
  * peer still reads its `raw` (epoch flags, system-scope release/acquire).  All ranks launch it with the same epoch. */
 int fgnn_exchange_forward(const fgnn_exchange_args* args, void* stream);
 
+/* ---- owner-computes sharding: the feature-halo pull (halo-restricted exchange) ---------------------------
+ * Every rank owns a contiguous range of variables and of each type's factors and evaluates all slots of its own
+ * destinations; the source rows other ranks own are its halo.  One launch copies the halo rows of up to four buffers
+ * (variables + factor types) straight out of their owners' arenas over NVLink; flags / counter / epoch / ctas as in
+ * fgnn_exchange_args (all ranks launch it the same number of times).  Rows are raw bytes: fp32 and bf16 alike. */
+typedef struct fgnn_halo_job {
+  const void* src[8];        /* per rank: base of that rank's buffer (its owned rows first)          */
+  void* dst;                 /* this rank's buffer                                                    */
+  const int32_t* src_row;    /* [n] row of halo row i in its owner's buffer                           */
+  const uint8_t* src_rank;   /* [n] owner of halo row i                                               */
+  int64_t dst_row0;          /* halo row i lands in row dst_row0 + i of dst                           */
+  int32_t n;                 /* halo rows                                                             */
+  int32_t row_bytes;         /* bytes per row, a multiple of 16                                       */
+} fgnn_halo_job;
+
+typedef struct fgnn_halo_args {
+  fgnn_halo_job jobs[4];
+  uint32_t* flags[8];
+  uint64_t* counter;
+  int32_t n_jobs, world, rank;
+  uint32_t epoch;
+  int32_t ctas;              /* 512-thread CTAs (<= 128; 0 = 32)                                       */
+  int32_t reserved_;
+} fgnn_halo_args;
+
+int fgnn_halo_pull(const fgnn_halo_args* args, void* stream);
+
 /* InstanceNorm2d (affine = false, biased variance, statistics of instance (b,c) over its N nodes) + activation on a
  * logical [B,C,N] tensor with element strides: the v2v / f2f maps of FactorNN's layer body (reference
  * base_model.py:83-90, iid_mapping_in) after their 1x1 convolution.  out may alias x. */

@@ -708,6 +708,71 @@ def test_sharded_plan_equals_single_gpu(world, kernel):
         assert sum(p.f2v[j].live_slots for p in plans) == ty.idx_f2v.size
 
 
+@pytest.mark.parametrize("world,band,dtype", [(2, 0, "f32"), (3, 64, "f32"), (4, 64, "bf16"), (2, 0, "bf16")])
+def test_halo_sharded_layers_equal_single_gpu(world, band, dtype):
+    """Owner-computes sharding with feature halos (parallel.HaloLayerPlan): `world` ranks simulated on one
+    device (their arenas addressed directly, their kernels on separate streams) run three layers; the owned rows of
+    every rank, put together, are BIT-IDENTICAL to the single-GPU layers -- fp32 and bf16 I/O (cfg 4 at small scale),
+    uniform-random and banded incidence with the locality order."""
+    from fgnn_b200 import parallel
+    rng = np.random.default_rng(world * 10 + band)
+    types = graphs.synthetic_map_graph(3000, 9000, 1500, 4, seed=3, local_band=band)
+    if band:
+        types = graphs.locality_order(types)
+    C, T, L, J = 64, 16, 3, len(types)
+    td = torch.bfloat16 if dtype == "bf16" else torch.float32
+    fd = lambda a: t(a).to(td)
+    x_v = fd(rng.random((1, 3000, C), dtype=np.float32))
+    x_f = [fd(np.abs(rng.standard_normal((1, ty.n_factors, C))).astype(np.float32)) for ty in types]
+    et_v2f = [fd(rng.standard_normal((1, T, ty.n_factors, ty.order)).astype(np.float32)) for ty in types]
+    et_f2v = []
+    for ty in types:
+        e = rng.standard_normal((1, T, ty.n_vars, ty.kv)).astype(np.float32)
+        e[np.broadcast_to(ty.pad_f2v[None, None], e.shape)] = 0.0
+        et_f2v.append(fd(e))
+    W = [[{d: dict(filters=t(rng.uniform(-0.05, 0.05, (C, C * T)).astype(np.float32)), bias=t(rng.uniform(0, 0.05, C).astype(np.float32)),
+                   scale=t(rng.uniform(0.8, 1.2, C).astype(np.float32)), shift=t(rng.uniform(-0.1, 0.1, C).astype(np.float32)))
+           for d in ("v2f", "f2v")} for _ in range(J)] for _ in range(L)]
+    nm = lambda a: a.permute(0, 2, 1).unsqueeze(-1)
+    # single GPU
+    cv, cf = x_v, x_f
+    for l in range(L):
+        nv = torch.empty_like(cv)
+        nf = [torch.empty_like(f) for f in cf]
+        for j, ty in enumerate(types):
+            w = W[l][j]
+            fgnn_b200.mp_forward(nm(cv), t(ty.idx_v2f[None]), et_v2f[j], w["v2f"]["filters"], w["v2f"]["bias"], w["v2f"]["scale"],
+                                 w["v2f"]["shift"], extension=0, aggregator=0, out=nm(nf[j]))
+            fgnn_b200.mp_forward(nm(cf[j]), t(ty.idx_f2v[None]), et_f2v[j], w["f2v"]["filters"], w["f2v"]["bias"], w["f2v"]["scale"],
+                                 w["f2v"]["shift"], extension=0, aggregator=0, out=nm(nv), accumulate=j > 0)
+        cv, cf = nv, nf
+    torch.cuda.synchronize()
+    # `world` ranks on this device
+    plans = [parallel.HaloLayerPlan(types, r, world, DEV, td, C, ctas=8) for r in range(world)]
+    infos = [p.info() for p in plans]
+    for p in plans:
+        p.connect(infos, same_process=True)
+    streams = [torch.cuda.Stream(device=DEV) for _ in range(world)]
+    ets = [p.local_etypes(et_v2f, et_f2v) for p in plans]
+    try:
+        for p in plans:
+            p.load_features(x_v, x_f)
+        torch.cuda.synchronize()
+        outs = [None] * world
+        for l in range(L):
+            for r, p in enumerate(plans):
+                with torch.cuda.stream(streams[r]):
+                    outs[r] = p.layer(l, ets[r][0], ets[r][1], W[l], last=(l == L - 1))
+        torch.cuda.synchronize()
+        got = torch.cat(outs, dim=1)
+        assert torch.equal(got, cv), f"max |diff| = {float((got.float() - cv.float()).abs().max())}"
+        if band:                                             # locality: the halos are a small part of the rows
+            assert all(len(p.var_halo) < 0.2 * p.n_own_v for p in plans)
+    finally:
+        for p in plans:
+            p.close()
+
+
 def test_peer_exchange_two_ranks_on_one_device():
     """fgnn_exchange_forward (max over ranks + per-type epilogue + sum over types + broadcast, one kernel over peer
     memory): two ranks' arenas on this device, their kernels running concurrently on two streams, against
