@@ -69,8 +69,10 @@ def parse_args():
                     help="which core calls run source-stationary (one row-product per source row, csrc/mp_src.cu): "
                          "'auto' (fan-out rule of mp_conv_v2), 'none', or a comma list of v2f<j>/f2v<j> (j = factor type)")
     ap.add_argument("--cpu-sample-scale", type=int, default=2, help="cpu_baseline runs on 1/scale of the graph")
-    ap.add_argument("--exchange", default="halo", choices=["halo", "peer", "nccl"],
-                    help="multi-GPU: 'halo' = owner-computes sharding, one NVLink peer-memory kernel pulls the feature halos "
+    ap.add_argument("--exchange", default="auto", choices=["auto", "halo", "peer", "nccl"],
+                    help="multi-GPU: 'auto' = halo for graphs with index locality (--local-band) and for bf16, peer for "
+                         "uniform-random fp32 graphs (every variable is a boundary variable there: measured, DESIGN.md 7); "
+                         "'halo' = owner-computes sharding, one NVLink peer-memory kernel pulls the feature halos "
                          "per layer (parallel.HaloLayerPlan); 'peer' = factor sharding + fused max-reduce/epilogue/broadcast "
                          "kernel over peer memory; 'nccl' = factor sharding + NCCL all_reduce(MAX) + epilogue kernel")
     ap.add_argument("--order", default="locality", choices=["locality", "none"],
@@ -104,6 +106,8 @@ def parse_args():
         args.layers, args.edge_types = 10, 4
         if args.batch == 1:
             args.batch = 4096
+    if args.exchange == "auto":
+        args.exchange = "halo" if (args.local_band or args.dtype == "bf16") else "peer"
     return args
 
 

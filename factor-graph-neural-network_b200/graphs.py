@@ -68,20 +68,41 @@ def _var_side_table(idx_v2f, n_vars, kv=None):
 def random_factor_type(n_vars, n_factors, order, rng, local_band=0, name="factors"):
     """`n_factors` factors of `order` distinct-ish variables each, built from random permutations
     so that variable degrees are as even as possible (n_factors*order / n_vars, +-1).
-    local_band > 0: every factor's variables lie within a window of that many consecutive
+    local_band > 0: every factor's variables lie within (less than) two windows of that many consecutive
     variables (graphs with index locality: chains, kNN, LDPC-like)."""
     total = n_factors * order
+    reps = -(-total // n_vars)
     if local_band > 0:
-        base = rng.integers(0, n_vars, size=n_factors)
-        offs = rng.integers(0, local_band, size=(n_factors, order))
-        offs[:, 0] = 0
-        idx_v2f = (base[:, None] + offs) % n_vars
+        # the same construction with BLOCK-LOCAL permutations: permutation r shuffles the variables inside windows of
+        # `local_band` consecutive ids (windows shifted by half a band on alternate permutations, so neighbouring
+        # windows are tied together); position p of every permutation then lies within one band of p, and a factor --
+        # one position of `order` different permutations -- spans less than two bands.  Degrees stay as even as in
+        # the uniform case (every variable appears once per permutation).
+        def block_perm(r):
+            shift = (r % 2) * (local_band // 2)
+            ids = (np.arange(n_vars) + shift) % n_vars
+            out = np.empty(n_vars, dtype=np.int64)
+            for b0 in range(0, n_vars, local_band):
+                blk = ids[b0:b0 + local_band]
+                out[b0:b0 + local_band] = rng.permutation(blk)
+            return out
+        # column j of the table walks its own sequence of R block-local permutations; factor f sits at the same
+        # relative position of every column's sequence, i.e. near variable (f * R * N // F) % N in all of them
+        R = -(-n_factors // n_vars)
+        step = max(1, (R * n_vars) // n_factors)
+        pos = (np.arange(n_factors, dtype=np.int64) * (R * n_vars)) // n_factors
+        cols = []
+        for j in range(order):
+            seq = np.concatenate([block_perm(j * R + r) for r in range(R)])
+            cols.append(seq[(pos + j % step) % (R * n_vars)])
+        idx_v2f = np.stack(cols, 1)
+        idx_f2v, pad = _var_side_table(idx_v2f, n_vars)
+        return FactorType(idx_v2f, idx_f2v, pad, name)
     else:
-        reps = -(-total // n_vars)
         pool = np.concatenate([rng.permutation(n_vars) for _ in range(reps)])[:total]
-        # column-major fill: column j of the table is (a slice of) one permutation, so the
-        # variables of one factor come from different permutations
-        idx_v2f = pool.reshape(order, n_factors).T
+    # column-major fill: column j of the table is (a slice of) one permutation, so the
+    # variables of one factor come from different permutations
+    idx_v2f = pool.reshape(order, n_factors).T
     idx_f2v, pad = _var_side_table(idx_v2f, n_vars)
     return FactorType(idx_v2f, idx_f2v, pad, name)
 

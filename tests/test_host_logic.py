@@ -107,9 +107,17 @@ def test_synthetic_graph_tables_are_consistent():
         assert (t.idx_v2f[t.idx_f2v[v, s]] == v[:, None]).any(1).all()
         assert (~t.pad_f2v).sum() == t.n_factors * t.order
         assert (t.idx_f2v[t.pad_f2v] == 0).all()
-    loc = graphs.synthetic_map_graph(1000, 3000, 0, 0, seed=5, local_band=16)[0]
-    span = (loc.idx_v2f.max(1) - loc.idx_v2f.min(1))
-    assert ((span < 16) | (span > 1000 - 16)).all()
+    for loc in graphs.synthetic_map_graph(1000, 3000, 500, 3, seed=5, local_band=16):
+        span = (loc.idx_v2f.max(1) - loc.idx_v2f.min(1))
+        assert ((span < 32) | (span > 1000 - 32)).all()                      # within two bands (or wrapped around)
+        assert (~loc.pad_f2v).sum() == loc.n_factors * loc.order
+    pw = graphs.synthetic_map_graph(1000, 3000, 0, 0, seed=5, local_band=16)[0]
+    assert pw.kv == 6 and not pw.pad_f2v.any()                                   # degrees as even as the uniform graph's
+    # locality order: factors sorted by their smallest variable, tables still consistent
+    ordered = graphs.locality_order([pw])[0]
+    assert np.all(np.diff(ordered.idx_v2f.min(1)) >= 0)
+    v, s_ = np.nonzero(~ordered.pad_f2v)
+    assert (ordered.idx_v2f[ordered.idx_f2v[v, s_]] == v[:, None]).any(1).all()
 
 
 def test_parse_alist_small():
