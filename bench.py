@@ -586,8 +586,10 @@ def run_native(args):
         torch.cuda.synchronize()
 
     def checksum_of(t):
-        """Exact, order-independent fingerprint of a float tensor: the integer sum of its bit patterns."""
-        return int(t.contiguous().view(torch.int16 if t.dtype == torch.bfloat16 else torch.int32).to(torch.int64).sum().item())
+        """Exact, order-independent fingerprint of a float tensor: the integer sum of its bit patterns (after adding
+        +0, which turns a -0 into +0: ReLU written as max(v, 0) and as v * 0 differ in the sign of their zeros only)."""
+        t = (t + 0.0).contiguous()
+        return int(t.view(torch.int16 if t.dtype == torch.bfloat16 else torch.int32).to(torch.int64).sum().item())
 
     # ---- device-resident timing -----------------------------------------------------------
     for _ in range(2):

@@ -181,6 +181,50 @@ def owner_of(ids, n, world):
     return np.searchsorted(bounds, np.asarray(ids, dtype=np.int64), side="right")
 
 
+class HaloPartition:
+    """Host side (numpy) of the owner-computes sharding: rank `rank` of `world` owns the variables
+    shard_range(N, rank, world) and, per type, the factors shard_range(F_j, rank, world).  Local numbering of a
+    feature buffer: owned rows first, then the halo rows (sorted by global id).
+
+        idx_v2f[j]  [F_own_j, K]   local VARIABLE rows read by my factors           (V->F call, destinations = my factors)
+        idx_f2v[j]  [N_own, Kv]    local FACTOR rows of type j read by my variables  (F->V call, destinations = my variables)
+        var_halo / fac_halo[j]     global ids of the halo rows;  src_v / src_f[j] = (owner rank, row in the owner's buffer)
+    """
+
+    def __init__(self, types, rank, world):
+        N = types[0].n_vars
+        self.rank, self.world = rank, world
+        self.v0, self.v1 = shard_range(N, rank, world)
+        self.fr = [shard_range(t.n_factors, rank, world) for t in types]
+        n_own = self.v1 - self.v0
+        tv = [np.asarray(t.idx_v2f[f0:f1]) for t, (f0, f1) in zip(types, self.fr)]
+        outside = [a[(a < self.v0) | (a >= self.v1)] for a in tv]
+        self.var_halo = np.unique(np.concatenate(outside)) if outside else np.zeros(0, np.int64)
+
+        def to_local(a, lo, hi, halo, n_owned):
+            a = np.asarray(a, dtype=np.int64)
+            own = (a >= lo) & (a < hi)
+            return np.where(own, a - lo, n_owned + np.searchsorted(halo, a)).astype(np.int64)
+
+        self.idx_v2f = [to_local(a, self.v0, self.v1, self.var_halo, n_own) for a in tv]
+        self.fac_halo, self.idx_f2v = [], []
+        for t, (f0, f1) in zip(types, self.fr):
+            a = np.asarray(t.idx_f2v[self.v0:self.v1])
+            h = np.unique(a[(a < f0) | (a >= f1)])
+            self.fac_halo.append(h)
+            self.idx_f2v.append(to_local(a, f0, f1, h, f1 - f0))
+        self.n_own_v, self.n_own_f = n_own, [f1 - f0 for f0, f1 in self.fr]
+        self.rows_v = n_own + len(self.var_halo)
+        self.rows_f = [n + len(h) for n, h in zip(self.n_own_f, self.fac_halo)]
+
+        def src_of(halo, n):
+            own = owner_of(halo, n, world)
+            starts = np.array([shard_range(n, q, world)[0] for q in range(world)], dtype=np.int64)
+            return own.astype(np.uint8), (halo - starts[own]).astype(np.int32)
+        self.src_v = src_of(self.var_halo, N)
+        self.src_f = [src_of(h, t.n_factors) for h, t in zip(self.fac_halo, types)]
+
+
 class HaloLayerPlan:
     """Owner-computes sharding with feature halos (halo-restricted exchange).
 
@@ -201,37 +245,17 @@ class HaloLayerPlan:
         self.types, self.rank, self.world, self.device, self.dtype, self.C, self.ctas = types, rank, world, device, dtype, C, ctas
         J = len(types)
         N = types[0].n_vars
-        self.v0, self.v1 = shard_range(N, rank, world)
-        self.fr = [shard_range(t.n_factors, rank, world) for t in types]
-        n_own = self.v1 - self.v0
-        # ---- V->F: my factors read variables; halo = the variables outside my range
-        tv = [np.asarray(t.idx_v2f[f0:f1]) for t, (f0, f1) in zip(types, self.fr)]
-        outside = [a[(a < self.v0) | (a >= self.v1)] for a in tv]
-        self.var_halo = np.unique(np.concatenate(outside)) if outside else np.zeros(0, np.int64)
-
-        def to_local(a, lo, hi, halo, n_owned):
-            a = np.asarray(a, dtype=np.int64)
-            own = (a >= lo) & (a < hi)
-            return np.where(own, a - lo, n_owned + np.searchsorted(halo, a)).astype(np.int64)
-
-        self.idx_v2f = [torch.from_numpy(to_local(a, self.v0, self.v1, self.var_halo, n_own)[None]).to(device) for a in tv]
-        # ---- F->V: my variables read factors of every type; halo = the factors outside my range
-        self.fac_halo, self.idx_f2v = [], []
-        for t, (f0, f1) in zip(types, self.fr):
-            a = np.asarray(t.idx_f2v[self.v0:self.v1])
-            h = np.unique(a[(a < f0) | (a >= f1)])
-            self.fac_halo.append(h)
-            self.idx_f2v.append(torch.from_numpy(to_local(a, f0, f1, h, f1 - f0)[None]).to(device))
-        self.rows_v = n_own + len(self.var_halo)
-        self.rows_f = [(f1 - f0) + len(h) for (f0, f1), h in zip(self.fr, self.fac_halo)]
-        self.n_own_v, self.n_own_f = n_own, [f1 - f0 for f0, f1 in self.fr]
-        # halo sources: owner and row inside the owner's buffer (its owned rows come first)
-        def src_of(halo, n):
-            own = owner_of(halo, n, world)
-            starts = np.array([shard_range(n, q, world)[0] for q in range(world)], dtype=np.int64)
-            return (torch.from_numpy(own.astype(np.uint8)).to(device), torch.from_numpy((halo - starts[own]).astype(np.int32)).to(device))
-        self.src_v = src_of(self.var_halo, N)
-        self.src_f = [src_of(h, t.n_factors) for h, t in zip(self.fac_halo, types)]
+        part = HaloPartition(types, rank, world)
+        self.part = part
+        self.v0, self.v1, self.fr = part.v0, part.v1, part.fr
+        self.var_halo, self.fac_halo = part.var_halo, part.fac_halo
+        self.n_own_v, self.n_own_f, self.rows_v, self.rows_f = part.n_own_v, part.n_own_f, part.rows_v, part.rows_f
+        n_own = self.n_own_v
+        self.idx_v2f = [torch.from_numpy(a[None]).to(device) for a in part.idx_v2f]
+        self.idx_f2v = [torch.from_numpy(a[None]).to(device) for a in part.idx_f2v]
+        dev_pair = lambda pr: (torch.from_numpy(pr[0]).to(device), torch.from_numpy(pr[1]).to(device))
+        self.src_v = dev_pair(part.src_v)
+        self.src_f = [dev_pair(pr) for pr in part.src_f]
         # ---- arena: header | two sets of [xv, xf_0 .. xf_J-1]
         esz = 2 if dtype == torch.bfloat16 else 4
         self.row_bytes = C * esz

@@ -56,6 +56,26 @@ def test_struct_layout_matches_header(tmp_path):
         assert getattr(_lib.MpArgs, f).offset == off, f
 
 
+def test_halo_struct_layout_matches_header(tmp_path):
+    prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){',
+            'printf("%zu\\n", sizeof(fgnn_halo_args));', 'printf("%zu\\n", sizeof(fgnn_halo_job));']
+    prog += [f'printf("%zu\\n", offsetof(fgnn_halo_args, {f[0]}));' for f in _lib.HaloArgs._fields_]
+    prog += [f'printf("%zu\\n", offsetof(fgnn_halo_job, {f[0]}));' for f in _lib.HaloJob._fields_]
+    prog += ['return 0;}']
+    src = tmp_path / "layout_halo.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout_halo"
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([cc, "-std=c11", "-o", str(exe), str(src)])
+    out = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert out[0] == ctypes.sizeof(_lib.HaloArgs) and out[1] == ctypes.sizeof(_lib.HaloJob)
+    offs = out[2:]
+    for f, off in zip(_lib.HaloArgs._fields_, offs):
+        assert getattr(_lib.HaloArgs, f[0]).offset == off, f[0]
+    for f, off in zip(_lib.HaloJob._fields_, offs[len(_lib.HaloArgs._fields_):]):
+        assert getattr(_lib.HaloJob, f[0]).offset == off, f[0]
+
+
 def test_exchange_struct_layout_matches_header(tmp_path):
     fields = [f[0] for f in _lib.ExchangeArgs._fields_]
     prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){',

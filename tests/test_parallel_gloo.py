@@ -136,3 +136,103 @@ def test_single_process_simulation_of_four_ranks():
         out = out + _epilogue(raw, d)
     ref = sum(_full(t, d) for t, d in zip(types, data))
     assert np.abs(out - ref).max() <= 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# owner-computes sharding with feature halos (parallel.HaloPartition): host logic over gloo
+# ---------------------------------------------------------------------------------------------
+
+def _full_layer(types, data, x_v):
+    """One FGNN layer on the whole graph with the oracle: (new x_v [1,O,N,1], new x_f list)."""
+    new_v, new_f = 0, []
+    for t, d in zip(types, data):
+        et_v2f = d["et_v2f"]
+        new_f.append(orc.mp_conv_forward(x_v, t.idx_v2f[None], et_v2f, d["W"], d["bias"], d["bn"], extension=0, aggregator="max"))
+        new_v = new_v + orc.mp_conv_forward(d["x_f"], t.idx_f2v[None], d["et"], d["W"], d["bias"], d["bn"], extension=0,
+                                            aggregator="max")
+    return new_v, new_f
+
+
+def _halo_problem(band):
+    rng = np.random.default_rng(11)
+    types = graphs.synthetic_map_graph(N_VARS, 600, 150, 3, seed=5, local_band=band)
+    if band:
+        types = graphs.locality_order(types)
+    types2, data = types, []
+    for t in types2:
+        d = dict(x_f=rng.standard_normal((1, C, t.n_factors, 1)).astype(np.float32),
+                 et=rng.standard_normal((1, T, t.n_vars, t.kv)).astype(np.float32),
+                 et_v2f=rng.standard_normal((1, T, t.n_factors, t.order)).astype(np.float32),
+                 W=rng.uniform(-0.5, 0.5, (C, O * T)).astype(np.float32), bias=rng.uniform(-0.2, 0.2, O).astype(np.float32),
+                 bn=dict(weight=np.ones(O, np.float32), bias=np.zeros(O, np.float32), running_mean=np.zeros(O, np.float32),
+                         running_var=np.ones(O, np.float32)))
+        d["et"][np.broadcast_to(t.pad_f2v[None, None], d["et"].shape)] = 0.0
+        data.append(d)
+    x_v = rng.standard_normal((1, C, N_VARS, 1)).astype(np.float32)
+    return types2, data, x_v
+
+
+def _halo_worker(rank, world, port, band, out_q):
+    from fgnn_b200.parallel import HaloPartition
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        types, data, x_v = _halo_problem(band)
+        part = HaloPartition(types, rank, world)
+
+        def pull(own_rows, halo_src, n_rows_by_rank):
+            """The halo pull, emulated: all-gather every rank's owned rows, pick (owner, row)."""
+            width = own_rows.shape[1]
+            pad = max(n_rows_by_rank)
+            buf = torch.zeros(pad, width)
+            buf[:own_rows.shape[0]] = torch.from_numpy(own_rows)
+            gathered = [torch.zeros(pad, width) for _ in range(world)]
+            dist.all_gather(gathered, buf)
+            owner, row = halo_src
+            return np.stack([gathered[int(o)][int(r)].numpy() for o, r in zip(owner, row)]) if len(owner) else np.zeros((0, width), np.float32)
+
+        nv_by_rank = [shard_range(N_VARS, q, world)[1] - shard_range(N_VARS, q, world)[0] for q in range(world)]
+        own_v = x_v[0, :, part.v0:part.v1, 0].T                                   # [N_own, C]
+        loc_v = np.concatenate([own_v, pull(np.ascontiguousarray(own_v), part.src_v, nv_by_rank)], 0)
+        new_v, new_f = 0, []
+        for j, (t, d) in enumerate(zip(types, data)):
+            f0, f1 = part.fr[j]
+            nf_by_rank = [shard_range(t.n_factors, q, world)[1] - shard_range(t.n_factors, q, world)[0] for q in range(world)]
+            own_f = d["x_f"][0, :, f0:f1, 0].T
+            loc_f = np.concatenate([own_f, pull(np.ascontiguousarray(own_f), part.src_f[j], nf_by_rank)], 0)
+            # V->F of my factors, F->V of my variables, local tables
+            new_f.append(orc.mp_conv_forward(loc_v.T[None, :, :, None], part.idx_v2f[j][None], d["et_v2f"][:, :, f0:f1], d["W"],
+                                             d["bias"], d["bn"], extension=0, aggregator="max"))
+            new_v = new_v + orc.mp_conv_forward(loc_f.T[None, :, :, None], part.idx_f2v[j][None], d["et"][:, :, part.v0:part.v1],
+                                                d["W"], d["bias"], d["bn"], extension=0, aggregator="max")
+        out_q.put((rank, part.v0, part.v1, part.fr, new_v, new_f, len(part.var_halo), [len(h) for h in part.fac_halo]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("band", [0, 32])
+def test_halo_partition_two_ranks_gloo(band):
+    """world_size 2 over gloo: every rank evaluates its own destinations from [owned | pulled halo] rows through the
+    renumbered tables; the owned rows put together equal the single-process layer bit for bit (same slots, same order)."""
+    world = 2
+    types, data, x_v = _halo_problem(band)
+    want_v, want_f = _full_layer(types, data, x_v)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_halo_worker, args=(r, world, port, band, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, v0, v1, fr, new_v, new_f, hv, hf in res:
+        assert np.array_equal(new_v, want_v[:, :, v0:v1])
+        for j, (f0, f1) in enumerate(fr):
+            assert np.array_equal(new_f[j], want_f[j][:, :, f0:f1])
+        if band:
+            assert hv < 0.5 * (v1 - v0)                       # locality order: the halo is a fraction of the shard
