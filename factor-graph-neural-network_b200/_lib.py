@@ -120,6 +120,11 @@ EXPORTS = {
                                       ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
     "fgnn_bwd_scatter": (ctypes.c_int, [ctypes.POINTER(MpArgs), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
                                         ctypes.c_void_p]),
+    "fgnn_plan_build_host": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                              ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64),
+                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "fgnn_locality_order_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                                ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "fgnn_comm_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
     "fgnn_comm_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
     "fgnn_comm_close": (ctypes.c_int, [ctypes.c_void_p]),

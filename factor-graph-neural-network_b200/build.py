@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfgnn_b200.so")
-SOURCES = ["api.cu", "mp_simt.cu", "mp_tc.cu", "mp_src.cu", "exchange.cu", "emodel.cu", "backward.cu"]
+SOURCES = ["api.cu", "mp_simt.cu", "mp_tc.cu", "mp_src.cu", "exchange.cu", "emodel.cu", "backward.cu", "plan.cu"]
 HEADERS = ["common.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "fgnn_b200.h")]
 
 

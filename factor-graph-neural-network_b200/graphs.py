@@ -126,6 +126,30 @@ def locality_order(types):
     follow the new numbering)."""
     out = []
     for t in types:
+        out.append(FactorType(*_locality_order_native(t), t.pad_f2v, t.name))
+    return out
+
+
+def _locality_order_native(t):
+    """fgnn_locality_order_host (csrc/plan.cu): stable sort of the factors by smallest variable + renumbering."""
+    import ctypes
+    from . import _lib
+    F, K = t.idx_v2f.shape
+    N, Kv = t.idx_f2v.shape
+    order = np.empty(F, dtype=np.int64)
+    v2f = np.empty((F, K), dtype=np.int64)
+    f2v = np.empty((N, Kv), dtype=np.int64)
+    pad = np.ascontiguousarray(t.pad_f2v, dtype=np.uint8)
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    _lib.check(_lib.lib().fgnn_locality_order_host(p(t.idx_v2f), F, K, p(t.idx_f2v), p(pad), N, Kv, p(order), p(v2f), p(f2v)),
+               "locality_order_host")
+    return v2f, f2v
+
+
+def locality_order_numpy(types):
+    """The same renumbering with numpy (cross-check of the native builder)."""
+    out = []
+    for t in types:
         order = np.argsort(t.idx_v2f.min(1), kind="stable")             # new factor i = old factor order[i]
         inv = np.empty_like(order)
         inv[order] = np.arange(order.size)

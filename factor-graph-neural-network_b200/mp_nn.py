@@ -113,6 +113,9 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+_ptr_host = _ptr
+
+
 def _bn_version(bn):
     """Identity of a BatchNorm's eval-mode state: in-place version counters and addresses of the four tensors."""
     parts = []
@@ -190,8 +193,13 @@ class SourcePlan:
     _cache = {}
     TILE_COST = {3: 1.0, 6: 1.4}       # relative cost of a 128-row tile (row_cap 6 reads the accumulators twice)
 
-    def __init__(self, nn_idx, n_src, mask_negative=False, row_cap=None):
+    def __init__(self, nn_idx, n_src, mask_negative=False, row_cap=None, device=None):
         B, M, K = nn_idx.shape
+        if not nn_idx.is_cuda:
+            # a host table (what a DataLoader hands over): the library's own O(E) counting-sort builder
+            # (csrc/plan.cu, fgnn_plan_build_host); `device` = where the plan's arrays go
+            self._build_native(nn_idx, n_src, row_cap, device)
+            return
         dev = nn_idx.device
         R = B * n_src
         flat = nn_idx.reshape(B, M * K).long()
@@ -227,6 +235,47 @@ class SourcePlan:
         self.max_fan_out = int(counts.max().item()) if counts.numel() else 0
         self._msg = None
         self._et = None                    # (weakref(etype), version, data_ptr, permuted)
+
+    def _build_native(self, nn_idx, n_src, row_cap, device):
+        B, M, K = nn_idx.shape
+        t = nn_idx if nn_idx.dtype in (torch.int64, torch.int32) else nn_idx.long()
+        if t.stride(2) != 1 or t.stride(1) != K or (B > 1 and t.stride(0) not in (0, M * K)):
+            t = t.contiguous()
+        sb = t.stride(0) if B > 1 else M * K
+        dt = _lib.I64 if t.dtype == torch.int64 else _lib.I32
+        lib = _lib.lib()
+        E = ctypes.c_int64()
+
+        def size_for(cap):
+            v = lib.fgnn_plan_build_host(_ptr_host(t), dt, B, M, K, sb, n_src, cap, ctypes.byref(E), None, None, None, None)
+            if v < 0:
+                _lib.check(int(v), "plan_build_host")
+            return int(v)
+        if row_cap is None:
+            tiles = {c: -(-size_for(c) // 128) for c in (3, 6)}
+            row_cap = min((3, 6), key=lambda c: tiles[c] * self.TILE_COST[c])
+        if row_cap not in (3, 6):
+            raise ValueError("row_cap must be 3 or 6")
+        V = size_for(row_cap)
+        R = B * n_src
+        src_ptr = torch.empty(V + 1, dtype=torch.int32)
+        slot_edge = torch.empty(B * M * K, dtype=torch.int32)
+        edge_slot = torch.empty(max(1, E.value), dtype=torch.int32)
+        src_rows = torch.empty(max(1, V - R), dtype=torch.int32)
+        v = lib.fgnn_plan_build_host(_ptr_host(t), dt, B, M, K, sb, n_src, row_cap, ctypes.byref(E), _ptr_host(src_ptr),
+                                     _ptr_host(slot_edge), _ptr_host(edge_slot), _ptr_host(src_rows))
+        if v < 0:
+            _lib.check(int(v), "plan_build_host")
+        dev = torch.device(device) if device is not None else nn_idx.device
+        self.B, self.M, self.K, self.n_src, self.n_edges = B, M, K, n_src, int(E.value)
+        self.row_cap, self.n_rows = row_cap, V
+        self.src_ptr, self.slot_edge = src_ptr.to(dev), slot_edge.to(dev)
+        self.edge_slot, self.src_rows = edge_slot[:self.n_edges].to(dev), src_rows[:V - R].to(dev)
+        self.fan_out = self.n_edges / max(1, R)
+        d = src_ptr[1:R + 1] - src_ptr[:R]
+        self.max_fan_out = int(d.max()) if R else 0
+        self._msg = None
+        self._et = None
 
     @classmethod
     def for_table(cls, nn_idx, n_src, mask_negative=False):

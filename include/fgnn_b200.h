@@ -201,6 +201,22 @@ int fgnn_bwd_outer(const fgnn_mp_args* a, float* H_inout, const float* ge, float
 /* dx [B,N,C] node-major, zero-initialised by the caller, += dXin [B*mc*K, C or 2C] (atomic adds) */
 int fgnn_bwd_scatter(const fgnn_mp_args* a, const float* dxin, float* dx, int32_t m0, int32_t mc, void* stream);
 
+/* ---- native graph preprocessing (host) ---------------------------------------------------------
+ * The source-stationary plan of a HOST table nn_idx [B,M,K] (batch stride idx_sb elements) in O(E) counting-sort
+ * passes, stable in slot order: call once with the output pointers NULL to get V (virtual rows, the return value) and
+ * E (*n_edges_out), then with src_ptr [V+1], slot_edge [B*M*K], edge_slot [E], src_rows [V - B*n_src] (may be NULL when
+ * V == B*n_src).  Entries outside [0, n_src) are empty slots.  Layout as documented at fgnn_mp_args.src_ptr. */
+int64_t fgnn_plan_build_host(const void* idx, int32_t idx_dtype, int32_t B, int32_t M, int32_t K, int64_t idx_sb, int32_t n_src,
+                             int32_t row_cap, int64_t* n_edges_out, int32_t* src_ptr, int32_t* slot_edge, int32_t* edge_slot,
+                             int32_t* src_rows);
+
+/* Factors renumbered by their smallest variable (stable): order [F] (new factor i = old factor order[i]), the
+ * factor-side table with its rows permuted, the variable-side table [N,Kv] with its entries renumbered (pad slots --
+ * pad[i] != 0 -- keep the reference's valid-index pad 0).  With index locality in the graph, contiguous factor shards
+ * then touch (nearly) contiguous variable ranges: the precondition for halo-sized exchanges (fgnn_halo_pull). */
+int fgnn_locality_order_host(const int64_t* idx_v2f, int64_t F, int32_t K, const int64_t* idx_f2v, const uint8_t* pad, int64_t N,
+                             int32_t Kv, int64_t* order, int64_t* idx_v2f_out, int64_t* idx_f2v_out);
+
 /* Index validation the reference gets for free from ATen's gather (mp_nn.py:111): returns
  * FGNN_ERR_INDEX_RANGE if any entry of idx[count] is outside [lo, N).  Synchronises `stream`.
  * `scratch` = 8 bytes of device memory. */

@@ -289,6 +289,38 @@ def test_source_plan_layout(row_cap):
     assert fgnn_b200.SourcePlan.for_table(tbl, N, True) is fgnn_b200.SourcePlan.for_table(tbl, N, True)
 
 
+@pytest.mark.parametrize("row_cap", [3, 6, None])
+def test_native_plan_builder_matches_torch_builder(row_cap):
+    """fgnn_plan_build_host (csrc/plan.cu, counting sort on the host) == the torch-op builder, array for array; it
+    needs no GPU, so it is what SourcePlan uses for tables that still live on the host."""
+    import torch
+    import fgnn_b200
+    rng = np.random.default_rng(3)
+    B, N, M, K = 3, 40, 90, 4
+    idx = rng.integers(-1, N, (B, M, K))
+    idx[1, :, 1] = 5                                            # a hub
+    t64 = torch.from_numpy(idx)
+    native = fgnn_b200.SourcePlan(t64, N, row_cap=row_cap)                       # host table -> native builder
+
+    class _Dev(torch.Tensor):                                   # the same table posing as a device tensor: torch-op builder
+        @property
+        def is_cuda(self):
+            return True
+    ref = fgnn_b200.SourcePlan(t64.as_subclass(_Dev), N, row_cap=row_cap)
+    assert (native.row_cap, native.n_rows, native.n_edges) == (ref.row_cap, ref.n_rows, ref.n_edges)
+    for name in ("src_ptr", "slot_edge", "edge_slot", "src_rows"):
+        assert torch.equal(getattr(native, name), torch.as_tensor(getattr(ref, name))), name
+    native32 = fgnn_b200.SourcePlan(t64.int(), N, row_cap=native.row_cap)
+    assert torch.equal(native32.slot_edge, native.slot_edge)
+
+
+def test_native_locality_order_matches_numpy():
+    types = graphs.synthetic_map_graph(500, 1500, 250, 3, seed=9, local_band=32)
+    a, b = graphs.locality_order(types), graphs.locality_order_numpy(types)
+    for x, y in zip(a, b):
+        assert np.array_equal(x.idx_v2f, y.idx_v2f) and np.array_equal(x.idx_f2v, y.idx_f2v)
+
+
 def test_source_plan_picks_row_cap_by_cost():
     import torch
     import fgnn_b200
