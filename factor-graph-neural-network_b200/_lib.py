@@ -99,6 +99,12 @@ EXPORTS = {
                                                    ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                                    ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_float,
                                                    ctypes.c_int32, ctypes.c_float, ctypes.c_void_p]),
+    "fgnn_instance_norm_partial": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
+                                                   ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
+    "fgnn_instance_norm_apply": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                                 ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                                 ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_float,
+                                                 ctypes.c_void_p]),
     "fgnn_to_node_major": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                           ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
                                           ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),

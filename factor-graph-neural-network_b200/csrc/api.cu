@@ -213,6 +213,51 @@ instance_norm_warp_kernel(const float* __restrict__ x, float* __restrict__ out, 
   }
 }
 
+// Sharded InstanceNorm (the f2f / v2v maps of a FactorNN layer whose nodes are split over ranks, base_model.py:83-90,
+// SURVEY 8f rank 4): the statistics of instance (b, c) run over ALL ranks' rows, so every rank reduces its own rows
+// to partial sums -- pass 1: sum x; pass 2 (mean given): sum (x - mean)^2, the two-pass variance of the single-GPU
+// kernel -- the host all-reduces the [B, C] partials (2 * C floats per instance), and the apply kernel normalises.
+__global__ void __launch_bounds__(256)
+instance_norm_partial_kernel(const float* __restrict__ x, const float* __restrict__ mean, float* __restrict__ out, int C, int N,
+                             int64_t x_sb, int64_t x_sc, int64_t x_sn) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx, b = blockIdx.y;
+  float s = 0.f;
+  if (c < C) {
+    const float* xb = x + (int64_t)b * x_sb + (int64_t)c * x_sc;
+    const float m = mean ? mean[(int64_t)b * C + c] : 0.f;
+    for (int n = ty; n < N; n += 8) {
+      const float d = xb[(int64_t)n * x_sn] - m;
+      s += mean ? d * d : d;
+    }
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a += red[j][tx];
+    out[(int64_t)b * C + c] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+instance_norm_apply_kernel(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ mean,
+                           const float* __restrict__ inv_std, int B, int C, int N, int64_t x_sb, int64_t x_sc, int64_t x_sn,
+                           int64_t o_sb, int64_t o_sc, int64_t o_sn, int act, float slope) {
+  const int64_t total = (int64_t)B * C * N;
+  const float neg = act == FGNN_ACT_NONE ? 1.f : (act == FGNN_ACT_RELU ? 0.f : slope);
+  const bool cl = x_sc == 1;                                  // channels fastest in memory: iterate them fastest
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int b, c, n;
+    if (cl) { c = (int)(i % C); n = (int)((i / C) % N); b = (int)(i / ((int64_t)C * N)); }
+    else { n = (int)(i % N); c = (int)((i / N) % C); b = (int)(i / ((int64_t)C * N)); }
+    const float y = (x[b * x_sb + c * x_sc + n * x_sn] - mean[(int64_t)b * C + c]) * inv_std[(int64_t)b * C + c];
+    out[b * o_sb + c * o_sc + n * o_sn] = y >= 0.f ? y : y * neg;
+  }
+}
+
 static int device_ok() {
   static int cached = -100;
   if (cached != -100) return cached;
@@ -329,6 +374,31 @@ int fgnn_instance_norm_forward(const float* x, float* out, int32_t B, int32_t C,
     instance_norm_warp_kernel<<<(unsigned)((inst + 7) / 8), 256, 0, stream>>>(x, out, B, C, N, x_sb, x_sc, x_sn, out_sb, out_sc,
                                                                           out_sn, eps, activation, act_slope);
   }
+  count_launch();
+  FGNN_CUDA(cudaGetLastError());
+  return FGNN_OK;
+}
+
+int fgnn_instance_norm_partial(const float* x, const float* mean, float* sums, int32_t B, int32_t C, int32_t N, int64_t x_sb,
+                               int64_t x_sc, int64_t x_sn, void* stream_) {
+  if (!x || !sums || B <= 0 || C <= 0 || N < 0 || B > 65535) return FGNN_ERR_INVALID_ARG;
+  dim3 grid((C + 31) / 32, B);
+  instance_norm_partial_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, mean, sums, C, N, x_sb, x_sc, x_sn);
+  count_launch();
+  FGNN_CUDA(cudaGetLastError());
+  return FGNN_OK;
+}
+
+int fgnn_instance_norm_apply(const float* x, float* out, const float* mean, const float* inv_std, int32_t B, int32_t C, int32_t N,
+                             int64_t x_sb, int64_t x_sc, int64_t x_sn, int64_t out_sb, int64_t out_sc, int64_t out_sn,
+                             int32_t activation, float act_slope, void* stream_) {
+  if (!x || !out || !mean || !inv_std || B <= 0 || C <= 0 || N < 0 || activation < 0 || activation > 2) return FGNN_ERR_INVALID_ARG;
+  const int64_t total = (int64_t)B * C * N;
+  if (total == 0) return FGNN_OK;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  instance_norm_apply_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      x, out, mean, inv_std, B, C, N, x_sb, x_sc, x_sn, out_sb, out_sc, out_sn, activation, act_slope);
   count_launch();
   FGNN_CUDA(cudaGetLastError());
   return FGNN_OK;

@@ -181,6 +181,37 @@ def owner_of(ids, n, world):
     return np.searchsorted(bounds, np.asarray(ids, dtype=np.int64), side="right")
 
 
+def sharded_instance_norm_act(x_local, n_total, group=None, eps=1e-5, activation=None, reduce=None):
+    """InstanceNorm2d (affine = False) + activation (None | 'relu') of a [B,C,N_local,1] fp32 CUDA tensor whose N
+    axis is split over the ranks of `group` (FactorNN's f2f / v2v maps on sharded factor / variable features,
+    base_model.py:83-90): local partial sums -> all-reduce of 2 x C floats per instance -> normalise.  Two-pass
+    variance, like the single-GPU kernel.  `reduce` replaces the all-reduce (tests: sum over simulated shards)."""
+    lib = _lib.lib()
+    B, C, N, W = x_local.shape
+    assert W == 1 and x_local.is_cuda and x_local.dtype == torch.float32
+    dev = x_local.device
+    if reduce is None:
+        def reduce(t):
+            if torch.distributed.is_initialized():
+                torch.distributed.all_reduce(t, group=group)
+            return t
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    st = lambda: ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    sb, sc, sn = x_local.stride(0), x_local.stride(1), x_local.stride(2)
+    out = torch.empty_like(x_local)
+    with torch.cuda.device(dev):
+        s1 = torch.empty((B, C), dtype=torch.float32, device=dev)
+        _lib.check(lib.fgnn_instance_norm_partial(p(x_local), None, p(s1), B, C, N, sb, sc, sn, st()), "instance_norm_partial")
+        mean = reduce(s1) / float(n_total)
+        s2 = torch.empty((B, C), dtype=torch.float32, device=dev)
+        _lib.check(lib.fgnn_instance_norm_partial(p(x_local), p(mean), p(s2), B, C, N, sb, sc, sn, st()), "instance_norm_partial")
+        inv = torch.rsqrt(reduce(s2) / float(n_total) + eps)
+        _lib.check(lib.fgnn_instance_norm_apply(p(x_local), p(out), p(mean), p(inv), B, C, N, sb, sc, sn, out.stride(0), out.stride(1),
+                                                out.stride(2), _lib.ACT_RELU if activation == "relu" else _lib.ACT_NONE, 0.0, st()),
+                   "instance_norm_apply")
+    return out
+
+
 class HaloPartition:
     """Host side (numpy) of the owner-computes sharding: rank `rank` of `world` owns the variables
     shard_range(N, rank, world) and, per type, the factors shard_range(F_j, rank, world).  Local numbering of a

@@ -316,6 +316,17 @@ int fgnn_instance_norm_forward(const float* x, float* out, int32_t B, int32_t C,
                                int64_t x_sn, int64_t out_sb, int64_t out_sc, int64_t out_sn, float eps,
                                int32_t activation, float act_slope, void* stream);
 
+/* The same norm when the N nodes of an instance are split over ranks (a sharded FactorNN layer's f2f / v2v maps;
+ * SURVEY 8f rank 4): fgnn_instance_norm_partial reduces THIS rank's rows to sums [B,C] -- of x when mean == NULL, of
+ * (x - mean)^2 when the (all-reduced) mean [B,C] is given: the two-pass variance of the single-GPU kernel -- the caller
+ * all-reduces the 2 x C floats per instance (torch.distributed), and fgnn_instance_norm_apply normalises the local rows
+ * with the global mean / inverse standard deviation and applies the activation. */
+int fgnn_instance_norm_partial(const float* x, const float* mean, float* sums, int32_t B, int32_t C, int32_t N, int64_t x_sb,
+                               int64_t x_sc, int64_t x_sn, void* stream);
+int fgnn_instance_norm_apply(const float* x, float* out, const float* mean, const float* inv_std, int32_t B, int32_t C, int32_t N,
+                             int64_t x_sb, int64_t x_sc, int64_t x_sn, int64_t out_sb, int64_t out_sc, int64_t out_sn,
+                             int32_t activation, float act_slope, void* stream);
+
 /* Layout helper: channel-major [B,C,N] -> node-major [B,N,C] (the reference's
  * x.permute(0,2,3,1).contiguous(), mp_nn.py:125). */
 int fgnn_to_node_major(const float* x, float* out, int32_t B, int32_t C, int32_t N, int64_t x_sb,

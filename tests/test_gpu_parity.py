@@ -639,6 +639,40 @@ def test_full_size_properties_cfg2():
     assert_close(yz.cpu().numpy(), np.broadcast_to(const.reshape(1, O, 1, 1), (1, O, M, 1)), 1e-6, "zero etype")
 
 
+@pytest.mark.parametrize("T", [16, 4])
+def test_full_size_cfg2_all_four_calls_vs_oracle(T):
+    """BASELINE configs[1] at FULL size, all four core calls of a layer (V->F / F->V of the pairwise and the order-3
+    type, the bench's own graph with its zero-etype pads): destination-stationary and source-stationary evaluation
+    against the C oracle on 4 000 sampled destination rows per call (the oracle evaluates exactly those rows from the
+    full source features), and bit-identical to each other."""
+    rng = np.random.default_rng(20 + T)
+    types = graphs.synthetic_map_graph(100_000, 300_000, 50_000, 3, seed=0)
+    C = O = 64
+    x_v = rng.random((1, C, 100_000, 1), dtype=np.float32)
+    for ty in types:
+        x_f = np.abs(rng.standard_normal((1, C, ty.n_factors, 1))).astype(np.float32)
+        for name, x, idx, pad in (("v2f", x_v, ty.idx_v2f, None), ("f2v", x_f, ty.idx_f2v, ty.pad_f2v)):
+            M, K = idx.shape
+            et = rng.standard_normal((1, T, M, K)).astype(np.float32)
+            if pad is not None:
+                et[np.broadcast_to(pad[None, None], et.shape)] = 0.0
+            W = (rng.uniform(-1, 1, (C, O * T)) * 0.05).astype(np.float32)
+            bias = rng.uniform(0, 0.05, O).astype(np.float32)
+            bn = dict(weight=rng.uniform(0.8, 1.2, O).astype(np.float32), bias=rng.uniform(-0.1, 0.1, O).astype(np.float32),
+                      running_mean=rng.uniform(-0.05, 0.05, O).astype(np.float32), running_var=rng.uniform(0.5, 1.5, O).astype(np.float32))
+            y = _native(x, idx[None], et, W, bias, bn, kernel=_lib.KERNEL_TCGEN05)
+            d_idx = t(idx[None])
+            plan = fgnn_b200.SourcePlan(d_idx, x.shape[2])
+            scale = bn["weight"] / np.sqrt(bn["running_var"] + 1e-5)
+            shift = bn["bias"] - bn["running_mean"] * scale
+            y_src = fgnn_b200.mp_forward(t(x).contiguous(memory_format=torch.channels_last), d_idx, t(et), t(W), t(bias),
+                                         t(scale.astype(np.float32)), t(shift.astype(np.float32)), extension=0, aggregator=0, plan=plan)
+            assert torch.equal(y, y_src), f"{ty.name} {name}: source-stationary differs"
+            rows = np.sort(rng.choice(M, 4000, replace=False))
+            ref = orc.mp_conv_forward_c(x, idx[None][:, rows], et[:, :, rows], W, bias, bn, extension=0, aggregator="max")
+            assert_close(y[:, :, torch.from_numpy(rows).to(DEV)].cpu().numpy(), ref, RTOL, f"{ty.name} {name} T={T}")
+
+
 # ---------------------------------------------------------------------------------------------
 # factor-sharded layer (SURVEY 8e): N-GPU result == 1-GPU result, ranks simulated on one device
 # ---------------------------------------------------------------------------------------------
@@ -771,6 +805,40 @@ def test_halo_sharded_layers_equal_single_gpu(world, band, dtype):
     finally:
         for p in plans:
             p.close()
+
+
+@pytest.mark.parametrize("layout", ["channels_first", "channels_last"])
+def test_sharded_instance_norm_matches_full(layout):
+    """InstanceNorm + ReLU with the nodes of every instance split over three shards (two-pass statistics, partial sums
+    added across the shards = the 2 x C-float all-reduce of a sharded FactorNN layer) == the norm of the whole tensor."""
+    from fgnn_b200 import parallel
+    torch.manual_seed(1)
+    B, C, N = 3, 64, 1000
+    x = torch.randn(B, C, N, 1, device=DEV) * 2 + 0.5
+    if layout == "channels_last":
+        x = x.contiguous(memory_format=torch.channels_last)
+    want = torch.relu(torch.nn.functional.instance_norm(x))
+    cuts = [0, 250, 700, N]
+    shards = [x[:, :, a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+    # emulate the collective: the partial sums of every shard are computed up front through the C ABI, and each shard's
+    # call gets a reducer that returns the total of the pass it is in (first call: sum x, second: sum (x - mean)^2)
+    lib, p = _lib.lib(), (lambda tt: ctypes.c_void_p(tt.data_ptr()))
+    st = ctypes.c_void_p(torch.cuda.current_stream(DEV).cuda_stream)
+
+    def partials(mean):
+        out = [torch.empty(B, C, device=DEV) for _ in shards]
+        for s_, sh in zip(out, shards):
+            _lib.check(lib.fgnn_instance_norm_partial(p(sh), p(mean) if mean is not None else None, p(s_), B, C, sh.shape[2],
+                                                      sh.stride(0), sh.stride(1), sh.stride(2), st), "partial")
+        return sum(out)
+    tot1 = partials(None)
+    tot2 = partials(tot1 / N)
+    outs = []
+    for sh in shards:
+        seq = iter([tot1, tot2])
+        outs.append((sh, lambda tt, seq=seq: next(seq).clone()))
+    got = torch.cat([parallel.sharded_instance_norm_act(sh, N, activation="relu", reduce=red) for sh, red in outs], dim=2)
+    assert_close(got.cpu().numpy(), want.cpu().numpy(), 2e-5, "sharded instance norm")
 
 
 def test_peer_exchange_two_ranks_on_one_device():

@@ -7,23 +7,42 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-# north_star tolerance: 1e-4 relative, fp32.  "Relative" is taken against the magnitude of the
-# reference tensor: |got - ref| <= RTOL * max(|ref|, max|ref| of the tensor) -- elementwise rtol
-# with the tensor's own scale as the floor (outputs pass through ReLU, so exact zeros are common).
+# north_star tolerance: 1e-4 relative, fp32.  Stated ELEMENTWISE with an explicit absolute floor:
+#     |got - ref| <= rtol * |ref| + ATOL_FRAC * rtol * scale,      scale = max |ref| over the tensor,
+# i.e. for rtol = 1e-4 an element may be off by 1e-4 of its own magnitude plus 2e-5 of the tensor's scale (outputs
+# pass through ReLU, so exact zeros are common and need the floor; the kernels' measured error is 4-7e-6 of scale).
+# `rel_err` reports the worst element in units of that bound times rtol, so `rel_err <= rtol` is the criterion.
 RTOL = 1e-4
+ATOL_FRAC = 0.2
 
 
-def rel_err(got, ref):
+def rel_err(got, ref, rtol=RTOL):
     got = np.asarray(got, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
-    scale = max(float(np.abs(ref).max()) if ref.size else 0.0, 1e-30)
-    return float((np.abs(got - ref) / np.maximum(np.abs(ref), scale)).max()) if ref.size else 0.0
+    if not ref.size:
+        return 0.0
+    scale = max(float(np.abs(ref).max()), 1e-30)
+    bound = np.abs(ref) + ATOL_FRAC * scale                    # the admissible error per element, divided by rtol
+    return float((np.abs(got - ref) / bound).max())
+
+
+def error_profile(got, ref):
+    """Elementwise error distribution (for logs): max / 99.9th percentile of |d| / scale and of |d| / |ref| over the
+    elements with |ref| > 1e-3 * scale."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    scale = max(float(np.abs(ref).max()), 1e-30)
+    d = np.abs(got - ref)
+    big = np.abs(ref) > 1e-3 * scale
+    rel = d[big] / np.abs(ref[big]) if big.any() else np.zeros(1)
+    return dict(max_abs_over_scale=float(d.max() / scale), p999_abs_over_scale=float(np.quantile(d, 0.999) / scale),
+                max_rel=float(rel.max()), p999_rel=float(np.quantile(rel, 0.999)))
 
 
 def assert_close(got, ref, rtol=RTOL, what=""):
     assert np.asarray(got).shape == np.asarray(ref).shape, (what, np.asarray(got).shape, np.asarray(ref).shape)
-    e = rel_err(got, ref)
-    assert e <= rtol, f"{what}: relative error {e:.3e} > {rtol:g}"
+    e = rel_err(got, ref, rtol)
+    assert e <= rtol, f"{what}: elementwise error {e:.3e} x (|ref| + {ATOL_FRAC} scale) exceeds rtol {rtol:g}; {error_profile(got, ref)}"
     return e
 
 
