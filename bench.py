@@ -519,6 +519,11 @@ def run_native(args):
                 if idx.numel() == 0:
                     continue
                 fan = idx.numel() / (n_src * B_loc)
+                if args.src_calls == "auto" and args.edge_types == 4 and n_src <= 128 and B_loc >= 64:
+                    sp = fgnn_b200.SourcePlan(idx, n_src)   # batched small graphs: aggregation fused into the first pass
+                    if sp.fusable(C, args.edge_types):
+                        plans[name] = sp
+                    continue
                 if (args.src_calls == "auto" and fan >= rule) or name in args.src_calls.split(","):
                     sp = fgnn_b200.SourcePlan(idx, n_src)
                     if args.src_calls != "auto" or sp.n_rows * 1.25 <= idx.numel():

@@ -17,6 +17,7 @@ I64, I32 = 0, 1
 KERNEL_AUTO, KERNEL_SIMT, KERNEL_TCGEN05 = 0, 1, 2
 FLAG_MASK_NEGATIVE = 1
 FLAG_ACCUMULATE = 2
+FLAG_NO_FUSED_REDUCE = 4
 
 OK = 0
 ERR_INVALID_ARG, ERR_INDEX_RANGE, ERR_SHAPE, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA, ERR_NO_DEVICE = (
@@ -45,7 +46,7 @@ class MpArgs(ctypes.Structure):
         ("src_ptr", ctypes.c_void_p), ("slot_edge", ctypes.c_void_p), ("etype_edges", ctypes.c_void_p),
         ("messages", ctypes.c_void_p), ("n_edges", ctypes.c_int64),
         ("src_rows", ctypes.c_void_p), ("n_src_rows", ctypes.c_int64), ("src_row_cap", ctypes.c_int32),
-        ("reserved2_", ctypes.c_int32),
+        ("reserved2_", ctypes.c_int32), ("src_edge_slot", ctypes.c_void_p),
     ]
 
 

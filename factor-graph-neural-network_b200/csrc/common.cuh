@@ -40,6 +40,18 @@ __device__ __forceinline__ float apply_epilogue(float v, int o, const MpParams& 
   return v;
 }
 
+// One step of the online logsumexp of the softmax aggregator (mp_nn.py:80-83), with every rounding spelled out
+// (no FMA contraction left to the compiler): the kernels that must agree bit for bit all call this.
+__device__ __forceinline__ void softmax_push(float& a, float& s, float e, float gamma) {
+  const float z = __fmul_rn(gamma, e);
+  const float m = fmaxf(a, z);
+  s = __fmaf_rn(s, expf(__fsub_rn(a, m)), expf(__fsub_rn(z, m)));   // a = -inf on the first push: exp(-inf) = 0
+  a = m;
+}
+__device__ __forceinline__ float softmax_finish(float a, float s, float gamma) {
+  return __fmul_rn(__fadd_rn(logf(s), a), __frcp_rn(gamma));
+}
+
 // Online aggregator over the K slots of one destination (mp_nn.py:73-87).
 struct AggState {
   float a;   // max: running max | softmax: running max of gamma*e | mean: running sum
@@ -52,10 +64,7 @@ struct AggState {
     if (agg == FGNN_AGG_MAX) {
       a = fmaxf(a, e);
     } else if (agg == FGNN_AGG_SOFTMAX) {
-      const float z = gamma * e;
-      const float m = fmaxf(a, z);
-      s = s * expf(a - m) + expf(z - m);   // a = -inf on first push: exp(-inf) = 0
-      a = m;
+      softmax_push(a, s, e, gamma);
     } else {
       a += e;
       s += 1.f;
@@ -63,7 +72,7 @@ struct AggState {
   }
   __device__ __forceinline__ float finish(int agg, float gamma) const {
     if (agg == FGNN_AGG_MAX) return a;
-    if (agg == FGNN_AGG_SOFTMAX) return s > 0.f ? (logf(s) + a) / gamma : -INFINITY;
+    if (agg == FGNN_AGG_SOFTMAX) return s > 0.f ? softmax_finish(a, s, gamma) : -INFINITY;
     return s > 0.f ? a / s : 0.f;
   }
 };

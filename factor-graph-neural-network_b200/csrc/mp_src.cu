@@ -76,7 +76,15 @@ struct SrcParams {
   uint32_t rows;                       // B * N
   uint32_t vrows;                      // virtual rows (>= rows)
   int O, T;
+  // fused aggregation (FUSE): a tile = ONE batch element, whose destinations only read its own source rows
+  const int32_t* edge_slot;            // [E] slot (b*M + m)*K + k of every edge
+  uint32_t rpt;                        // source rows per tile: N (<= 128) when fused, 128 otherwise
+  int M, K;
 };
+
+// per-slot message staging of the fused path: [M*K slots][O floats], the 16-byte chunks of a slot's row XOR-swizzled
+// with the slot number (source threads write to scattered slots; the 16 reader threads of a slot read it whole)
+__host__ __device__ constexpr int src_fuse_staging_max() { return 74 * 1024; }
 
 // raw x stages by mode: the edge-splitting mode stages twice the edge types and its tiles take longer
 #ifdef FGNN_SRC_DBG_NST1
@@ -120,9 +128,10 @@ __device__ __forceinline__ void stg256(float* dst, const float (&v)[8]) {
 
 // T edge types, NCH accumulator chunks of 128 columns per CTA, ES: the two warps of a lane quadrant split the
 // row's EDGES (row cap 6) instead of alternating over the chunks (row cap 3)
-template <int T, int NCH, bool ES>
+template <int T, int NCH, bool ES, bool FUSE>
 __global__ void __launch_bounds__(tc::kThreads, 1)
-mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, const int n_workers, const int n_tiles) {
+mp_src_kernel(const SrcParams p, const MpParams mp, const uint8_t* __restrict__ wimg, const int S, const int n_workers,
+              const int n_tiles) {
   constexpr int NC = 128;                      // accumulator columns per chunk
   constexpr int COLS = NC * NCH;               // columns of W this CTA owns
   constexpr int CPC = NC / T;                  // output channels per chunk
@@ -139,7 +148,8 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
   uint8_t* sB = smem;                                        // [2 parts][COLS rows][128 B]  UMMA K-major SW128
   uint8_t* sA = sB + w_bytes(COLS, false);                   // [NST][128 rows][256 B]      raw x tiles
   uint8_t* sEt = sA + NST * STAGEB;                          // [<= 128 RC][T]              edge types of the tile's edges
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sEt + ETB);
+  uint8_t* sMsg = sEt + ETB;                                 // FUSE: [M*K slots][O floats]  messages of the tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMsg + (FUSE ? src_fuse_staging_max() : 0));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   const uint32_t bar0 = smem_u32(bars);
   // barrier slots of tc_common.cuh: the raw ring has at most two stages here, a spare slot carries the edge-type staging
@@ -199,11 +209,11 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
     const uint32_t sEt_u = smem_u32(sEt);
     // first edge of the tile (= of its row 0) and this row's edge range
     auto edge_range = [&](int tile, int32_t& et0, int32_t& e0, int32_t& e1) {
-      const uint32_t v = (uint32_t)tile * kTileM + r;
+      const uint32_t v = (uint32_t)tile * p.rpt + r;
       et0 = e0 = e1 = 0;
       if (tile < n_tiles) {
-        et0 = __ldg(p.vptr + (uint32_t)tile * kTileM);
-        if (v < p.vrows) { e0 = __ldg(p.vptr + v); e1 = __ldg(p.vptr + v + 1); }
+        et0 = __ldg(p.vptr + (uint32_t)tile * p.rpt);
+        if ((uint32_t)r < p.rpt && v < p.vrows) { e0 = __ldg(p.vptr + v); e1 = __ldg(p.vptr + v + 1); }
       }
     };
     int32_t et0n, e0n, e1n;
@@ -221,6 +231,15 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
       // 16-byte pieces of edge e XOR-swizzled by et_key(e) (et_permute_kernel), so that the row-per-thread reads of
       // a warp spread over the banks.
       if ((warp & 3) == 0) SRC_TRACE(it, 6 + 4 * eg);         // epilogue: tile start
+      // FUSE: where my edges' messages go -- their slot inside this tile's (batch element's) table
+      int32_t sl[kEB];
+      if constexpr (FUSE) {
+#pragma unroll
+        for (int i = 0; i < kEB; ++i) {
+          const int ks = ES ? eg + 2 * i : i;
+          sl[i] = i < n_mine ? __ldg(p.edge_slot + e0 + ks) - tile * (p.M * p.K) : 0;
+        }
+      }
       mbar_wait(et_full, it & 1);
       if ((warp & 3) == 0) SRC_TRACE(it, 7 + 4 * eg);         // edge types landed
       float et[kEB][T];
@@ -286,7 +305,16 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
             for (int i = 0; i < kEB; ++i) {
               if (i < n_mine) {
                 const int ks = ES ? eg + 2 * i : i;
-                stg256(msg_base + (int64_t)(e0 + ks) * p.O + chunk * CPC + (q / QPS) * 8, o[i]);
+                if constexpr (FUSE) {
+                  // eight channels = two 16-byte chunks of the slot's staging row, chunk index XOR (slot & swz)
+                  const int cg = (chunk * CPC + (q / QPS) * 8) >> 2;
+                  const uint32_t swz = (uint32_t)((p.O >> 2) < 16 ? (p.O >> 2) - 1 : 15), sk = (uint32_t)sl[i] & swz;
+                  float* row = reinterpret_cast<float*>(sMsg) + (size_t)sl[i] * p.O;
+                  *reinterpret_cast<float4*>(row + (((uint32_t)cg ^ sk) << 2)) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+                  *reinterpret_cast<float4*>(row + (((uint32_t)(cg + 1) ^ sk) << 2)) = make_float4(o[i][4], o[i][5], o[i][6], o[i][7]);
+                } else {
+                  stg256(msg_base + (int64_t)(e0 + ks) * p.O + chunk * CPC + (q / QPS) * 8, o[i]);
+                }
               }
             }
           }
@@ -296,6 +324,55 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
             mbar_arrive(t_empty(st));
           }
         }
+      }
+      if constexpr (FUSE) {
+        // ---- fused pass 2: every destination of this batch element aggregates its K staged messages (slot order, like
+        // the other kernels), then bias / eval-BN / activation and the store -- the messages never leave the SM
+        named_bar_sync(1, kEpiWarps * 32);                   // all of the tile's messages are staged
+        const int O4 = p.O >> 2, tasks = p.M * O4;
+        const uint32_t swz = (uint32_t)(O4 < 16 ? O4 - 1 : 15);
+        const float neg = mp.act == FGNN_ACT_NONE ? 1.f : (mp.act == FGNN_ACT_RELU ? 0.f : mp.slope);
+        for (int task = tid; task < tasks; task += kEpiWarps * 32) {
+          const int m = task / O4, c4 = task - m * O4;
+          float a[4], sx[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { a[c] = mp.agg == FGNN_AGG_MEAN ? 0.f : -INFINITY; sx[c] = 0.f; }
+          for (int k = 0; k < p.K; ++k) {
+            const uint32_t slot = (uint32_t)(m * p.K + k);
+            const float4 v4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sMsg) + (size_t)slot * p.O +
+                                                               (((uint32_t)c4 ^ (slot & swz)) << 2));
+            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (mp.agg == FGNN_AGG_MAX) {
+                a[c] = fmaxf(a[c], v[c]);
+              } else if (mp.agg == FGNN_AGG_SOFTMAX) {
+                softmax_push(a[c], sx[c], v[c], mp.gamma);
+              } else {
+                a[c] += v[c];
+              }
+            }
+          }
+          float y[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int oc = c4 * 4 + c;
+            float rr;
+            if (mp.agg == FGNN_AGG_MAX) rr = a[c];
+            else if (mp.agg == FGNN_AGG_SOFTMAX) rr = softmax_finish(a[c], sx[c], mp.gamma);
+            else rr = __fmul_rn(a[c], __frcp_rn((float)p.K));
+            const float bi = mp.bias ? mp.bias[oc] : 0.f, sc = mp.scale ? mp.scale[oc] : 1.f, sh = mp.scale ? mp.shift[oc] : 0.f;
+            float vv = fmaf(rr + bi, sc, sh);
+            y[c] = vv >= 0.f ? vv : vv * neg;
+          }
+          float* dst = mp.out + ((int64_t)tile * p.M + m) * mp.o_sm + c4 * 4;
+          if (mp.accumulate) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(y[0]), "f"(y[1]), "f"(y[2]), "f"(y[3]) : "memory");
+          } else {
+            *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
+          }
+        }
+        named_bar_sync(2, kEpiWarps * 32);                   // the staging may take the next tile's messages
       }
       if ((warp & 3) == 0) SRC_TRACE(it, 9 + 4 * eg);         // tile done
     }
@@ -358,9 +435,10 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
     auto meta_of = [&](int tile, Meta& m) {
       m.xr0 = m.xr1 = 0xffffffffu;
       if (tile >= n_tiles) return;
-      const uint32_t v0 = (uint32_t)tile * kTileM + pw * ROWS_W + lane, v1 = v0 + 32;
-      if (v0 < p.vrows) m.xr0 = v0 < p.rows ? v0 : (uint32_t)__ldg(p.xrow + (v0 - p.rows));
-      if (v1 < p.vrows) m.xr1 = v1 < p.rows ? v1 : (uint32_t)__ldg(p.xrow + (v1 - p.rows));
+      const uint32_t l0 = (uint32_t)(pw * ROWS_W + lane), l1 = l0 + 32;          // rows of the tile
+      const uint32_t v0 = (uint32_t)tile * p.rpt + l0, v1 = (uint32_t)tile * p.rpt + l1;
+      if (l0 < p.rpt && v0 < p.vrows) m.xr0 = v0 < p.rows ? v0 : (uint32_t)__ldg(p.xrow + (v0 - p.rows));
+      if (l1 < p.rpt && v1 < p.vrows) m.xr1 = v1 < p.rows ? v1 : (uint32_t)__ldg(p.xrow + (v1 - p.rows));
     };
     Meta cur, nxt;
     meta_of(worker, cur);
@@ -405,7 +483,7 @@ mp_src_kernel(const SrcParams p, const uint8_t* __restrict__ wimg, const int S, 
       auto range = [&](int tile, int32_t& a, int32_t& b) {
         a = b = 0;
         if (tile >= n_tiles) return;
-        const uint32_t v0 = (uint32_t)tile * kTileM, v1 = v0 + kTileM < p.vrows ? v0 + kTileM : p.vrows;
+        const uint32_t v0 = (uint32_t)tile * p.rpt, v1 = v0 + p.rpt < p.vrows ? v0 + p.rpt : p.vrows;
         a = __ldg(p.vptr + v0); b = __ldg(p.vptr + v1);
       };
       int32_t a, b, an, bn;
@@ -530,9 +608,7 @@ mp_reduce_kernel(const MpParams p, const float* __restrict__ msg, const int32_t*
           if (AGG == FGNN_AGG_MAX) {
             a[c] = fmaxf(a[c], v[j][c]);
           } else if (AGG == FGNN_AGG_SOFTMAX) {
-            const float z = p.gamma * v[j][c], mx = fmaxf(a[c], z);
-            s[c] = s[c] * expf(a[c] - mx) + expf(z - mx);
-            a[c] = mx;
+            softmax_push(a[c], s[c], v[j][c], p.gamma);
           } else {
             a[c] += v[j][c];
           }
@@ -544,8 +620,8 @@ mp_reduce_kernel(const MpParams p, const float* __restrict__ msg, const int32_t*
     for (int c = 0; c < 8; ++c) {
       float r;
       if (AGG == FGNN_AGG_MAX) r = a[c];
-      else if (AGG == FGNN_AGG_SOFTMAX) r = live > 0.f ? (logf(s[c]) + a[c]) * (1.f / p.gamma) : -INFINITY;
-      else r = a[c] * (live > 0.f ? 1.f / live : 0.f);
+      else if (AGG == FGNN_AGG_SOFTMAX) r = live > 0.f ? softmax_finish(a[c], s[c], p.gamma) : -INFINITY;
+      else r = __fmul_rn(a[c], live > 0.f ? __frcp_rn(live) : 0.f);
       const float bi = p.bias ? p.bias[o + c] : 0.f, sc = p.scale ? p.scale[o + c] : 1.f, sh = p.scale ? p.shift[o + c] : 0.f;
       float v = fmaf(r + bi, sc, sh);
       v = v >= 0.f ? v : v * neg;
@@ -579,17 +655,17 @@ __global__ void et_permute_kernel(const float* __restrict__ et, int64_t et_sb, c
   }
 }
 
-template <int T, int NCH, bool ES>
+template <int T, int NCH, bool ES, bool FUSE>
 constexpr size_t src_smem_bytes() {
   constexpr int RC = ES ? 2 * kEB : kEB;
   return 1024 + (size_t)tc::w_bytes(128 * NCH, false) + (size_t)src_x_stages(ES) * tc::stage_bytes(false) +
-         (size_t)tc::kTileM * RC * T * 4 + tc::kNumBars * 8 + 16;
+         (size_t)tc::kTileM * RC * T * 4 + (FUSE ? src_fuse_staging_max() : 0) + tc::kNumBars * 8 + 16;
 }
 
-template <int T, int NCH, bool ES>
-int launch_src(const SrcParams& sp, const uint8_t* wimg, int S, int workers, int tiles, cudaStream_t st) {
-  auto kern = mp_src_kernel<T, NCH, ES>;
-  constexpr size_t smem = src_smem_bytes<T, NCH, ES>();
+template <int T, int NCH, bool ES, bool FUSE = false>
+int launch_src(const SrcParams& sp, const MpParams& mp, const uint8_t* wimg, int S, int workers, int tiles, cudaStream_t st) {
+  auto kern = mp_src_kernel<T, NCH, ES, FUSE>;
+  constexpr size_t smem = src_smem_bytes<T, NCH, ES, FUSE>();
   static_assert(smem <= (size_t)tc::kSmemBudget, "shared memory budget");
   static bool attr_set = false;
   if (!attr_set) {
@@ -610,20 +686,20 @@ int launch_src(const SrcParams& sp, const uint8_t* wimg, int S, int workers, int
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = tc_pdl_enabled() ? 1 : 0;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, sp, wimg, S, workers, tiles);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, sp, mp, wimg, S, workers, tiles);
   count_launch();
   return e == cudaSuccess ? (int)FGNN_OK : (int)FGNN_ERR_CUDA;
 }
 
 template <int T, int NCH>
-int launch_src_es(bool es, const SrcParams& sp, const uint8_t* wimg, int S, int workers, int tiles, cudaStream_t st) {
-  return es ? launch_src<T, NCH, true>(sp, wimg, S, workers, tiles, st) : launch_src<T, NCH, false>(sp, wimg, S, workers, tiles, st);
+int launch_src_es(bool es, const SrcParams& sp, const MpParams& mp, const uint8_t* wimg, int S, int workers, int tiles, cudaStream_t st) {
+  return es ? launch_src<T, NCH, true>(sp, mp, wimg, S, workers, tiles, st) : launch_src<T, NCH, false>(sp, mp, wimg, S, workers, tiles, st);
 }
 
 }  // namespace
 
 bool src_supported(const fgnn_mp_args* a) {
-  if (!a->src_ptr || !a->slot_edge || !a->etype_edges || !a->messages) return false;
+  if (!a->src_ptr || !a->slot_edge || !a->etype_edges || (!a->messages && !a->src_edge_slot)) return false;
   if (a->extension != FGNN_NO_EXTENSION || a->dtype != FGNN_F32 || a->C != tc::kC) return false;
   if (a->aggregator == FGNN_AGG_NONE) return false;
   if (a->T != 16 && a->T != 8 && a->T != 4) return false;
@@ -637,7 +713,7 @@ bool src_supported(const fgnn_mp_args* a) {
   if ((int64_t)a->B * a->N * tc::row_bytes(false) >= (int64_t)UINT32_MAX) return false;
   if (a->n_edges <= 0 || a->n_edges >= INT32_MAX) return false;
   if ((reinterpret_cast<uintptr_t>(a->x) & 15) || (reinterpret_cast<uintptr_t>(a->out) & 15) ||
-      (reinterpret_cast<uintptr_t>(a->messages) & 31) || (reinterpret_cast<uintptr_t>(a->etype_edges) & 15))
+      (a->messages && (reinterpret_cast<uintptr_t>(a->messages) & 31)) || (reinterpret_cast<uintptr_t>(a->etype_edges) & 15))
     return false;
   if (a->out_so != 1 || (a->out_sm & 3)) return false;
   if (a->B > 1 && a->out_sb != (int64_t)a->M * a->out_sm) return false;
@@ -656,6 +732,7 @@ int launch_mp_src(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream)
   sp.rows = (uint32_t)((int64_t)p.B * p.N);
   sp.vrows = (uint32_t)a->n_src_rows;
   sp.O = p.O; sp.T = p.T;
+  sp.edge_slot = a->src_edge_slot; sp.rpt = tc::kTileM; sp.M = p.M; sp.K = p.K;
   const bool es = a->src_row_cap == 2 * kEB;
   // columns per CTA: 512 (the split-bf16 image of 512 columns is 128 KB), or all 256 of them
   const int cols = OT < 512 ? OT : 512;
@@ -663,16 +740,29 @@ int launch_mp_src(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream)
   int sms = tc_num_sms();
   if (a->sm_limit > 0 && a->sm_limit < sms) sms = a->sm_limit;
   if (S > sms) return FGNN_ERR_UNSUPPORTED;
+  // Fused aggregation: a table [B,M,K] is block-diagonal over the batch -- the destinations of batch element b read
+  // source rows of b only -- so when one batch element's sources fit a tile (N <= 128), the CTA owns all filter
+  // columns (O*T = 256: T = 4 at O = 64, the LDPC shape) and every slot is live, the messages go to shared memory and
+  // the CTA aggregates them itself: no message round trip through HBM, no second launch.
+  const bool fuse = !(a->flags & FGNN_FLAG_NO_FUSED_REDUCE) && a->src_edge_slot && S == 1 && p.T == 4 && NCH == 2 && p.N <= tc::kTileM &&
+                    a->n_src_rows == (int64_t)p.B * p.N && a->n_edges == (int64_t)p.B * p.M * p.K && !p.tile_k && !p.out_rows &&
+                    !p.mask_neg && (int64_t)p.M * p.K * p.O * 4 <= src_fuse_staging_max() && p.B >= 2;
+  if (fuse) {
+    sp.rpt = (uint32_t)p.N;
+    int workers = sms < p.B ? sms : p.B;
+    return es ? launch_src<4, 2, true, true>(sp, p, ws, 1, workers, p.B, stream) : launch_src<4, 2, false, true>(sp, p, ws, 1, workers, p.B, stream);
+  }
+  if (!sp.msg) return FGNN_ERR_INVALID_ARG;
   const int tiles = (int)((sp.vrows + tc::kTileM - 1) / tc::kTileM);
   int workers = sms / S;
   if (workers > tiles) workers = tiles;
   int rc = FGNN_ERR_UNSUPPORTED;
-  if (p.T == 16 && NCH == 4) rc = launch_src_es<16, 4>(es, sp, ws, S, workers, tiles, stream);
-  else if (p.T == 16 && NCH == 2) rc = launch_src_es<16, 2>(es, sp, ws, S, workers, tiles, stream);
-  else if (p.T == 8 && NCH == 4) rc = launch_src_es<8, 4>(es, sp, ws, S, workers, tiles, stream);
-  else if (p.T == 8 && NCH == 2) rc = launch_src_es<8, 2>(es, sp, ws, S, workers, tiles, stream);
-  else if (p.T == 4 && NCH == 4) rc = launch_src_es<4, 4>(es, sp, ws, S, workers, tiles, stream);
-  else if (p.T == 4 && NCH == 2) rc = launch_src_es<4, 2>(es, sp, ws, S, workers, tiles, stream);
+  if (p.T == 16 && NCH == 4) rc = launch_src_es<16, 4>(es, sp, p, ws, S, workers, tiles, stream);
+  else if (p.T == 16 && NCH == 2) rc = launch_src_es<16, 2>(es, sp, p, ws, S, workers, tiles, stream);
+  else if (p.T == 8 && NCH == 4) rc = launch_src_es<8, 4>(es, sp, p, ws, S, workers, tiles, stream);
+  else if (p.T == 8 && NCH == 2) rc = launch_src_es<8, 2>(es, sp, p, ws, S, workers, tiles, stream);
+  else if (p.T == 4 && NCH == 4) rc = launch_src_es<4, 4>(es, sp, p, ws, S, workers, tiles, stream);
+  else if (p.T == 4 && NCH == 2) rc = launch_src_es<4, 2>(es, sp, p, ws, S, workers, tiles, stream);
   if (rc != FGNN_OK) return rc;
   // pass 2
   const int64_t total = (int64_t)p.B * p.M * (p.O / 8);

@@ -299,11 +299,7 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
               if (AGG == FGNN_AGG_MAX) {
                 acc[c] = live ? fmaxf(acc[c], e) : acc[c];
               } else if (AGG == FGNN_AGG_SOFTMAX) {
-                if (live) {
-                  const float z = p.gamma * e, mx = fmaxf(acc[c], z);
-                  acc2[c] = acc2[c] * expf(acc[c] - mx) + expf(z - mx);
-                  acc[c] = mx;
-                }
+                if (live) softmax_push(acc[c], acc2[c], e, p.gamma);
               } else {
                 acc[c] += live ? e : 0.f;
               }
@@ -323,7 +319,7 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
         constexpr int SW = (CPR < 8 ? CPR : 8) - 1;          // chunk-index bits XOR-ed with the row
         uint8_t* stage = sOut + wq * (32 * CPR * 16);        // this quarter's [32 rows][CPR chunks]
         const float4* epi4 = reinterpret_cast<const float4*>(s_epi);
-        const float inv_gamma = 1.f / p.gamma, inv_live = live_count > 0.f ? 1.f / live_count : 0.f;
+        const float inv_live = live_count > 0.f ? __frcp_rn(live_count) : 0.f;
         // negative-side slope of the activation: 1 = none, 0 = ReLU, slope = LeakyReLU
         const float neg = p.act == FGNN_ACT_NONE ? 1.f : (p.act == FGNN_ACT_RELU ? 0.f : p.slope);
         named_bar_sync(1 + wq, 64);                          // both warps of the quarter are done reading the previous tile
@@ -350,8 +346,8 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
             const int la = g * 4 + j;                        // accumulator index (compile time)
             float a;
             if (AGG == FGNN_AGG_MAX) a = acc[la];
-            else if (AGG == FGNN_AGG_SOFTMAX) a = live_count > 0.f ? (logf(acc2[la]) + acc[la]) * inv_gamma : -INFINITY;
-            else a = acc[la] * inv_live;
+            else if (AGG == FGNN_AGG_SOFTMAX) a = live_count > 0.f ? softmax_finish(acc[la], acc2[la], p.gamma) : -INFINITY;
+            else a = __fmul_rn(acc[la], inv_live);
             float y = fmaf(a + bia[j], sca[j], shi[j]);      // bias, then eval BN folded to scale/shift
             y = y >= 0.f ? y : y * neg;
             v[j] = a == -INFINITY ? a : y;                   // no live slot on this shard: stay -inf

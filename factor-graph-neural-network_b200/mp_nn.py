@@ -288,6 +288,14 @@ class SourcePlan:
         cls._cache[key] = (ref, nn_idx._version, nn_idx.data_ptr(), n_src, plan)
         return plan
 
+    FUSE_STAGING_BYTES = 74 * 1024
+
+    def fusable(self, O, T):
+        """True when the library aggregates inside the first pass (fgnn_mp_args.src_edge_slot): one batch element per
+        tile (N <= 128), all filter columns in one CTA (O*T = 256 at T = 4), every slot live, no virtual rows."""
+        return (T == 4 and O * T == 256 and self.n_src <= 128 and self.B >= 2 and self.n_rows == self.B * self.n_src
+                and self.n_edges == self.B * self.M * self.K and self.M * self.K * O * 4 <= self.FUSE_STAGING_BYTES)
+
     def messages(self, O):
         if self._msg is None or self._msg.numel() < self.n_edges * O:
             self._msg = torch.empty(max(8, self.n_edges * O), dtype=torch.float32, device=self.src_ptr.device)
@@ -313,7 +321,7 @@ def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=Non
                extension=0, aggregator=_lib.AGG_MAX, activation=_lib.ACT_RELU, act_slope=0.01,
                gamma=_SOFTMAX_GAMMA, kernel=_lib.KERNEL_AUTO, mask_negative=False, validate=True,
                out=None, accumulate=False, workspace=None, filters_version=0, tile_slots=None, out_rows=None, sm_limit=0,
-               plan=None):
+               plan=None, fused_reduce=True):
     """Functional form of the hot path: one `fgnn_mp_forward` call on x's device / current stream.
 
     x [B,C,N,1] or [B,C,N] (any strides; node-major == channels_last is the fast layout),
@@ -448,7 +456,8 @@ def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=Non
     a.dtype = _lib.F32 if x3.dtype == torch.float32 else _lib.BF16
     a.idx_dtype = _lib.I64 if nn_idx.dtype == torch.int64 else _lib.I32
     a.kernel = int(kernel)
-    a.flags = (_lib.FLAG_MASK_NEGATIVE if mask_negative else 0) | (_lib.FLAG_ACCUMULATE if accumulate else 0)
+    a.flags = ((_lib.FLAG_MASK_NEGATIVE if mask_negative else 0) | (_lib.FLAG_ACCUMULATE if accumulate else 0) |
+               (0 if fused_reduce else _lib.FLAG_NO_FUSED_REDUCE))
     if accumulate and out_given is None:
         raise ValueError("accumulate=True needs an `out` tensor to add into")
     a.gamma, a.act_slope = float(gamma), float(act_slope)
@@ -463,9 +472,11 @@ def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=Non
             raise ValueError("plan was built for another index table")
         if x3.dtype != torch.float32:
             raise TypeError("the source-stationary path is fp32")
-        keep = (plan.etype_edges(etype, et_sb), plan.messages(O))
+        fusable = fused_reduce and plan.fusable(O, T) and tile_slots is None and out_rows is None and not mask_negative
+        keep = (plan.etype_edges(etype, et_sb), None if fusable else plan.messages(O))
         a.src_ptr, a.slot_edge = plan.src_ptr.data_ptr(), plan.slot_edge.data_ptr()
-        a.etype_edges, a.messages, a.n_edges = keep[0].data_ptr(), keep[1].data_ptr(), plan.n_edges
+        a.etype_edges, a.messages, a.n_edges = keep[0].data_ptr(), (keep[1].data_ptr() if keep[1] is not None else None), plan.n_edges
+        a.src_edge_slot = plan.edge_slot.data_ptr()
         a.src_rows = plan.src_rows.data_ptr() if plan.src_rows.numel() else None
         a.n_src_rows, a.src_row_cap = plan.n_rows, plan.row_cap
     with torch.cuda.device(dev):
@@ -759,6 +770,14 @@ class mp_conv_v2(base_mp_nn):
             return None
         n_src = x.shape[2]
         B, M, K = nn_idx.shape
+        if mode == "auto" and T == 4 and OT == 256 and n_src <= 128 and B >= 64 and M * K * self.nou * 4 <= SourcePlan.FUSE_STAGING_BYTES:
+            # batched small graphs (LDPC decoding): messages stay in shared memory, the first pass aggregates itself
+            if self.index_check is not True and not _table_seen(nn_idx, n_src, False):
+                return None
+            if _table_use_count(nn_idx) < self.AUTO_MIN_USES:
+                return None
+            plan = SourcePlan.for_table(nn_idx, n_src)
+            return plan if plan.fusable(self.nou, T) else None
         if mode == "auto":
             if B * M * K < self.AUTO_MIN_SLOTS or B * M * K < self.AUTO_FAN_OUT[T] * B * n_src:
                 return None

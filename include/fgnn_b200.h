@@ -75,7 +75,9 @@ enum {
   FGNN_FLAG_MASK_NEGATIVE = 1u,
   /* out += result instead of out = result: fuses the caller's `nfeature = nfeature + nv`
      (FactorNN, factor_mpnn_sp.py:147,151) into the store.  Not valid with FGNN_AGG_NONE. */
-  FGNN_FLAG_ACCUMULATE = 2u
+  FGNN_FLAG_ACCUMULATE = 2u,
+  /* source-stationary calls only: never aggregate inside the first pass (see src_edge_slot); for tests / comparisons */
+  FGNN_FLAG_NO_FUSED_REDUCE = 4u
 };
 
 /* One message-passing call: out[b,o,m] = act(BN(bias[o] + AGG_k sum_t etype[b,t,m,k] *
@@ -142,6 +144,10 @@ typedef struct fgnn_mp_args {
   int32_t src_row_cap;       /* 3: tables with few edges per row; 6: the epilogue splits a row's edges over two warps
                                 (tables whose rows mostly have 4-6 edges)                                        */
   int32_t reserved2_;
+  const int32_t* src_edge_slot; /* [E]: slot (b*M + m)*K + k of every edge (optional).  With it, a call whose batch elements
+                                each fit one tile (N <= 128), whose CTA owns all filter columns (O*T = 256) and whose slots are
+                                all live keeps the messages in shared memory and aggregates inside the first pass: the
+                                per-codeword graphs of LDPC decoding (train_ldpc.py) never send a message through HBM.      */
 } fgnn_mp_args;
 
 int fgnn_version(void);

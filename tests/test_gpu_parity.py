@@ -563,6 +563,52 @@ def test_source_stationary_masked_accumulate_and_module_auto():
     assert torch.equal(y_auto, y_off)
 
 
+@pytest.mark.parametrize("agg", ["max", "softmax", "mean"])
+@pytest.mark.parametrize("direction", ["v2f", "f2v"])
+def test_fused_aggregation_ldpc_shapes(direction, agg):
+    """The LDPC decoding graph (96.3.963 tables of the golden fixture, batch of codewords, T = 4): with a plan the
+    first pass keeps the messages in shared memory and aggregates per codeword inside the CTA (one launch, no message
+    buffer) -- bit-identical to the two-pass evaluation and to the destination-stationary kernel, and within 1e-4 of
+    the oracle.  V->F: 96 source rows per codeword, 3 edges each; F->V: 48 source rows, 6 edges each (edge split)."""
+    g = load_npz("ldpc_factornn.npz")
+    rng = np.random.default_rng(7 + len(agg))
+    B, C, O, T = 37, 64, 64, 4
+    tbl = g["idx_v2f"] if direction == "v2f" else g["idx_f2v"]          # [48,6] values < 96  |  [96,3] values < 48
+    M, K = tbl.shape
+    N = 96 if direction == "v2f" else 48
+    idx = np.broadcast_to(tbl[None], (B, M, K)).copy()
+    x = rng.standard_normal((B, C, N, 1)).astype(np.float32)
+    et = rng.standard_normal((B, T, M, K)).astype(np.float32)
+    W = (rng.uniform(-1, 1, (C, O * T)) * 0.1).astype(np.float32)
+    bias = rng.uniform(-0.2, 0.2, O).astype(np.float32)
+    bn = dict(weight=rng.uniform(0.8, 1.2, O).astype(np.float32), bias=rng.uniform(-0.2, 0.2, O).astype(np.float32),
+              running_mean=rng.uniform(-0.1, 0.1, O).astype(np.float32), running_var=rng.uniform(0.5, 1.5, O).astype(np.float32))
+    code = {"max": 0, "softmax": 1, "mean": 2}[agg]
+    d_idx = t(idx)
+    plan = fgnn_b200.SourcePlan(d_idx, N)
+    assert plan.fusable(O, T) and plan.row_cap == (3 if direction == "v2f" else 6)
+    scale = bn["weight"] / np.sqrt(bn["running_var"] + 1e-5)
+    shift = bn["bias"] - bn["running_mean"] * scale
+    args = (t(x).contiguous(memory_format=torch.channels_last), d_idx, t(et), t(W), t(bias), t(scale.astype(np.float32)),
+            t(shift.astype(np.float32)))
+    y_dst = fgnn_b200.mp_forward(*args, extension=0, aggregator=code, kernel=_lib.KERNEL_TCGEN05)
+    y_fused = fgnn_b200.mp_forward(*args, extension=0, aggregator=code, plan=plan)
+    assert plan._msg is None                                       # no message buffer was ever allocated
+    l0 = fgnn_b200.launch_count()
+    y_fused = fgnn_b200.mp_forward(*args, extension=0, aggregator=code, plan=plan)
+    l1 = fgnn_b200.launch_count()
+    y_two = fgnn_b200.mp_forward(*args, extension=0, aggregator=code, plan=plan, fused_reduce=False)
+    l2 = fgnn_b200.launch_count()
+    assert plan._msg is not None and (l1 - l0) == (l2 - l1) - 1    # one launch fewer: no second pass
+    assert torch.equal(y_fused, y_dst), f"max |diff| = {float((y_fused - y_dst).abs().max())}"
+    assert torch.equal(y_two, y_dst)
+    ref = orc.mp_conv_forward_c(x, idx, et, W, bias, bn, extension=0, aggregator=agg)
+    assert_close(y_fused.cpu().numpy(), ref, RTOL, f"fused {direction} {agg}")
+    acc = torch.full_like(y_dst, 0.5)
+    fgnn_b200.mp_forward(*args, extension=0, aggregator=code, plan=plan, out=acc, accumulate=True)
+    assert torch.allclose(acc, y_dst + 0.5, rtol=0, atol=1e-6)
+
+
 def test_source_stationary_column_slices():
     """O*T must be 256 or a multiple of 512 (a CTA owns 256 or 512 filter columns; round-1 advice: widths like
     O = 48 at T = 16 silently skipped the trailing 256 columns).  O = 48: the explicit plan raises and the module
