@@ -520,7 +520,7 @@ def run_native(args):
                     continue
                 fan = idx.numel() / (n_src * B_loc)
                 if args.src_calls == "auto" and args.edge_types == 4 and n_src <= 128 and B_loc >= 64:
-                    sp = fgnn_b200.SourcePlan(idx, n_src)   # batched small graphs: aggregation fused into the first pass
+                    sp = fgnn_b200.SourcePlan(idx, n_src, batch_local=True)   # batched small graphs: aggregation fused into the first pass
                     if sp.fusable(C, args.edge_types):
                         plans[name] = sp
                     continue

@@ -46,7 +46,7 @@ class MpArgs(ctypes.Structure):
         ("src_ptr", ctypes.c_void_p), ("slot_edge", ctypes.c_void_p), ("etype_edges", ctypes.c_void_p),
         ("messages", ctypes.c_void_p), ("n_edges", ctypes.c_int64),
         ("src_rows", ctypes.c_void_p), ("n_src_rows", ctypes.c_int64), ("src_row_cap", ctypes.c_int32),
-        ("reserved2_", ctypes.c_int32), ("src_edge_slot", ctypes.c_void_p),
+        ("src_rows_per_batch", ctypes.c_int32), ("src_edge_slot", ctypes.c_void_p),
     ]
 
 

@@ -87,7 +87,7 @@ size_t tc_workspace_bytes(const fgnn_mp_args* a);
 int launch_mp_tc(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream);
 void tc_set_pdl(bool on);
 bool tc_pdl_enabled();
-int tc_prepare_weights(const float* W, uint8_t* ws, int C, int OT, int64_t version, cudaStream_t stream, int diff = 0);
+int tc_prepare_weights(const float* W, uint8_t* ws, int C, int OT, int64_t version, cudaStream_t stream, int diff = 0, int T = 0);
 int tc_num_sms();
 
 // source-stationary path (mp_src.cu)

@@ -82,8 +82,9 @@ struct SrcParams {
   int M, K;
 };
 
-// per-slot message staging of the fused path: [M*K slots][O floats], the 16-byte chunks of a slot's row XOR-swizzled
-// with the slot number (source threads write to scattered slots; the 16 reader threads of a slot read it whole)
+// per-slot message staging of the fused path: one region per accumulator chunk, [M*K slots][channels of the chunk],
+// the 16-byte pieces of a slot's row XOR-swizzled with the slot number (source threads write to scattered slots; the
+// reader threads of a slot read its row whole)
 __host__ __device__ constexpr int src_fuse_staging_max() { return 74 * 1024; }
 
 // raw x stages by mode: the edge-splitting mode stages twice the edge types and its tiles take longer
@@ -140,6 +141,7 @@ mp_src_kernel(const SrcParams p, const MpParams mp, const uint8_t* __restrict__ 
   constexpr int EB = T * 4;                    // bytes of one edge-type vector
   constexpr int ETB = kTileM * RC * EB;        // edge-type staging: the tile's (at most 128 RC) vectors, contiguous
   constexpr int NST = src_x_stages(ES);        // raw x stages (a tile's rows must be in flight while the previous one converts)
+  constexpr int ETS = FUSE ? 2 : 1;            // edge-type staging stages (fused tiles are short: the copy needs a tile's head start)
   constexpr int ROWB = row_bytes(false), STAGEB = stage_bytes(false);
   static_assert(16 % T == 0 && T >= 4 && CPH % 4 == 0 && NCH % 2 == 0, "unsupported shape");
 
@@ -148,14 +150,15 @@ mp_src_kernel(const SrcParams p, const MpParams mp, const uint8_t* __restrict__ 
   uint8_t* sB = smem;                                        // [2 parts][COLS rows][128 B]  UMMA K-major SW128
   uint8_t* sA = sB + w_bytes(COLS, false);                   // [NST][128 rows][256 B]      raw x tiles
   uint8_t* sEt = sA + NST * STAGEB;                          // [<= 128 RC][T]              edge types of the tile's edges
-  uint8_t* sMsg = sEt + ETB;                                 // FUSE: [M*K slots][O floats]  messages of the tile
+  uint8_t* sMsg = sEt + ETS * ETB;                           // FUSE: [M*K slots][O floats]  messages of the tile
   uint64_t* bars = reinterpret_cast<uint64_t*>(sMsg + (FUSE ? src_fuse_staging_max() : 0));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   const uint32_t bar0 = smem_u32(bars);
   // barrier slots of tc_common.cuh: the raw ring has at most two stages here, a spare slot carries the edge-type staging
   auto raw_full = [&](uint32_t s) { return bar0 + 8u * s; };
   auto raw_empty = [&](uint32_t s) { return bar0 + 8u * (kMaxAStages + s); };
-  const uint32_t et_full = bar0 + 8u * 2, et_empty = bar0 + 8u * (kMaxAStages + 2);
+  auto et_full = [&](uint32_t s) { return bar0 + 8u * (2 + s); };
+  auto et_empty = [&](uint32_t s) { return bar0 + 8u * (kMaxAStages + 2 + s); };
   auto ta_full = [&](uint32_t s) { return bar0 + 8u * (2 * kMaxAStages + s); };
   auto ta_empty = [&](uint32_t s) { return bar0 + 8u * (2 * kMaxAStages + kTA + s); };
   auto t_full = [&](uint32_t s) { return bar0 + 8u * (2 * kMaxAStages + 2 * kTA + s); };
@@ -173,8 +176,10 @@ mp_src_kernel(const SrcParams p, const MpParams mp, const uint8_t* __restrict__ 
       mbar_init(raw_full(s), kGatherWarps * 32);
       mbar_init(raw_empty(s), 128);
     }
-    mbar_init(et_full, 1);                                   // one arrive.expect_tx + the bytes of the bulk copy
-    mbar_init(et_empty, kEpiWarps * 32);
+    for (int s = 0; s < ETS; ++s) {
+      mbar_init(et_full(s), 1);                              // one arrive.expect_tx + the bytes of the bulk copy
+      mbar_init(et_empty(s), kEpiWarps * 32);
+    }
     for (int s = 0; s < kTA; ++s) {
       mbar_init(ta_full(s), 128);
       mbar_init(ta_empty(s), 1);
@@ -216,14 +221,35 @@ mp_src_kernel(const SrcParams p, const MpParams mp, const uint8_t* __restrict__ 
         if ((uint32_t)r < p.rpt && v < p.vrows) { e0 = __ldg(p.vptr + v); e1 = __ldg(p.vptr + v + 1); }
       }
     };
-    int32_t et0n, e0n, e1n;
+    // edge ranges are fetched TWO tiles ahead, the slots of a tile's edges one tile ahead: no tile starts with a load
+    // that depends on a load of the same iteration
+    int32_t et0n, e0n, e1n, et0f, e0f, e1f;
     edge_range(worker, et0n, e0n, e1n);
+    edge_range(worker + n_workers, et0f, e0f, e1f);
+    int32_t sl_nx[kEB] = {0, 0, 0};
+    // FUSE: a thread of the aggregation phase always handles the same four channels (128 threads, CPC/4 pieces per row):
+    // their bias / BN scale / BN shift live in registers for the whole kernel
+    float e_bi[4] = {0.f, 0.f, 0.f, 0.f}, e_sc[4] = {1.f, 1.f, 1.f, 1.f}, e_sh[4] = {0.f, 0.f, 0.f, 0.f};
+    if constexpr (FUSE) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int oc = eg * CPC + ((tid & 127) % (CPC / 4)) * 4 + c;
+        if (mp.bias) e_bi[c] = mp.bias[oc];
+        if (mp.scale) { e_sc[c] = mp.scale[oc]; e_sh[c] = mp.shift[oc]; }
+      }
+    }
+    if constexpr (FUSE) {
+      static_assert(!FUSE || !ES, "the fused path alternates over the chunks (row cap 3)");
+#pragma unroll
+      for (int i = 0; i < kEB; ++i) sl_nx[i] = e0n + i < e1n ? __ldg(p.edge_slot + e0n + i) : 0;
+    }
     uint32_t it = 0;
     bool waited = false;
     float* const msg_base = p.msg + ch0;
     for (int tile = worker; tile < n_tiles; tile += n_workers, ++it) {
       const int32_t e0 = e0n, ne = e1n - e0n, el0 = e0n - et0n;        // el0: the row's first edge within the tile
-      edge_range(tile + n_workers, et0n, e0n, e1n);          // next tile's range: in flight during this tile
+      et0n = et0f; e0n = e0f; e1n = e1f;                     // the next tile's range (loaded a tile ago) ...
+      edge_range(tile + 2 * n_workers, et0f, e0f, e1f);      // ... and the one after it goes in flight
       // my edges: slot ks(i) = ES ? eg + 2 i : i of the row, i < n_mine
       const int n_mine = ES ? (ne > eg ? (ne - eg + 1) >> 1 : 0) : ne;
       const int n_warp = __reduce_max_sync(0xffffffffu, n_mine);
@@ -231,16 +257,17 @@ mp_src_kernel(const SrcParams p, const MpParams mp, const uint8_t* __restrict__ 
       // 16-byte pieces of edge e XOR-swizzled by et_key(e) (et_permute_kernel), so that the row-per-thread reads of
       // a warp spread over the banks.
       if ((warp & 3) == 0) SRC_TRACE(it, 6 + 4 * eg);         // epilogue: tile start
-      // FUSE: where my edges' messages go -- their slot inside this tile's (batch element's) table
+      // FUSE: where my edges' messages go -- their slot inside this tile's (batch element's) table; the slots of the
+      // NEXT tile's edges are fetched now (their range is already known), so no tile starts with a dependent load
       int32_t sl[kEB];
       if constexpr (FUSE) {
 #pragma unroll
-        for (int i = 0; i < kEB; ++i) {
-          const int ks = ES ? eg + 2 * i : i;
-          sl[i] = i < n_mine ? __ldg(p.edge_slot + e0 + ks) - tile * (p.M * p.K) : 0;
-        }
+        for (int i = 0; i < kEB; ++i) sl[i] = sl_nx[i] - tile * (p.M * p.K);
+#pragma unroll
+        for (int i = 0; i < kEB; ++i) sl_nx[i] = e0n + i < e1n ? __ldg(p.edge_slot + e0n + i) : 0;
       }
-      mbar_wait(et_full, it & 1);
+      const uint32_t es = it % ETS;
+      mbar_wait(et_full(es), (it / ETS) & 1);
       if ((warp & 3) == 0) SRC_TRACE(it, 7 + 4 * eg);         // edge types landed
       float et[kEB][T];
 #pragma unroll
@@ -250,7 +277,7 @@ mp_src_kernel(const SrcParams p, const MpParams mp, const uint8_t* __restrict__ 
           const uint32_t key = et_key<T>((uint32_t)(e0 + ks));
 #pragma unroll
           for (int t4 = 0; t4 < T / 4; ++t4) {
-            const float4 v = lds_f4(sEt_u + (uint32_t)(el0 + ks) * EB + (((uint32_t)t4 ^ key) << 4));
+            const float4 v = lds_f4(sEt_u + es * ETB + (uint32_t)(el0 + ks) * EB + (((uint32_t)t4 ^ key) << 4));
             et[i][4 * t4] = v.x; et[i][4 * t4 + 1] = v.y; et[i][4 * t4 + 2] = v.z; et[i][4 * t4 + 3] = v.w;
           }
         } else {
@@ -266,7 +293,7 @@ mp_src_kernel(const SrcParams p, const MpParams mp, const uint8_t* __restrict__ 
 #pragma unroll
       for (int i = 0; i < kEB; ++i) touch_reg(et[i][T - 1]);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(et_empty);                                 // the next tile's edge types may be staged
+      mbar_arrive(et_empty(es));                             // the staging stage may take another tile's edge types
       if (!waited) { pdl_wait(); waited = true; }            // first store: the preceding launch may still read msg
 #pragma unroll 1
 #ifdef FGNN_SRC_DBG_NOALT
@@ -295,9 +322,18 @@ mp_src_kernel(const SrcParams p, const MpParams mp, const uint8_t* __restrict__ 
 #pragma unroll
           for (int i = 0; i < kEB; ++i) {
             if (i < n_warp) {                                // warp-uniform
+              if constexpr (T == 4) {                        // channel pairs (tc_common.cuh), as in mp_tc.cu: bit-identical
+                uint64_t et2[4];
 #pragma unroll
-              for (int c = 0; c < CPQ; ++c)                  // channel c of this quarter: columns c*T .. c*T+T-1
-                o[i][(q % QPS) * CPQ + c] = contract_types<T>(et[i], &d[q & 1][c * T]);      // same function as mp_tc.cu: bit-identical
+                for (int t = 0; t < 4; ++t) et2[t] = pack2(et[i][t], et[i][t]);
+#pragma unroll
+                for (int c2 = 0; c2 < CPQ / 2; ++c2)
+                  unpack2(contract_pair4(et2, &d[q & 1][c2 * 8]), o[i][(q % QPS) * CPQ + 2 * c2], o[i][(q % QPS) * CPQ + 2 * c2 + 1]);
+              } else {
+#pragma unroll
+                for (int c = 0; c < CPQ; ++c)                // channel c of this quarter: columns c*T .. c*T+T-1
+                  o[i][(q % QPS) * CPQ + c] = contract_types<T>(et[i], &d[q & 1][c * T]);      // same function as mp_tc.cu: bit-identical
+              }
             }
           }
           if ((q + 1) % QPS == 0) {
@@ -306,12 +342,13 @@ mp_src_kernel(const SrcParams p, const MpParams mp, const uint8_t* __restrict__ 
               if (i < n_mine) {
                 const int ks = ES ? eg + 2 * i : i;
                 if constexpr (FUSE) {
-                  // eight channels = two 16-byte chunks of the slot's staging row, chunk index XOR (slot & swz)
-                  const int cg = (chunk * CPC + (q / QPS) * 8) >> 2;
-                  const uint32_t swz = (uint32_t)((p.O >> 2) < 16 ? (p.O >> 2) - 1 : 15), sk = (uint32_t)sl[i] & swz;
-                  float* row = reinterpret_cast<float*>(sMsg) + (size_t)sl[i] * p.O;
-                  *reinterpret_cast<float4*>(row + (((uint32_t)cg ^ sk) << 2)) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
-                  *reinterpret_cast<float4*>(row + (((uint32_t)(cg + 1) ^ sk) << 2)) = make_float4(o[i][4], o[i][5], o[i][6], o[i][7]);
+                  // eight channels = two 16-byte pieces of the slot's row in this chunk's region (CPC channels per row),
+                  // piece index XOR (slot & 7)
+                  constexpr uint32_t PPR = CPC / 4;                     // pieces per row: 8 at T = 4
+                  const uint32_t pc = (uint32_t)(q / QPS) * 2, sk = (uint32_t)sl[i] & (PPR - 1);
+                  const uint32_t row = smem_u32(sMsg) + (uint32_t)chunk * (uint32_t)(p.M * p.K) * (CPC * 4) + (uint32_t)sl[i] * (CPC * 4);
+                  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((pc ^ sk) << 4)), "f"(o[i][0]), "f"(o[i][1]), "f"(o[i][2]), "f"(o[i][3]) : "memory");
+                  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((pc + 1) ^ sk) << 4)), "f"(o[i][4]), "f"(o[i][5]), "f"(o[i][6]), "f"(o[i][7]) : "memory");
                 } else {
                   stg256(msg_base + (int64_t)(e0 + ks) * p.O + chunk * CPC + (q / QPS) * 8, o[i]);
                 }
@@ -326,53 +363,61 @@ mp_src_kernel(const SrcParams p, const MpParams mp, const uint8_t* __restrict__ 
         }
       }
       if constexpr (FUSE) {
-        // ---- fused pass 2: every destination of this batch element aggregates its K staged messages (slot order, like
-        // the other kernels), then bias / eval-BN / activation and the store -- the messages never leave the SM
-        named_bar_sync(1, kEpiWarps * 32);                   // all of the tile's messages are staged
-        const int O4 = p.O >> 2, tasks = p.M * O4;
-        const uint32_t swz = (uint32_t)(O4 < 16 ? O4 - 1 : 15);
+        // ---- fused pass 2, per warp group and chunk: group eg has staged the messages of chunk eg (its CPC channels of
+        // every slot); its 128 threads now aggregate every destination's K slots for those channels (slot order, like
+        // the other kernels), apply bias / eval-BN / activation and store.  The two groups never wait for each other,
+        // so one group's tensor-memory reads overlap the other's aggregation.  (NCH == 2: chunk == eg.)
+        static_assert(!FUSE || (NCH == 2 && 128 % (CPC / 4) == 0), "one chunk per warp group; fixed channels per thread");
+        constexpr int PPR = CPC / 4;                         // 16-byte pieces per staged row
+        named_bar_sync(1 + eg, 4 * 32);                      // the group's messages of this tile are staged
+        const int tasks = p.M * PPR, gt = tid & 127;
         const float neg = mp.act == FGNN_ACT_NONE ? 1.f : (mp.act == FGNN_ACT_RELU ? 0.f : mp.slope);
-        for (int task = tid; task < tasks; task += kEpiWarps * 32) {
-          const int m = task / O4, c4 = task - m * O4;
-          float a[4], sx[4];
+        const uint32_t region = smem_u32(sMsg) + (uint32_t)eg * (uint32_t)(p.M * p.K) * (CPC * 4);
+        for (int task = gt; task < tasks; task += 128) {
+          const int m = task / PPR, c4 = task - m * PPR;
+          float y[4];
+          const uint32_t slot0 = (uint32_t)(m * p.K);
+          auto piece = [&](int k) {
+            const uint32_t slot = slot0 + (uint32_t)k;
+            return lds_f4(region + slot * (CPC * 4) + ((((uint32_t)c4) ^ (slot & (PPR - 1))) << 4));
+          };
+          if (mp.agg == FGNN_AGG_MAX) {                        // the FGNN aggregator: a lean loop of its own
+            float4 a = piece(0);
+            for (int k = 1; k < p.K; ++k) {
+              const float4 v = piece(k);
+              a.x = fmaxf(a.x, v.x); a.y = fmaxf(a.y, v.y); a.z = fmaxf(a.z, v.z); a.w = fmaxf(a.w, v.w);
+            }
+            y[0] = a.x; y[1] = a.y; y[2] = a.z; y[3] = a.w;
+          } else {
+            float a[4], sx[4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) { a[c] = mp.agg == FGNN_AGG_MEAN ? 0.f : -INFINITY; sx[c] = 0.f; }
-          for (int k = 0; k < p.K; ++k) {
-            const uint32_t slot = (uint32_t)(m * p.K + k);
-            const float4 v4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sMsg) + (size_t)slot * p.O +
-                                                               (((uint32_t)c4 ^ (slot & swz)) << 2));
-            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+            for (int c = 0; c < 4; ++c) { a[c] = mp.agg == FGNN_AGG_MEAN ? 0.f : -INFINITY; sx[c] = 0.f; }
+            for (int k = 0; k < p.K; ++k) {
+              const float4 v4 = piece(k);
+              const float v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              if (mp.agg == FGNN_AGG_MAX) {
-                a[c] = fmaxf(a[c], v[c]);
-              } else if (mp.agg == FGNN_AGG_SOFTMAX) {
-                softmax_push(a[c], sx[c], v[c], mp.gamma);
-              } else {
-                a[c] += v[c];
+              for (int c = 0; c < 4; ++c) {
+                if (mp.agg == FGNN_AGG_SOFTMAX) softmax_push(a[c], sx[c], v[c], mp.gamma);
+                else a[c] += v[c];
               }
             }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              y[c] = mp.agg == FGNN_AGG_SOFTMAX ? softmax_finish(a[c], sx[c], mp.gamma) : __fmul_rn(a[c], __frcp_rn((float)p.K));
           }
-          float y[4];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const int oc = c4 * 4 + c;
-            float rr;
-            if (mp.agg == FGNN_AGG_MAX) rr = a[c];
-            else if (mp.agg == FGNN_AGG_SOFTMAX) rr = softmax_finish(a[c], sx[c], mp.gamma);
-            else rr = __fmul_rn(a[c], __frcp_rn((float)p.K));
-            const float bi = mp.bias ? mp.bias[oc] : 0.f, sc = mp.scale ? mp.scale[oc] : 1.f, sh = mp.scale ? mp.shift[oc] : 0.f;
-            float vv = fmaf(rr + bi, sc, sh);
+            const float vv = fmaf(y[c] + e_bi[c], e_sc[c], e_sh[c]);
             y[c] = vv >= 0.f ? vv : vv * neg;
           }
-          float* dst = mp.out + ((int64_t)tile * p.M + m) * mp.o_sm + c4 * 4;
+          float* dst = mp.out + ((int64_t)tile * p.M + m) * mp.o_sm + eg * CPC + c4 * 4;
           if (mp.accumulate) {
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(y[0]), "f"(y[1]), "f"(y[2]), "f"(y[3]) : "memory");
           } else {
             *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
           }
         }
-        named_bar_sync(2, kEpiWarps * 32);                   // the staging may take the next tile's messages
+        named_bar_sync(1 + eg, 4 * 32);                      // the region may take the next tile's messages
       }
       if ((warp & 3) == 0) SRC_TRACE(it, 9 + 4 * eg);         // tile done
     }
@@ -491,14 +536,15 @@ mp_src_kernel(const SrcParams p, const MpParams mp, const uint8_t* __restrict__ 
       uint32_t i = 0;
       for (int tile = worker; tile < n_tiles; tile += n_workers, ++i) {
         range(tile + n_workers, an, bn);
-        mbar_wait(et_empty, (i & 1) ^ 1);
+        const uint32_t es = i % ETS;
+        mbar_wait(et_empty(es), ((i / ETS) & 1) ^ 1);
         SRC_TRACE(i, 14);                                    // edge-type staging free: bulk copy issued
         const uint32_t bytes = (uint32_t)(b - a) * EB;
         if (bytes) {
-          mbar_expect_tx(et_full, bytes);
-          bulk_g2s(sEt_u, reinterpret_cast<const uint8_t*>(p.et_edges) + (int64_t)a * EB, bytes, et_full);
+          mbar_expect_tx(et_full(es), bytes);
+          bulk_g2s(sEt_u + es * ETB, reinterpret_cast<const uint8_t*>(p.et_edges) + (int64_t)a * EB, bytes, et_full(es));
         } else {
-          mbar_arrive(et_full);
+          mbar_arrive(et_full(es));
         }
         a = an; b = bn;
       }
@@ -659,7 +705,7 @@ template <int T, int NCH, bool ES, bool FUSE>
 constexpr size_t src_smem_bytes() {
   constexpr int RC = ES ? 2 * kEB : kEB;
   return 1024 + (size_t)tc::w_bytes(128 * NCH, false) + (size_t)src_x_stages(ES) * tc::stage_bytes(false) +
-         (size_t)tc::kTileM * RC * T * 4 + (FUSE ? src_fuse_staging_max() : 0) + tc::kNumBars * 8 + 16;
+         (size_t)(FUSE ? 2 : 1) * tc::kTileM * RC * T * 4 + (FUSE ? src_fuse_staging_max() : 0) + tc::kNumBars * 8 + 16;
 }
 
 template <int T, int NCH, bool ES, bool FUSE = false>
@@ -724,7 +770,7 @@ int launch_mp_src(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream)
   uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
   if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255)) return FGNN_ERR_WORKSPACE;
   const int OT = p.O * p.T;
-  const int wrc = tc_prepare_weights(p.W, ws, tc::kC, OT, a->filters_version, stream);
+  const int wrc = tc_prepare_weights(p.W, ws, tc::kC, OT, a->filters_version, stream, 0, p.T);
   if (wrc != FGNN_OK) return wrc;
   SrcParams sp;
   sp.x = p.x; sp.vptr = a->src_ptr; sp.xrow = a->src_rows; sp.et_edges = reinterpret_cast<const float*>(a->etype_edges);
@@ -744,13 +790,19 @@ int launch_mp_src(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream)
   // source rows of b only -- so when one batch element's sources fit a tile (N <= 128), the CTA owns all filter
   // columns (O*T = 256: T = 4 at O = 64, the LDPC shape) and every slot is live, the messages go to shared memory and
   // the CTA aggregates them itself: no message round trip through HBM, no second launch.
-  const bool fuse = !(a->flags & FGNN_FLAG_NO_FUSED_REDUCE) && a->src_edge_slot && S == 1 && p.T == 4 && NCH == 2 && p.N <= tc::kTileM &&
-                    a->n_src_rows == (int64_t)p.B * p.N && a->n_edges == (int64_t)p.B * p.M * p.K && !p.tile_k && !p.out_rows &&
-                    !p.mask_neg && (int64_t)p.M * p.K * p.O * 4 <= src_fuse_staging_max() && p.B >= 2;
-  if (fuse) {
-    sp.rpt = (uint32_t)p.N;
+  // The plan for it (SourcePlan(batch_local=True)) numbers the virtual rows batch element by batch element --
+  // src_rows_per_batch of them each, row cap 3, src_rows naming the source row of EVERY virtual row.
+  const int rpb = a->src_rows_per_batch;
+  const bool fuse = !(a->flags & FGNN_FLAG_NO_FUSED_REDUCE) && a->src_edge_slot && rpb > 0 && rpb <= tc::kTileM && !es && S == 1 &&
+                    p.T == 4 && NCH == 2 && a->src_rows && a->n_src_rows == (int64_t)p.B * rpb &&
+                    a->n_edges == (int64_t)p.B * p.M * p.K && !p.tile_k && !p.out_rows && !p.mask_neg &&
+                    (int64_t)p.M * p.K * p.O * 4 <= src_fuse_staging_max();
+  if (rpb > 0) {
+    if (!fuse) return FGNN_ERR_UNSUPPORTED;                   // a batch-local plan only serves the fused path
+    sp.rpt = (uint32_t)rpb;
+    sp.rows = 0;                                              // every virtual row takes its source row from src_rows
     int workers = sms < p.B ? sms : p.B;
-    return es ? launch_src<4, 2, true, true>(sp, p, ws, 1, workers, p.B, stream) : launch_src<4, 2, false, true>(sp, p, ws, 1, workers, p.B, stream);
+    return launch_src<4, 2, false, true>(sp, p, ws, 1, workers, p.B, stream);
   }
   if (!sp.msg) return FGNN_ERR_INVALID_ARG;
   const int tiles = (int)((sp.vrows + tc::kTileM - 1) / tc::kTileM);

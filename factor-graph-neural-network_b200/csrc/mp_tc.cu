@@ -67,7 +67,7 @@ namespace fgnn {
 // ---------------------------------------------------------------------------------------------
 // diff != 0 (ORIG_WITH_DIFF, C = 2 x 64 filter rows): the image holds [W_top + W_bot ; -W_bot], so that
 // [x_i || x_j] . image == [x_i || x_i - x_j] . W  (mp_nn.py:136-159 evaluated as x_i (W_top + W_bot) - x_j W_bot).
-__global__ void w_split_kernel(const float* __restrict__ W, uint8_t* __restrict__ ws, int C, int OT, int64_t version, int diff) {
+__global__ void w_split_kernel(const float* __restrict__ W, uint8_t* __restrict__ ws, int C, int OT, int64_t version, int diff, int T) {
   tc::Header* h = reinterpret_cast<tc::Header*>(ws);
   if (version != 0 && h->version == version && h->filters == W && h->C == C && h->OT == OT) return;
   uint8_t* img = ws + tc::kHeaderBytes;
@@ -91,7 +91,8 @@ __global__ void w_split_kernel(const float* __restrict__ W, uint8_t* __restrict_
       lo[j] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
     }
     const int ka = chunk >> 3, cc = chunk & 7;
-    const size_t off = (size_t)ka * OT * 128 + (size_t)n * 128 + (size_t)((cc ^ (n & 7)) * 16);
+    const int ni = tc::image_column(n, T);                   // T = 4: channel pairs interleaved (tc_common.cuh)
+    const size_t off = (size_t)ka * OT * 128 + (size_t)ni * 128 + (size_t)((cc ^ (ni & 7)) * 16);
     *reinterpret_cast<uint4*>(img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(img + (size_t)KA * OT * 128 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
@@ -258,6 +259,11 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
         float et[T];
 #pragma unroll
         for (int t = 0; t < T; ++t) et[t] = et_nx[t];
+        uint64_t et2[4];
+        if constexpr (T == 4) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) et2[t] = pack2(et[t], et[t]);
+        }
         const bool live = live_nx;
         // prefetch the next item's edge types: their latency hides behind this item's math
         if (k + 1 < kt) fetch(tile, k + 1); else fetch(tile + n_workers, 0);
@@ -283,25 +289,38 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
           tc_fence_before();
           mbar_arrive(t_empty(st));
           ++ct;
+          auto fold = [&](int c, float e) {
+            if (AGG == FGNN_AGG_MAX) {
+              acc[c] = live ? fmaxf(acc[c], e) : acc[c];
+            } else if (AGG == FGNN_AGG_SOFTMAX) {
+              if (live) softmax_push(acc[c], acc2[c], e, p.gamma);
+            } else {
+              acc[c] += live ? e : 0.f;
+            }
+          };
 #pragma unroll
           for (int gq = 0; gq < NLD; ++gq) {
+            if constexpr (T == 4) {                          // channel pairs, one packed FMA per edge type (tc_common.cuh)
 #pragma unroll
-            for (int q = 0; q < CH_PER_LD; ++q) {
-              float e;
-              if constexpr (T >= 4) {                        // packed fp32x2 chains (tc_common.cuh)
-                e = contract_types<T>(et, &d[gq][q * T]);
-              } else {
-                e = 0.f;
-#pragma unroll
-                for (int t = 0; t < T; ++t) e = fmaf(et[t], __uint_as_float(d[gq][q * T + t]), e);
+              for (int q2 = 0; q2 < 2; ++q2) {
+                float e0, e1;
+                unpack2(contract_pair4(et2, &d[gq][q2 * 8]), e0, e1);
+                const int c = chunk * CPG + gq * CH_PER_LD + q2 * 2;
+                fold(c, e0);
+                fold(c + 1, e1);
               }
-              const int c = chunk * CPG + gq * CH_PER_LD + q;
-              if (AGG == FGNN_AGG_MAX) {
-                acc[c] = live ? fmaxf(acc[c], e) : acc[c];
-              } else if (AGG == FGNN_AGG_SOFTMAX) {
-                if (live) softmax_push(acc[c], acc2[c], e, p.gamma);
-              } else {
-                acc[c] += live ? e : 0.f;
+            } else {
+#pragma unroll
+              for (int q = 0; q < CH_PER_LD; ++q) {
+                float e;
+                if constexpr (T >= 4) {                      // packed fp32x2 chains (tc_common.cuh)
+                  e = contract_types<T>(et, &d[gq][q * T]);
+                } else {
+                  e = 0.f;
+#pragma unroll
+                  for (int t = 0; t < T; ++t) e = fmaf(et[t], __uint_as_float(d[gq][q * T + t]), e);
+                }
+                fold(chunk * CPG + gq * CH_PER_LD + q, e);
               }
             }
           }
@@ -727,8 +746,8 @@ extern "C" int fgnn_debug_trace_read(unsigned long long* host, size_t count) {
 // The bf16 image of `W` in `ws` is rebuilt unless this workspace is known to hold the image of exactly these
 // filters (pointer + caller-supplied version).  Host-side mirror of the device header: a cached image costs
 // no launch at all.  version == 0 always rebuilds.
-int tc_prepare_weights(const float* W, uint8_t* ws, int C, int OT, int64_t version, cudaStream_t stream, int diff) {
-  if (version != 0) version = version * 2 + (diff ? 1 : 0);                 // the image depends on the transform
+int tc_prepare_weights(const float* W, uint8_t* ws, int C, int OT, int64_t version, cudaStream_t stream, int diff, int T) {
+  if (version != 0) version = version * 4 + (diff ? 1 : 0) + (T == 4 ? 2 : 0);      // the image depends on the transform / layout
   static std::mutex mu;
   static std::unordered_map<const void*, tc::Header> known;
   bool fresh = false;
@@ -746,7 +765,7 @@ int tc_prepare_weights(const float* W, uint8_t* ws, int C, int OT, int64_t versi
     known.erase(ws);
   }
   if (!fresh) {
-    w_split_kernel<<<(OT * (C / 8) + 255) / 256, 256, 0, stream>>>(W, ws, C, OT, 0, diff);
+    w_split_kernel<<<(OT * (C / 8) + 255) / 256, 256, 0, stream>>>(W, ws, C, OT, 0, diff, T);
     count_launch();
     if (cudaGetLastError() != cudaSuccess) return FGNN_ERR_CUDA;
   }
@@ -807,7 +826,7 @@ int launch_mp_tc(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream) 
   uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
   if (reinterpret_cast<uintptr_t>(ws) & 255) return FGNN_ERR_WORKSPACE;
   const int OT = p.O * p.T;
-  const int wrc = tc_prepare_weights(p.W, ws, ka * tc::kC, OT, a->filters_version, stream, p.ext == FGNN_ORIG_WITH_DIFF);
+  const int wrc = tc_prepare_weights(p.W, ws, ka * tc::kC, OT, a->filters_version, stream, p.ext == FGNN_ORIG_WITH_DIFF, p.T);
   if (wrc != FGNN_OK) return wrc;
 
   const int num_sms = tc_num_sms();

@@ -238,6 +238,26 @@ __device__ __forceinline__ float contract_types(const float (&et)[T], const uint
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(s));
   return lo + hi;
 }
+// T = 4: the filter image keeps the columns of a channel PAIR interleaved -- image column (o >> 1) * 8 + 2 t + (o & 1)
+// for filter column o * 4 + t (w_split_kernel) -- so an aligned 64-bit register pair of an accumulator row is
+// (H[2g][t], H[2g+1][t]) and ONE packed FMA per edge type updates both channels: four FFMA2 for two channels and no
+// horizontal add (the T >= 8 scheme above spends half of its instructions on T = 4 outside the multiply-adds).
+// et2[t] = (et[t], et[t]).  Returns (channel 2g, channel 2g+1) = sum_t et[t] * H[.][t], accumulated in order t = 0..3.
+__device__ __forceinline__ uint64_t contract_pair4(const uint64_t (&et2)[4], const uint32_t* h8) {
+  uint64_t s = ffma2(et2[0], pack2u(h8[0], h8[1]), pack2(0.f, 0.f));
+  s = ffma2(et2[1], pack2u(h8[2], h8[3]), s);
+  s = ffma2(et2[2], pack2u(h8[4], h8[5]), s);
+  s = ffma2(et2[3], pack2u(h8[6], h8[7]), s);
+  return s;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// image column of filter column n = o * T + t
+__host__ __device__ __forceinline__ int image_column(int n, int T) {
+  return T == 4 ? ((n >> 3) << 3) + 2 * (n & 3) + ((n >> 2) & 1) : n;
+}
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // named barrier over `count` threads (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) {

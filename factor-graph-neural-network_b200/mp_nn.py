@@ -193,8 +193,12 @@ class SourcePlan:
     _cache = {}
     TILE_COST = {3: 1.0, 6: 1.4}       # relative cost of a 128-row tile (row_cap 6 reads the accumulators twice)
 
-    def __init__(self, nn_idx, n_src, mask_negative=False, row_cap=None, device=None):
+    def __init__(self, nn_idx, n_src, mask_negative=False, row_cap=None, device=None, batch_local=False):
         B, M, K = nn_idx.shape
+        self.rows_per_batch = 0
+        if batch_local:
+            self._build_batch_local(nn_idx, n_src)
+            return
         if not nn_idx.is_cuda:
             # a host table (what a DataLoader hands over): the library's own O(E) counting-sort builder
             # (csrc/plan.cu, fgnn_plan_build_host); `device` = where the plan's arrays go
@@ -235,6 +239,47 @@ class SourcePlan:
         self.max_fan_out = int(counts.max().item()) if counts.numel() else 0
         self._msg = None
         self._et = None                    # (weakref(etype), version, data_ptr, permuted)
+
+    def _build_batch_local(self, nn_idx, n_src):
+        """Plan for FUSED aggregation (fgnn_mp_args.src_rows_per_batch): the virtual rows (row cap 3; a source with f
+        edges gets ceil(f/3) of them, at least one) are numbered batch element by batch element -- the same count in
+        every element, at most 128 -- so a tile of the first pass is exactly one batch element and can aggregate its
+        own destinations.  `src_rows` names the source row of every virtual row."""
+        B, M, K = nn_idx.shape
+        dev = nn_idx.device
+        R, cap = B * n_src, 3
+        flat = nn_idx.reshape(B, M * K).long()
+        valid = (flat >= 0) & (flat < n_src)
+        key = flat + torch.arange(B, device=dev, dtype=torch.long)[:, None] * n_src
+        key = torch.where(valid, key, torch.full_like(key, R)).reshape(-1)
+        order = torch.argsort(key, stable=True)
+        E = int(valid.sum().item())
+        src = key[order[:E]]
+        counts = torch.bincount(src, minlength=R)[:R] if E else torch.zeros(R, dtype=torch.long, device=dev)
+        nv = torch.clamp((counts + cap - 1) // cap, min=1).view(B, n_src)            # virtual rows per source row
+        per_b = nv.sum(1)
+        rpb = int(per_b[0].item())
+        if rpb > 128 or not bool((per_b == rpb).all().item()):
+            raise ValueError("batch-local plan: every batch element needs the same number (<= 128) of virtual rows")
+        base = (torch.cumsum(nv, 1) - nv + torch.arange(B, device=dev)[:, None] * rpb).reshape(-1)      # first virtual row of (b, n)
+        start = torch.cumsum(counts, 0) - counts
+        rank = torch.arange(E, device=dev) - start[src]
+        vrow = base[src] + torch.div(rank, cap, rounding_mode="floor")
+        perm = torch.argsort(vrow, stable=True)
+        V = B * rpb
+        self.B, self.M, self.K, self.n_src, self.n_edges = B, M, K, n_src, E
+        self.row_cap, self.n_rows, self.rows_per_batch = cap, V, rpb
+        self.edge_slot = order[:E][perm].to(torch.int32).contiguous()
+        self.slot_edge = torch.full((B * M * K,), -1, dtype=torch.int32, device=dev)
+        self.slot_edge[self.edge_slot.long()] = torch.arange(E, dtype=torch.int32, device=dev)
+        vcounts = torch.bincount(vrow, minlength=V)[:V] if E else torch.zeros(V, dtype=torch.long, device=dev)
+        self.src_ptr = torch.zeros(V + 1, dtype=torch.int32, device=dev)
+        self.src_ptr[1:] = torch.cumsum(vcounts, 0).to(torch.int32)
+        self.src_rows = torch.repeat_interleave(torch.arange(R, device=dev), nv.reshape(-1)).to(torch.int32).contiguous()
+        self.fan_out = E / max(1, R)
+        self.max_fan_out = int(counts.max().item()) if counts.numel() else 0
+        self._msg = None
+        self._et = None
 
     def _build_native(self, nn_idx, n_src, row_cap, device):
         B, M, K = nn_idx.shape
@@ -278,12 +323,12 @@ class SourcePlan:
         self._et = None
 
     @classmethod
-    def for_table(cls, nn_idx, n_src, mask_negative=False):
-        ent = cls._cache.get(id(nn_idx))
+    def for_table(cls, nn_idx, n_src, mask_negative=False, batch_local=False):
+        key = (id(nn_idx), bool(batch_local))
+        ent = cls._cache.get(key)
         if ent is not None and ent[0]() is nn_idx and ent[1:4] == (nn_idx._version, nn_idx.data_ptr(), n_src):
             return ent[4]
-        plan = cls(nn_idx, n_src, mask_negative)
-        key = id(nn_idx)
+        plan = cls(nn_idx, n_src, mask_negative, batch_local=batch_local)
         ref = weakref.ref(nn_idx, lambda _r, key=key: cls._cache.pop(key, None))
         cls._cache[key] = (ref, nn_idx._version, nn_idx.data_ptr(), n_src, plan)
         return plan
@@ -291,10 +336,10 @@ class SourcePlan:
     FUSE_STAGING_BYTES = 74 * 1024
 
     def fusable(self, O, T):
-        """True when the library aggregates inside the first pass (fgnn_mp_args.src_edge_slot): one batch element per
-        tile (N <= 128), all filter columns in one CTA (O*T = 256 at T = 4), every slot live, no virtual rows."""
-        return (T == 4 and O * T == 256 and self.n_src <= 128 and self.B >= 2 and self.n_rows == self.B * self.n_src
-                and self.n_edges == self.B * self.M * self.K and self.M * self.K * O * 4 <= self.FUSE_STAGING_BYTES)
+        """True when the library aggregates inside the first pass (fgnn_mp_args.src_edge_slot): a batch-local plan (one
+        batch element per tile), all filter columns in one CTA (O*T = 256 at T = 4), every slot live."""
+        return (self.rows_per_batch > 0 and T == 4 and O * T == 256 and self.n_edges == self.B * self.M * self.K
+                and self.M * self.K * O * 4 <= self.FUSE_STAGING_BYTES)
 
     def messages(self, O):
         if self._msg is None or self._msg.numel() < self.n_edges * O:
@@ -477,6 +522,9 @@ def mp_forward(x, nn_idx, etype, filters, bias=None, bn_scale=None, bn_shift=Non
         a.src_ptr, a.slot_edge = plan.src_ptr.data_ptr(), plan.slot_edge.data_ptr()
         a.etype_edges, a.messages, a.n_edges = keep[0].data_ptr(), (keep[1].data_ptr() if keep[1] is not None else None), plan.n_edges
         a.src_edge_slot = plan.edge_slot.data_ptr()
+        a.src_rows_per_batch = plan.rows_per_batch
+        if plan.rows_per_batch and not fusable:
+            raise RuntimeError("fgnn_b200: a batch-local plan only serves the fused aggregation (T = 4, O*T = 256, every slot live)")
         a.src_rows = plan.src_rows.data_ptr() if plan.src_rows.numel() else None
         a.n_src_rows, a.src_row_cap = plan.n_rows, plan.row_cap
     with torch.cuda.device(dev):
@@ -776,7 +824,10 @@ class mp_conv_v2(base_mp_nn):
                 return None
             if _table_use_count(nn_idx) < self.AUTO_MIN_USES:
                 return None
-            plan = SourcePlan.for_table(nn_idx, n_src)
+            try:
+                plan = SourcePlan.for_table(nn_idx, n_src, batch_local=True)
+            except ValueError:
+                return None
             return plan if plan.fusable(self.nou, T) else None
         if mode == "auto":
             if B * M * K < self.AUTO_MIN_SLOTS or B * M * K < self.AUTO_FAN_OUT[T] * B * n_src:

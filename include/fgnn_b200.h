@@ -143,11 +143,14 @@ typedef struct fgnn_mp_args {
   int64_t n_src_rows;        /* virtual rows, >= B*N                                                             */
   int32_t src_row_cap;       /* 3: tables with few edges per row; 6: the epilogue splits a row's edges over two warps
                                 (tables whose rows mostly have 4-6 edges)                                        */
-  int32_t reserved2_;
-  const int32_t* src_edge_slot; /* [E]: slot (b*M + m)*K + k of every edge (optional).  With it, a call whose batch elements
-                                each fit one tile (N <= 128), whose CTA owns all filter columns (O*T = 256) and whose slots are
-                                all live keeps the messages in shared memory and aggregates inside the first pass: the
-                                per-codeword graphs of LDPC decoding (train_ldpc.py) never send a message through HBM.      */
+  int32_t src_rows_per_batch; /* > 0: BATCH-LOCAL plan for fused aggregation (below): the virtual rows are numbered batch element
+                                by batch element, this many each (<= 128, row cap 3), and src_rows names the source row of
+                                EVERY virtual row (n_src_rows = B * src_rows_per_batch).  0: the layout described above.    */
+  const int32_t* src_edge_slot; /* [E]: slot (b*M + m)*K + k of every edge.  Fused aggregation: a table [B,M,K] is block-diagonal
+                                over the batch, so with a batch-local plan, all filter columns in one CTA (O*T = 256) and
+                                every slot live, a tile = one batch element keeps its messages in shared memory and aggregates
+                                them inside the first pass: the per-codeword graphs of LDPC decoding (train_ldpc.py) never
+                                send a message through HBM and need no second launch.                                        */
 } fgnn_mp_args;
 
 int fgnn_version(void);

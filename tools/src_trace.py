@@ -18,22 +18,34 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fgnn_b200  # noqa: E402
 from fgnn_b200 import _lib  # noqa: E402
 
-fan = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-cap = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-T = 16
-N = 300_000 if fan == 2 else 100_000
-K = 6 if fan == 2 else 2
-M = N * fan // K
 dev = "cuda:0"
 rng = np.random.default_rng(0)
-x = torch.randn(1, N, 64, device=dev).permute(0, 2, 1).unsqueeze(-1)
-idx_np = np.concatenate([rng.permutation(N) for _ in range(fan)]).reshape(1, M, K)
-idx = torch.from_numpy(idx_np).to(dev)
-et = torch.randn(1, T, M, K, device=dev)
+if len(sys.argv) > 1 and sys.argv[1] in ("ldpc_v2f", "ldpc_f2v"):
+    # the LDPC decoding graph, batch 4096, T = 4: fused aggregation (one codeword per tile)
+    z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ldpc_factornn.npz"))
+    tbl = z["idx_v2f"] if sys.argv[1] == "ldpc_v2f" else z["idx_f2v"]
+    B, T, cap = 4096, 4, None
+    N = 96 if sys.argv[1] == "ldpc_v2f" else 48
+    M, K = tbl.shape
+    fan = M * K // N
+    idx = torch.from_numpy(tbl[None]).to(dev).expand(B, M, K)
+    x = torch.randn(B, N, 64, device=dev).permute(0, 2, 1).unsqueeze(-1)
+    et = torch.randn(B, T, M, K, device=dev)
+else:
+    fan = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+    cap = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    T, B = 16, 1
+    N = 300_000 if fan == 2 else 100_000
+    K = 6 if fan == 2 else 2
+    M = N * fan // K
+    x = torch.randn(1, N, 64, device=dev).permute(0, 2, 1).unsqueeze(-1)
+    idx_np = np.concatenate([rng.permutation(N) for _ in range(fan)]).reshape(1, M, K)
+    idx = torch.from_numpy(idx_np).to(dev)
+    et = torch.randn(1, T, M, K, device=dev)
 W = torch.randn(64, 64 * T, device=dev) * 0.1
-out = torch.empty(1, 64, M, 1, device=dev, memory_format=torch.channels_last)
+out = torch.empty(B, 64, M, 1, device=dev, memory_format=torch.channels_last)
 ws = torch.zeros(64 * 64 * T * 4 + 4096, dtype=torch.uint8, device=dev)
-plan = fgnn_b200.SourcePlan(idx, N, row_cap=cap)
+plan = fgnn_b200.SourcePlan(idx, N, batch_local=True) if B > 1 else fgnn_b200.SourcePlan(idx, N, row_cap=cap)
 for _ in range(3):
     fgnn_b200.mp_forward(x, idx, et, W, None, None, None, extension=0, aggregator=0, kernel=_lib.KERNEL_TCGEN05,
                          out=out, workspace=ws, filters_version=7, plan=plan)
