@@ -620,6 +620,34 @@ __device__ __forceinline__ void ldg256(const float* src, float (&v)[8]) {
                : "l"(src));
 }
 
+// aggregate -> bias / eval BN / activation -> store (or accumulate) of eight channels of destination row g
+template <int AGG>
+__device__ __forceinline__ void reduce_finish(const MpParams& p, const float (&a)[8], const float (&s)[8], float live, int64_t g, int o,
+                                              float neg) {
+  float y[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float r;
+    if (AGG == FGNN_AGG_MAX) r = a[c];
+    else if (AGG == FGNN_AGG_SOFTMAX) r = live > 0.f ? softmax_finish(a[c], s[c], p.gamma) : -INFINITY;
+    else r = __fmul_rn(a[c], live > 0.f ? __frcp_rn(live) : 0.f);
+    const float bi = p.bias ? p.bias[o + c] : 0.f, sc = p.scale ? p.scale[o + c] : 1.f, sh = p.scale ? p.shift[o + c] : 0.f;
+    float v = fmaf(r + bi, sc, sh);
+    v = v >= 0.f ? v : v * neg;
+    y[c] = r == -INFINITY ? r : v;
+  }
+  const int64_t orow = p.out_rows ? (int64_t)p.out_rows[g] : g;
+  if (orow < 0) return;
+  float* dst = p.out + orow * p.o_sm + o;
+  if (p.accumulate) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(y[0]), "f"(y[1]), "f"(y[2]), "f"(y[3]) : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(y[4]), "f"(y[5]), "f"(y[6]), "f"(y[7]) : "memory");
+  } else {
+    *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(y[4], y[5], y[6], y[7]);
+  }
+}
+
 template <int AGG>
 __global__ void __launch_bounds__(256)
 mp_reduce_kernel(const MpParams p, const float* __restrict__ msg, const int32_t* __restrict__ slot_edge) {
@@ -661,27 +689,59 @@ mp_reduce_kernel(const MpParams p, const float* __restrict__ msg, const int32_t*
         }
       }
     }
-    float y[8];
+    reduce_finish<AGG>(p, a, s, live, g, o, neg);
+  }
+}
+
+// Tables with few slots (K = 2, 3: the factor side of pairwise / order-3 types): a thread of the kernel above would have
+// two or three loads in flight behind a dependent slot -> edge lookup.  Here a thread takes U = 6 / K items per
+// iteration, so six message pieces are always in flight (everything indexed at compile time).
+template <int AGG, int K>
+__global__ void __launch_bounds__(256)
+mp_reduce_small_kernel(const MpParams p, const float* __restrict__ msg, const int32_t* __restrict__ slot_edge) {
+  constexpr int U = 6 / K;
+  const int O8 = p.O >> 3;
+  const int64_t rows = (int64_t)p.B * p.M, total = rows * O8;
+  const float neg = p.act == FGNN_ACT_NONE ? 1.f : (p.act == FGNN_ACT_RELU ? 0.f : p.slope);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  pdl_wait();
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
+    int64_t g[U];
+    int o[U];
+    int32_t e[U][K];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float r;
-      if (AGG == FGNN_AGG_MAX) r = a[c];
-      else if (AGG == FGNN_AGG_SOFTMAX) r = live > 0.f ? softmax_finish(a[c], s[c], p.gamma) : -INFINITY;
-      else r = __fmul_rn(a[c], live > 0.f ? __frcp_rn(live) : 0.f);
-      const float bi = p.bias ? p.bias[o + c] : 0.f, sc = p.scale ? p.scale[o + c] : 1.f, sh = p.scale ? p.shift[o + c] : 0.f;
-      float v = fmaf(r + bi, sc, sh);
-      v = v >= 0.f ? v : v * neg;
-      y[c] = r == -INFINITY ? r : v;
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      g[u] = i < total ? i / O8 : -1;
+      o[u] = g[u] >= 0 ? (int)(i - g[u] * O8) * 8 : 0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) e[u][k] = g[u] >= 0 ? __ldg(slot_edge + g[u] * K + k) : -1;
     }
-    const int64_t orow = p.out_rows ? (int64_t)p.out_rows[g] : g;
-    if (orow < 0) continue;
-    float* dst = p.out + orow * p.o_sm + o;
-    if (p.accumulate) {
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(y[0]), "f"(y[1]), "f"(y[2]), "f"(y[3]) : "memory");
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(y[4]), "f"(y[5]), "f"(y[6]), "f"(y[7]) : "memory");
-    } else {
-      *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
-      *reinterpret_cast<float4*>(dst + 4) = make_float4(y[4], y[5], y[6], y[7]);
+    float v[U][K][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (e[u][k] >= 0) ldg256(msg + (int64_t)e[u][k] * p.O + o[u], v[u][k]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (g[u] < 0) continue;
+      float a[8], s[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { a[c] = AGG == FGNN_AGG_MEAN ? 0.f : -INFINITY; s[c] = 0.f; }
+      float live = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (e[u][k] < 0) continue;
+        live += 1.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (AGG == FGNN_AGG_MAX) a[c] = fmaxf(a[c], v[u][k][c]);
+          else if (AGG == FGNN_AGG_SOFTMAX) softmax_push(a[c], s[c], v[u][k][c], p.gamma);
+          else a[c] += v[u][k][c];
+        }
+      }
+      reduce_finish<AGG>(p, a, s, live, g[u], o[u], neg);
     }
   }
 }
@@ -825,9 +885,19 @@ int launch_mp_src(const MpParams& p, const fgnn_mp_args* a, cudaStream_t stream)
   cfg.blockDim = dim3(256);
   cfg.stream = stream;
   cudaError_t e;
-  if (p.agg == FGNN_AGG_MAX) e = cudaLaunchKernelEx(&cfg, mp_reduce_kernel<FGNN_AGG_MAX>, p, (const float*)sp.msg, a->slot_edge);
-  else if (p.agg == FGNN_AGG_SOFTMAX) e = cudaLaunchKernelEx(&cfg, mp_reduce_kernel<FGNN_AGG_SOFTMAX>, p, (const float*)sp.msg, a->slot_edge);
-  else e = cudaLaunchKernelEx(&cfg, mp_reduce_kernel<FGNN_AGG_MEAN>, p, (const float*)sp.msg, a->slot_edge);
+  const float* m = sp.msg;
+  const bool small = !p.tile_k && (p.K == 2 || p.K == 3);
+  if (small && p.K == 2) {
+    if (p.agg == FGNN_AGG_MAX) e = cudaLaunchKernelEx(&cfg, mp_reduce_small_kernel<FGNN_AGG_MAX, 2>, p, m, a->slot_edge);
+    else if (p.agg == FGNN_AGG_SOFTMAX) e = cudaLaunchKernelEx(&cfg, mp_reduce_small_kernel<FGNN_AGG_SOFTMAX, 2>, p, m, a->slot_edge);
+    else e = cudaLaunchKernelEx(&cfg, mp_reduce_small_kernel<FGNN_AGG_MEAN, 2>, p, m, a->slot_edge);
+  } else if (small) {
+    if (p.agg == FGNN_AGG_MAX) e = cudaLaunchKernelEx(&cfg, mp_reduce_small_kernel<FGNN_AGG_MAX, 3>, p, m, a->slot_edge);
+    else if (p.agg == FGNN_AGG_SOFTMAX) e = cudaLaunchKernelEx(&cfg, mp_reduce_small_kernel<FGNN_AGG_SOFTMAX, 3>, p, m, a->slot_edge);
+    else e = cudaLaunchKernelEx(&cfg, mp_reduce_small_kernel<FGNN_AGG_MEAN, 3>, p, m, a->slot_edge);
+  } else if (p.agg == FGNN_AGG_MAX) e = cudaLaunchKernelEx(&cfg, mp_reduce_kernel<FGNN_AGG_MAX>, p, m, a->slot_edge);
+  else if (p.agg == FGNN_AGG_SOFTMAX) e = cudaLaunchKernelEx(&cfg, mp_reduce_kernel<FGNN_AGG_SOFTMAX>, p, m, a->slot_edge);
+  else e = cudaLaunchKernelEx(&cfg, mp_reduce_kernel<FGNN_AGG_MEAN>, p, m, a->slot_edge);
   count_launch();
   return e == cudaSuccess ? (int)FGNN_OK : (int)FGNN_ERR_CUDA;
 }
