@@ -38,8 +38,10 @@ def build(force=False, verbose=False, trace=False, debug=False):
     """Compile the CUDA library if it is missing or older than its sources.  Returns its path.
     trace=True builds libfgnn_b200_trace.so with -DFGNN_TC_TRACE (per-item pipeline timestamps,
     tools/tc_trace.py); the product library never carries that code."""
-    if trace:
-        return _compile(LIB.replace(".so", "_trace.so"), verbose, ["-DFGNN_TC_TRACE"])
+    if trace:      # FGNN_TRACE_DEFS="-DX -DY" adds experiment switches, FGNN_TRACE_TAG names the library
+        extra = os.environ.get("FGNN_TRACE_DEFS", "").split()
+        tag = os.environ.get("FGNN_TRACE_TAG", "")
+        return _compile(LIB.replace(".so", "_trace%s.so" % tag), verbose, ["-DFGNN_TC_TRACE"] + extra)
     if debug:       # watchdog time-outs print the barrier they were waiting on before trapping
         return _compile(LIB.replace(".so", "_debug.so"), verbose, ["-DFGNN_TC_DEBUG"])
     if not force and not _stale():

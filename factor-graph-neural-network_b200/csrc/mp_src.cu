@@ -596,6 +596,9 @@ mp_src_kernel(const SrcParams p, const MpParams mp, const uint8_t* __restrict__ 
         ++ct;
       }
       SRC_TRACE(i, 5);                                       // all chunks of the tile issued
+#ifdef FGNN_TC_TRACE
+      if (blockIdx.x == 0 && i < 4096u && lane == 0) g_src_trace[i * 16 + 15] = (unsigned long long)clock64();      // SM clock beside the wall clock
+#endif
     }
   }
   }

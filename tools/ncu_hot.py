@@ -12,8 +12,11 @@ def main():
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    # find header row
-    hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+    # one section per profiled launch: take the one asked for (third argument, default the first)
+    heads = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+    which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    hi = heads[which]
+    rows = rows[:heads[which + 1]] if which + 1 < len(heads) else rows
     h = rows[hi]
     si = h.index("# Samples")
     src = h.index("Source")

@@ -54,9 +54,12 @@ lib = ctypes.CDLL(_lib.LIB_PATH)
 n = 16 * 4096
 buf = np.zeros(n, dtype=np.uint64)
 assert lib.fgnn_debug_src_trace_read(buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n)) == 0
-tr = buf.reshape(4096, 16).astype(np.int64)[:, :15]
+raw = buf.reshape(4096, 16).astype(np.int64)
+tr = raw[:, :15]
 items = int((tr[:, 4] > 0).sum())
 tr = tr[:items]
+if items > 8 and raw[items - 2, 15] > raw[3, 15]:        # SM cycles against nanoseconds between two late tiles
+    print(f"SM clock during the kernel: {(raw[items - 2, 15] - raw[3, 15]) / (raw[items - 2, 5] - raw[3, 5]) * 1e3:.0f} MHz")
 t0 = tr[tr > 0].min()
 tr = np.where(tr > 0, tr - t0, -1)
 names = ["x_free", "x_issued", "x_landed", "a_written", "m_ready", "m_issued", "e0_start", "e0_et", "e0_acc", "e0_done",
