@@ -79,18 +79,24 @@ class iid_mapping_in(torch.nn.Module):
                                         _InstanceNorm2d(nout), torch.nn.ReLU())
 
     def forward(self, x):
-        norm = self.main[1]
-        if (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[3] == 1 and x.shape[2] > 1
-                and not norm.affine and not norm.track_running_stats
-                and not (self.training and torch.is_grad_enabled()
-                         and (x.requires_grad or self.main[0].weight.requires_grad))):      # forward-only, like the core
-            conv = self.main[0]
-            with torch.no_grad():
-                y = conv1x1_native(x, conv.weight, conv.bias)              # tensor-core pass when the shape qualifies
-                if y is None:
-                    y = conv1x1(x, conv.weight, conv.bias)
-            return instance_norm_act(y, norm.eps, "relu")                   # norm + ReLU: one native pass
-        return self.main(x)
+        y = conv_in_relu(self.main[0], self.main[1], x, self.training)
+        return y if y is not None else self.main(x)
+
+
+def conv_in_relu(conv, norm, x, training=False):
+    """Conv2d(1x1) -> InstanceNorm2d(affine = False) -> ReLU on a CUDA fp32 [B,C,N,1] tensor as two native passes (the map
+    on the tensor-core kernel when the shape qualifies, norm + ReLU in one kernel); None when the input does not qualify
+    (then the caller runs its own nn.Sequential).  Forward-only, like the core."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[3] == 1 and x.shape[2] > 1
+            and isinstance(conv, torch.nn.Conv2d) and conv.kernel_size == (1, 1)
+            and isinstance(norm, torch.nn.InstanceNorm2d) and not norm.affine and not norm.track_running_stats
+            and not (training and torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad))):
+        return None
+    with torch.no_grad():
+        y = conv1x1_native(x, conv.weight, conv.bias)                      # tensor-core pass when the shape qualifies
+        if y is None:
+            y = conv1x1(x, conv.weight, conv.bias)
+    return instance_norm_act(y, norm.eps, "relu")                           # norm + ReLU: one native pass
 
 
 class mp_sequential(base_mp_nn):
@@ -186,6 +192,16 @@ class FactorNN(torch.nn.Module):
             return mpnn(node_feature, nn_idx, efeature)
         return mpnn(node_feature)
 
+    @staticmethod
+    def _add_core(acc, mpnn, node_feature, nn_idx, efeature):
+        """acc + mpnn(...) (factor_mpnn_sp.py:146-151); the native modules add into `acc` inside their last kernel's store
+        (`acc` is always a fresh tensor here: the output of this layer's v2v / f2f map)."""
+        if isinstance(mpnn, (mp_conv_v2, mp_conv_residual)):
+            return mpnn(node_feature, nn_idx, efeature, add_to=acc)
+        if isinstance(mpnn, base_mp_nn):
+            return acc + mpnn(node_feature, nn_idx, efeature)
+        return acc + mpnn(node_feature)
+
     def forward(self, node_feature, hop_features, nn_idx_f2v, nn_idx_v2f, etype_f2v, etype_v2f):
         x_v = self.node_mapping_module(node_feature)
         x_f = [m(f) for f, m in zip(hop_features, self.factor_mapping_modules)]
@@ -202,9 +218,8 @@ class FactorNN(torch.nn.Module):
             for j in range(len(self.f2v_modules[i])):
                 # the reference casts with .long() (factor_mpnn_sp.py:145,150); int32 tables go through as they are
                 # (the core takes both) so the per-table validation / plan caches keep hitting on the caller's object
-                new_v = new_v + self.mpnn_forward(self.f2v_modules[i][j], x_f[j],
-                                                  _as_index(nn_idx_f2v[j]), etype_f2v[j])
-                new_f[j] = new_f[j] + self.v2f_modules[i][j](x_v, _as_index(nn_idx_v2f[j]), etype_v2f[j])
+                new_v = self._add_core(new_v, self.f2v_modules[i][j], x_f[j], _as_index(nn_idx_f2v[j]), etype_f2v[j])
+                new_f[j] = self._add_core(new_f[j], self.v2f_modules[i][j], x_v, _as_index(nn_idx_v2f[j]), etype_v2f[j])
             if nin == nout:
                 x_v = x_v + new_v
                 x_f = [a + b for a, b in zip(new_f, x_f)]
@@ -215,7 +230,9 @@ class FactorNN(torch.nn.Module):
                 x_v = x_v + old_v
                 x_f = [a + b for a, b in zip(old_f, x_f)]
             history.append([x_v, x_f])
-        res = self.final_classifier(x_v)
+        fc = self.final_classifier
+        head = conv_in_relu(fc[0], fc[1], x_v, self.training)             # Conv -> InstanceNorm -> ReLU natively
+        res = fc[3](head) if head is not None else fc(x_v)
         if self.final_filter is not None:
             res = self.final_filter(res, node_feature)
         return (res, x_f) if self.ret_high else res

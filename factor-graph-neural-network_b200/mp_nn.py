@@ -739,7 +739,20 @@ class mp_conv_v2(base_mp_nn):
         """Private scratch so the split-bf16 image of `filters` is cached across calls."""
         return self._ws if self._ws is not None and self._ws.device == x.device else None
 
-    def forward(self, x, nn_idx, etype):
+    def forward(self, x, nn_idx, etype, add_to=None):
+        """`add_to` (not in the reference signature): a tensor the result is added to -- fused into the kernel's store
+        (FGNN_FLAG_ACCUMULATE) when it is a node-major fp32 tensor outside autograd, `add_to + result` otherwise."""
+        if add_to is not None:
+            return self._forward_add(x, nn_idx, etype, add_to)
+        return self._forward(x, nn_idx, etype)
+
+    def _forward_add(self, x, nn_idx, etype, add_to):
+        if (torch.is_grad_enabled() and self.training) or nn_idx.dim() != 3 or x.dim() != 4 \
+                or not _can_add_into(add_to, x.shape[0], self.nou, nn_idx.shape[1]):
+            return add_to + self._forward(x, nn_idx, etype)
+        return self._forward(x, nn_idx, etype, add_to)
+
+    def _forward(self, x, nn_idx, etype, add_to=None):
         aggregtor = self.aggregtor                        # AttributeError for an unknown string
         if self.training and torch.is_grad_enabled() and (
                 self.filters.requires_grad or x.requires_grad or etype.requires_grad):
@@ -761,13 +774,22 @@ class mp_conv_v2(base_mp_nn):
             scale, shift = _fold_bn(self.bn)
         ws = self._workspace_for(x)
         plan = self._plan_for(x, nn_idx, etype, ext, fused_agg)
+        fuse_add = add_to is not None and fuse_tail and post_act is None and fused_agg != _lib.AGG_NONE
         out = mp_forward(
             x, nn_idx, etype, self.filters,
             bias=self.bias if (fuse_tail or not custom_agg) else None,
             bn_scale=scale, bn_shift=shift, extension=ext, aggregator=fused_agg,
             activation=act_code if fuse_tail else _lib.ACT_NONE, act_slope=slope,
             kernel=self.kernel, workspace=ws, validate=self.index_check,
-            filters_version=self._filters_version() if ws is not None else 0, plan=plan)
+            filters_version=self._filters_version() if ws is not None else 0, plan=plan,
+            out=add_to if fuse_add else None, accumulate=fuse_add)
+        if fuse_add:
+            return out                                    # == add_to
+        if add_to is not None:
+            return add_to + self._tail(out, fuse_tail, post_act, custom_agg, aggregtor)
+        return self._tail(out, fuse_tail, post_act, custom_agg, aggregtor)
+
+    def _tail(self, out, fuse_tail, post_act, custom_agg, aggregtor):
         if fuse_tail:
             return post_act(out) if post_act is not None else out
         # tail in PyTorch: user aggregator and/or train-mode batch statistics (mp_nn.py:162-173)
@@ -873,32 +895,49 @@ _identity_tables = {}      # (device, N) -> (nn_idx [1,N,1] int32 = arange, etyp
 _map_images = {}           # id(weight) -> (weakref, version, filters [C,O], workspace)
 
 
-def conv1x1_native(x, weight, bias=None, bn_scale=None, bn_shift=None, activation=_lib.ACT_NONE, act_slope=0.01):
+def conv1x1_native(x, weight, bias=None, bn_scale=None, bn_shift=None, activation=_lib.ACT_NONE, act_slope=0.01,
+                   out=None, accumulate=False):
     """A per-node 1x1 map with its bias / folded eval-BatchNorm / activation as ONE launch of the tensor-core
     message-passing kernel: with the identity index table, a single slot and a single edge type equal to 1 the call
     computes out[n] = act(bn(bias + x[n] . W)) -- the split-bf16 MMA keeps fp32 accuracy (measured 5e-6), and the
     whole map is one pass over the features instead of GEMM + BatchNorm + activation passes.  First step of SURVEY 8f
     rank 1 (the maps either side of the core, mp_nn_residual.py:25-35).  Returns None when the call does not qualify
-    (x must be a node-major fp32 CUDA tensor [B,C,N,1] with C in {64, 128} and Cout a multiple of 64)."""
-    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[3] == 1 and x.shape[1] in (64, 128)
+    (x must be a node-major fp32 CUDA tensor [B,C,N,1] with C in {64, 128, 256} and Cout a multiple of 64).
+
+    C = 256 (the wide layers of train_ldpc.py's FactorNN) has no kernel instantiation of its own: a node-major row of 256
+    channels IS two consecutive rows of 128, so the map runs as a call with two slots (rows 2n, 2n+1), two edge types
+    selected by the unit edge-type vectors (1,0) / (0,1), filters [128, O*2] = 2 * (W_lo | W_hi) interleaved by type
+    and the MEAN aggregator: out = act(bn(bias + (2 x_lo W_lo + 2 x_hi W_hi) / 2)) -- every scaling is a power of two,
+    i.e. exact.  `out` / `accumulate`: store into / add to a caller tensor (fuses `acc = acc + map(x)`)."""
+    C = x.shape[1] if x.dim() == 4 else 0
+    split = 2 if C == 256 else 1
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[3] == 1 and C in (64, 128, 256)
             and x.stride(1) == 1 and x.stride(2) == x.shape[1] and (x.shape[0] == 1 or x.stride(0) == x.shape[1] * x.shape[2])
             and weight.shape[2:] == (1, 1) and weight.shape[0] % 64 == 0 and weight.shape[0] <= 256
             and x.shape[0] * x.shape[2] >= 4096):
         return None
-    B, C, N, _ = x.shape
+    B, _, N, _ = x.shape
     O = weight.shape[0]
+    Ck = C // split
     dev = x.device
-    tab = _identity_tables.get((dev, N))
+    tab = _identity_tables.get((dev, N, split))
     if tab is None:
-        tab = (torch.arange(N, dtype=torch.int32, device=dev).view(1, N, 1), torch.ones((1, 1, N, 1), dtype=torch.float32, device=dev))
-        _identity_tables[(dev, N)] = tab
+        if split == 1:
+            tab = (torch.arange(N, dtype=torch.int32, device=dev).view(1, N, 1), torch.ones((1, 1, N, 1), dtype=torch.float32, device=dev))
+        else:
+            tab = (torch.arange(N * split, dtype=torch.int32, device=dev).view(1, N, split),
+                   torch.eye(split, dtype=torch.float32, device=dev).view(1, split, 1, split).expand(1, split, N, split).contiguous())
+        _identity_tables[(dev, N, split)] = tab
     key = id(weight)
     ver = (weight._version, weight.data_ptr())
     ent = _map_images.get(key)
     if ent is None or ent[0]() is not weight or ent[1] != ver:
         with torch.no_grad():
-            filt = weight.detach().view(O, C).t().contiguous()                  # [C, O]: column o = output channel o (T = 1)
-        ws = torch.zeros(C * O * 4 + 4096, dtype=torch.uint8, device=dev)
+            if split == 1:
+                filt = weight.detach().view(O, C).t().contiguous()              # [C, O]: column o = output channel o (T = 1)
+            else:                                                               # [Ck, O*split]: column o*split + t = split * W[o, t*Ck + c]
+                filt = (weight.detach().view(O, split, Ck).permute(2, 0, 1) * float(split)).reshape(Ck, O * split).contiguous()
+        ws = torch.zeros(Ck * O * split * 4 + 4096, dtype=torch.uint8, device=dev)
         ref = weakref.ref(weight, lambda _r, key=key: _map_images.pop(key, None))
         # per-entry nonce: a rebuilt model can get the same weight / workspace addresses and version back from the
         # caching allocator, and the library's host-side record of "this workspace holds the image of these filters"
@@ -906,9 +945,18 @@ def conv1x1_native(x, weight, bias=None, bn_scale=None, bn_shift=None, activatio
         ent = (ref, ver, filt, ws, int.from_bytes(os.urandom(5), "little"))
         _map_images[key] = ent
     fver = ((ver[0] + 1) * 1000003 + (ver[1] >> 4) + (ent[4] << 20)) & 0x7fffffffffffffff or 1
-    return mp_forward(x, tab[0].expand(B, N, 1), tab[1].expand(B, 1, N, 1), ent[2], bias, bn_scale, bn_shift,
-                      extension=0, aggregator=_lib.AGG_MAX, activation=activation, act_slope=act_slope,
-                      kernel=_lib.KERNEL_TCGEN05, validate=False, workspace=ent[3], filters_version=fver)
+    if split > 1:                                                                # [B, C, N, 1] node-major == [B, Ck, split*N, 1] node-major
+        x = x.permute(0, 2, 3, 1).reshape(B, N * split, Ck).permute(0, 2, 1).unsqueeze(-1)
+    return mp_forward(x, tab[0].expand(B, N, split), tab[1].expand(B, split, N, split), ent[2], bias, bn_scale, bn_shift,
+                      extension=0, aggregator=_lib.AGG_MAX if split == 1 else _lib.AGG_MEAN, activation=activation,
+                      act_slope=act_slope, kernel=_lib.KERNEL_TCGEN05, validate=False, workspace=ent[3], filters_version=fver,
+                      out=out, accumulate=accumulate)
+
+
+def _can_add_into(acc, B, O, M):
+    """True when `acc` can take a fused `acc += result` store: a node-major fp32 CUDA tensor [B,O,M,1] outside autograd."""
+    return (acc is not None and acc.is_cuda and acc.dtype == torch.float32 and tuple(acc.shape) == (B, O, M, 1)
+            and acc.stride(1) == 1 and acc.stride(2) == O and (B == 1 or acc.stride(0) == O * M) and not acc.requires_grad)
 
 
 class mp_conv_residual(base_mp_nn):
@@ -928,7 +976,7 @@ class mp_conv_residual(base_mp_nn):
         self.with_residual = with_residual
         self.with_hop = with_hop
 
-    def _conv_bn_act(self, seq, x):
+    def _conv_bn_act(self, seq, x, add_to=None):
         """Conv2d(1x1) + BatchNorm2d + LeakyReLU.  In eval mode the BatchNorm is folded into the convolution
         (W' = W * gamma / sqrt(var + eps), b' = (b - mean) * gamma / sqrt(var + eps) + beta; cached per parameter
         version), which removes one full pass over the features per map; train mode is PyTorch's own sequence."""
@@ -939,9 +987,12 @@ class mp_conv_residual(base_mp_nn):
         if x.is_cuda:                         # conv + BN + LeakyReLU as one tensor-core pass when the shape qualifies
             with torch.no_grad():
                 scale, shift = _fold_bn(bn)
-                y = conv1x1_native(x, conv.weight, conv.bias, scale, shift, _lib.ACT_LEAKY_RELU, float(act.negative_slope))
+                into = add_to if (add_to is not None and x.dim() == 4
+                                  and _can_add_into(add_to, x.shape[0], conv.weight.shape[0], x.shape[2])) else None
+                y = conv1x1_native(x, conv.weight, conv.bias, scale, shift, _lib.ACT_LEAKY_RELU, float(act.negative_slope),
+                                   out=into, accumulate=into is not None)
             if y is not None:
-                return y
+                return y                      # `add_to` itself when the sum was fused into the store
         ver = (conv.weight._version, conv.weight.data_ptr(), -1 if conv.bias is None else conv.bias._version,
                bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
                bn.running_mean.data_ptr())
@@ -959,10 +1010,15 @@ class mp_conv_residual(base_mp_nn):
             y = conv1x1(x, ent[1], ent[2])
             return torch.nn.functional.leaky_relu_(y, act.negative_slope)
 
-    def forward(self, node_feature, nn_idx, etype):
+    def forward(self, node_feature, nn_idx, etype, add_to=None):
+        """`add_to` (not in the reference signature): a tensor the result is ADDED to, in place where the last map runs
+        natively (FactorNN's `nfeature = nfeature + f2v(...)`, factor_mpnn_sp.py:147,151, fused into the store)."""
         nfeature = self._conv_bn_act(self.conv1, node_feature)
         nfeature = self.mp_conv(nfeature, nn_idx, etype)
+        if add_to is not None and not self.with_residual:
+            y = self._conv_bn_act(self.conv2, nfeature, add_to=add_to)
+            return y if y is add_to else add_to + y
         nfeature = self._conv_bn_act(self.conv2, nfeature)
         if self.with_residual:
             nfeature = nfeature + node_feature
-        return nfeature
+        return nfeature if add_to is None else add_to + nfeature

@@ -972,7 +972,7 @@ def test_instance_norm_act_matches_torch(shape, layout):
     assert_close(y0.cpu().numpy(), torch.nn.functional.instance_norm(x, eps=1e-5).cpu().numpy(), 1e-5, "no activation")
 
 
-@pytest.mark.parametrize("cin,cout", [(64, 64), (64, 128), (128, 64), (64, 256)])
+@pytest.mark.parametrize("cin,cout", [(64, 64), (64, 128), (128, 64), (64, 256), (128, 256), (256, 64), (256, 128), (256, 256)])
 def test_conv1x1_native_matches_pytorch(cin, cout):
     """mp_nn.conv1x1_native: a 1x1 map + bias + folded eval BatchNorm + LeakyReLU as one launch of the tensor-core
     kernel (identity table, one slot, one edge type == 1) against Conv2d -> BatchNorm2d -> LeakyReLU in fp32."""
@@ -994,3 +994,52 @@ def test_conv1x1_native_matches_pytorch(cin, cout):
         raw = conv1x1_native(x, seq[0].weight, seq[0].bias)
         assert_close(raw.cpu().numpy(), seq[0](x).cpu().numpy(), RTOL, "plain map")
         assert conv1x1_native(x[:, :, :3], seq[0].weight) is None          # too small / not node-major: caller falls back
+        # fused `acc = acc + map(x)` (FactorNN's nfeature + f2v(...)): the map adds into the caller's tensor in its store
+        acc = torch.randn(37, cout, 129, 1, device=DEV).contiguous(memory_format=torch.channels_last)
+        want = acc + ref
+        got = conv1x1_native(x, seq[0].weight, seq[0].bias, scale, shift, _lib.ACT_LEAKY_RELU, 0.01, out=acc, accumulate=True)
+        assert got is acc
+        assert_close(acc.cpu().numpy(), want.cpu().numpy(), RTOL, "accumulating map")
+
+
+def test_factornn_wide_layers_fused_adds_match_pytorch_wrappers():
+    """train_ldpc.py's wide layers (128 -> 256 -> 256 -> 128): the C = 256 maps run on the tensor-core kernel as two-slot /
+    two-type calls, `nfeature + f2v(...)` is fused into the last kernel's store and the classifier head's
+    Conv -> InstanceNorm -> ReLU runs natively.  Reference: the same modules with every wrapper on PyTorch ops (the cores
+    stay native), i.e. factor_mpnn_sp.py:136-176 as written."""
+    from fgnn_b200 import factor_nn, mp_nn
+    torch.manual_seed(5)
+    B = 48
+    g = load_npz("ldpc_factornn.npz")
+    model = fgnn_b200.FactorNN(2, [6, 96], [64, 128, 256, 256, 128], [4, 1], 2, skip_link={3: 0}).to(DEV).eval()
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.uniform_(-0.2, 0.2)
+            m.running_var.uniform_(0.6, 1.4)
+    rng = np.random.default_rng(3)
+    node = t(rng.standard_normal((B, 2, 96, 1)).astype(np.float32))
+    hop = t(rng.standard_normal((B, 6, 48, 1)).astype(np.float32))
+    nhop = node[:, 0, :, :].reshape(B, 96, 1, 1)
+    rep = lambda a: t(a)[None].repeat(B, 1, 1)
+    args = (node, [hop, nhop], [rep(g["idx_f2v"]), torch.zeros(B, 96, 1, dtype=torch.long, device=DEV)],
+            [rep(g["idx_v2f"]), torch.arange(96, device=DEV).reshape(1, 1, 96).repeat(B, 1, 1)],
+            [t(rng.standard_normal((B, 4, 96, 3)).astype(np.float32)), torch.ones(B, 1, 96, 1, device=DEV)],
+            [t(rng.standard_normal((B, 4, 48, 6)).astype(np.float32)), torch.ones(B, 1, 1, 96, device=DEV)])
+    with torch.no_grad():
+        before = fgnn_b200.launch_count()
+        got = model(*args)
+        native_launches = fgnn_b200.launch_count() - before
+        # the same forward with the wrappers' native routes switched off
+        saved = (mp_nn.conv1x1_native, factor_nn.conv1x1_native, factor_nn.conv_in_relu, factor_nn.FactorNN._add_core)
+        try:
+            mp_nn.conv1x1_native = factor_nn.conv1x1_native = lambda *a, **k: None
+            factor_nn.conv_in_relu = lambda *a, **k: None
+            factor_nn.FactorNN._add_core = staticmethod(
+                lambda acc, m, x, idx, ef: acc + (m(x, idx, ef) if isinstance(m, fgnn_b200.base_mp_nn) else m(x)))
+            before = fgnn_b200.launch_count()
+            ref = model(*args)
+            plain_launches = fgnn_b200.launch_count() - before
+        finally:
+            mp_nn.conv1x1_native, factor_nn.conv1x1_native, factor_nn.conv_in_relu, factor_nn.FactorNN._add_core = saved
+    assert native_launches > plain_launches                      # the maps really ran on the library's kernels
+    assert_close(got.cpu().numpy(), ref.cpu().numpy(), RTOL, "FactorNN with wide layers")
