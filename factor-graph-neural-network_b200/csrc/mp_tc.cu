@@ -505,23 +505,37 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
     const int sub = lane / LPR, q = lane % LPR;
     // source rows (b*N + n, -1 = none) of tile rows pw*64 + j*32 + lane of an item; the index loads are
     // issued one item ahead and only CONSUMED (range check -> source row) after the stage wait
+    // The loaded words are kept RAW (lo / hi halves): a warp issues in order, so widening a 32-bit entry right behind its
+    // load would park the warp for the whole load latency -- 1.6 us per item on a streaming call (the trace of a 1x1 map
+    // through the identity table), where "one item ahead" then hides nothing.  index_value() widens at the point of use.
     struct Idx {
-      int64_t n[IPL];
+      int32_t lo[IPL], hi[IPL];
       int32_t base[IPL];
     };
     auto index_of = [&](const ItemIter& it, Idx& v) {
 #pragma unroll
       for (int j = 0; j < IPL; ++j) {
         v.base[j] = -1;
-        v.n[j] = -1;
+        v.lo[j] = -1;
+        v.hi[j] = -1;
         if (it.tile >= n_tiles) continue;
         const uint32_t g = (uint32_t)it.tile * kTileM + pw * ROWS_W + j * 32 + lane;
         if (g >= rows_total) continue;
         uint32_t b, m;
         split_row(g, b, m);
         v.base[j] = (int32_t)(b * (uint32_t)p.N);
-        v.n[j] = load_index(p.idx, p.idx64, (int64_t)b * p.idx_sb + (int64_t)m * p.K + it.k);
+        const int64_t off = (int64_t)b * p.idx_sb + (int64_t)m * p.K + it.k;
+        if (p.idx64) {
+          const int2 w = __ldg(reinterpret_cast<const int2*>(p.idx) + off);
+          v.lo[j] = w.x;
+          v.hi[j] = w.y;
+        } else {
+          v.lo[j] = __ldg(reinterpret_cast<const int32_t*>(p.idx) + off);
+        }
       }
+    };
+    auto index_value = [&](const Idx& v, int j) -> int64_t {
+      return p.idx64 ? (int64_t)(((uint64_t)(uint32_t)v.hi[j] << 32) | (uint32_t)v.lo[j]) : (int64_t)v.lo[j];
     };
     const uint8_t* xq = reinterpret_cast<const uint8_t*>(p.x) + q * 16;
     const uint32_t sA_u = smem_u32(sA);
@@ -558,8 +572,10 @@ mp_tc_kernel(const MpParams p, const uint8_t* __restrict__ wimg, const int S, co
       uint32_t off[IPL];
 #pragma unroll
       for (int j = 0; j < IPL; ++j)
-        off[j] = (cur.base[j] >= 0 && cur.n[j] >= 0 && cur.n[j] < p.N) ? (uint32_t)(cur.base[j] + (int32_t)cur.n[j]) * src_rowb
-                                                                       : 0xffffffffu;
+      {
+        const int64_t n = index_value(cur, j);
+        off[j] = (cur.base[j] >= 0 && n >= 0 && n < p.N) ? (uint32_t)(cur.base[j] + (int32_t)n) * src_rowb : 0xffffffffu;
+      }
 
       const uint32_t stage = sA_u + st * STAGEB;
 #pragma unroll

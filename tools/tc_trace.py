@@ -17,13 +17,18 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fgnn_b200  # noqa: E402
 from fgnn_b200 import _lib  # noqa: E402
 
-T = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-K = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-N, M = 100_000, 300_000 if K == 2 else 100_000
 dev = "cuda:0"
 rng = np.random.default_rng(0)
+if len(sys.argv) > 1 and sys.argv[1] == "map":          # a 1x1 map through the identity table (mp_nn.conv1x1_native), LDPC rows
+    T, K, N = 1, 1, 4096 * 96
+    M = N
+    idx = torch.arange(N, dtype=torch.int32, device=dev).view(1, N, 1)
+else:
+    T = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+    K = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    N, M = 100_000, 300_000 if K == 2 else 100_000
+    idx = torch.from_numpy(rng.integers(0, N, (1, M, K))).to(dev)
 x = torch.randn(1, N, 64, device=dev).permute(0, 2, 1).unsqueeze(-1)
-idx = torch.from_numpy(rng.integers(0, N, (1, M, K))).to(dev)
 et = torch.randn(1, T, M, K, device=dev)
 W = torch.randn(64, 64 * T, device=dev) * 0.1
 out = torch.empty(1, 64, M, 1, device=dev, memory_format=torch.channels_last)
