@@ -94,7 +94,9 @@ def parse_args():
     ap.add_argument("--config", default=None, choices=["cfg2", "cfg3", "cfg4", "cfg5"],
                     help="BASELINE.json presets: cfg2 = the default (configs[1]); cfg4 = configs[3] sizes on this many GPUs "
                          "(1 M variables, 3 M pairwise + 500 K order-4, 8 layers, bf16 I/O: single GPU); cfg5 = configs[4] "
-                         "sizes (65 536 variables, 524 288 pairwise + 8 192 order-16, 12 layers; random incidence)")
+                         "(65 536 points in 3-D numbered along a Z-order curve, kNN-16 as 524 288 pairwise factors + 8 192 patch factors of "
+                         "order 16, 12 layers: graphs.point_cloud_graph; --cfg5-random keeps the sizes with uniform-random incidence)")
+    ap.add_argument("--cfg5-random", action="store_true", help="cfg5 sizes on uniform-random incidence instead of the point cloud")
     args = ap.parse_args()
     if args.config == "cfg4":
         args.vars, args.pairwise, args.high, args.high_order, args.layers, args.dtype = 1_000_000, 3_000_000, 500_000, 4, 8, "bf16"
@@ -106,8 +108,9 @@ def parse_args():
         args.layers, args.edge_types = 10, 4
         if args.batch == 1:
             args.batch = 4096
+    args.point_cloud = args.config == "cfg5" and not args.cfg5_random and not args.local_band
     if args.exchange == "auto":
-        args.exchange = "halo" if (args.local_band or args.dtype == "bf16") else "peer"
+        args.exchange = "halo" if (args.local_band or args.point_cloud or args.dtype == "bf16") else "peer"
     return args
 
 
@@ -122,9 +125,13 @@ def build_graph(args, scale=1):
         # (lib/data/ldpc_dataset.py:92-106); the tables travel in the committed golden fixture
         z = np.load(os.path.join(ROOT, "tests", "golden", "ldpc_factornn.npz"))
         return [graphs.FactorType(z["idx_v2f"], z["idx_f2v"], np.zeros(z["idx_f2v"].shape, bool), "ldpc-checks")]
-    types = graphs.synthetic_map_graph(args.vars // scale, args.pairwise // scale, args.high // scale,
-                                       args.high_order, seed=args.seed, local_band=args.local_band)
-    if args.order == "locality" and args.local_band:
+    if args.point_cloud:
+        # kNN + patch factors over a seeded 3-D point set (SURVEY 8d cfg 5); the sizes follow from the point count
+        types = graphs.point_cloud_graph(args.vars // scale, 16, args.high // scale, args.high_order, seed=args.seed)
+    else:
+        types = graphs.synthetic_map_graph(args.vars // scale, args.pairwise // scale, args.high // scale,
+                                           args.high_order, seed=args.seed, local_band=args.local_band)
+    if args.order == "locality" and (args.local_band or args.point_cloud):
         types = graphs.locality_order(types)
     return types
 
@@ -182,6 +189,9 @@ def workload_name(args):
     if args.config == "cfg3":
         return (f"LDPC 96.3.963 decoding graph (96 variables, 48 check factors of order 6), batch {args.batch} codewords, "
                 f"{args.layers} message-passing iterations, C=O={args.dim}, T={args.edge_types}, fp32")
+    if args.point_cloud:
+        return (f"point cloud: {args.vars} points in 3-D (Z-order numbering), kNN-16 as {args.pairwise} pairwise factors + {args.high} "
+                f"patch factors of order {args.high_order}, {args.layers} FGNN layers, C=O={args.dim}, T={args.edge_types}, fp32")
     return (f"synthetic MAP inference: {args.vars} vars, {args.pairwise} pairwise + {args.high} order-{args.high_order} "
             f"factors, {args.layers} FGNN layers, C=O={args.dim}, T={args.edge_types}, {'bf16 I/O' if args.dtype == 'bf16' else 'fp32'}, "
             f"{'uniform-random' if not args.local_band else f'band-{args.local_band}'} incidence")
@@ -807,7 +817,7 @@ def run_native(args):
         par = "batch-sharded x%d: every rank runs its own codewords, no collective (replicas)" % world
     elif halo is not None:
         par = ("owner-computes sharding x%d (contiguous variable / factor ranges%s) + one NVLink peer-memory halo pull per layer"
-               % (world, ", factors ordered by smallest variable" if (args.order == "locality" and args.local_band) else ""))
+               % (world, ", factors ordered by smallest variable" if (args.order == "locality" and (args.local_band or args.point_cloud)) else ""))
     elif world > 1:
         par = "factor-sharded x%d + %s per layer" % (world, "fused max-reduce/epilogue/broadcast kernel over NVLink peer memory"
                                                       if args.exchange == "peer" else "NCCL max-all-reduce")

@@ -118,6 +118,44 @@ def synthetic_map_graph(n_vars, n_pairwise, n_high, high_order, seed=0, local_ba
     return types
 
 
+def point_cloud_graph(n_points=65_536, knn=16, n_patches=8_192, patch_order=16, seed=0):
+    """The point-cloud graph of BASELINE.json configs[4] (SURVEY 8d cfg 5): a seeded uniform 3-D point set, numbered
+    along a Z-order (Morton) curve so that index locality follows spatial locality; `n_points * knn / 2` pairwise
+    factors (point i, its j-th nearest neighbour), j = 1 .. knn/2 -- every point is the first variable of knn/2 factors
+    and the second variable of as many as name it a neighbour, knn incidences per point on average; `n_patches` factors
+    of order `patch_order`: the points nearest to a patch centre (centres = a seeded subset of the points).  The
+    variable-side tables are padded to the largest membership with the reference's convention (valid index + all-zero
+    edge type).  Needs scipy (cKDTree); host side, seconds at the default size."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(seed)
+    pts = rng.random((n_points, 3))
+    # Morton order: interleave the top 10 bits of every coordinate
+    q = np.minimum((pts * 1024).astype(np.uint64), 1023)
+
+    def spread(v):
+        v = (v | (v << 16)) & np.uint64(0x030000FF)
+        v = (v | (v << 8)) & np.uint64(0x0300F00F)
+        v = (v | (v << 4)) & np.uint64(0x030C30C3)
+        v = (v | (v << 2)) & np.uint64(0x09249249)
+        return v
+    code = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1)) | (spread(q[:, 2]) << np.uint64(2))
+    pts = pts[np.argsort(code, kind="stable")]
+    tree = cKDTree(pts)
+    half = knn // 2
+    _, nb = tree.query(pts, k=half + 1)                                # column 0 is the point itself
+    first = np.repeat(np.arange(n_points, dtype=np.int64), half)
+    pair = np.stack([first, nb[:, 1:].reshape(-1).astype(np.int64)], 1)                 # [N*knn/2, 2]
+    idx_f2v, pad = _var_side_table(pair, n_points)
+    types = [FactorType(pair, idx_f2v, pad, "knn-pairwise")]
+    if n_patches > 0:
+        centres = pts[rng.choice(n_points, n_patches, replace=False)]
+        _, members = tree.query(centres, k=patch_order)
+        patch = np.sort(members.astype(np.int64), 1)
+        idx_f2v, pad = _var_side_table(patch, n_points)
+        types.append(FactorType(patch, idx_f2v, pad, f"patch{patch_order}"))
+    return types
+
+
 def locality_order(types):
     """Renumber the factors of every type by their smallest variable (stable), so that a contiguous range of factors
     touches a (nearly) contiguous range of variables when the graph has index locality (banded / chain / kNN

@@ -120,6 +120,25 @@ def test_synthetic_graph_tables_are_consistent():
     assert (ordered.idx_v2f[ordered.idx_f2v[v, s_]] == v[:, None]).any(1).all()
 
 
+def test_point_cloud_graph_cfg5_shape():
+    """BASELINE configs[4] (SURVEY 8d cfg 5): kNN pairwise + patch factors over a Z-ordered point set."""
+    types = graphs.point_cloud_graph(4096, 16, 512, 16, seed=1)
+    knn, patch = types
+    assert knn.idx_v2f.shape == (4096 * 8, 2) and patch.idx_v2f.shape == (512, 16)
+    assert knn.real_messages + patch.real_messages == 2 * (4096 * 8 * 2 + 512 * 16)
+    assert (knn.idx_v2f[:, 0] != knn.idx_v2f[:, 1]).all()                        # a point is not its own neighbour
+    assert (np.diff(np.sort(patch.idx_v2f, 1), axis=1) > 0).all()                # 16 distinct members
+    for t in types:
+        assert t.idx_v2f.min() >= 0 and t.idx_v2f.max() < 4096
+        v, s = np.nonzero(~t.pad_f2v)
+        assert (t.idx_v2f[t.idx_f2v[v, s]] == v[:, None]).any(1).all()
+        assert (~t.pad_f2v).sum() == t.n_factors * t.order and (t.idx_f2v[t.pad_f2v] == 0).all()
+    # the Z-order numbering turns spatial neighbours into index neighbours: half of the kNN pairs span < 1 % of the ids
+    assert np.median(np.abs(knn.idx_v2f[:, 0] - knn.idx_v2f[:, 1])) < 41
+    a = graphs.point_cloud_graph(4096, 16, 512, 16, seed=1)[0].idx_v2f
+    assert np.array_equal(a, knn.idx_v2f)                                        # seeded
+
+
 def test_parse_alist_small():
     text = "4 2\n2 3\n1 2 1 2\n3 3\n1 0\n1 2\n2 0\n1 2\n1 2 4\n2 4 0\n"
     v2c, c2v = graphs.parse_alist(text)
