@@ -81,6 +81,9 @@ def parse_args():
     ap.add_argument("--concurrent-layer", action="store_true",
                     help="single GPU: issue the V->F calls of a layer on their own streams beside the F->V chain "
                          "(measured: +2 %% at T=4, nothing at T=16 -- programmatic launch already hides the hand-over)")
+    ap.add_argument("--no-zero-slots", action="store_true",
+                    help="source-stationary plans evaluate the padded slots (valid index + zero edge type) like any other slot "
+                         "instead of treating them as constant-zero messages")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch every step from Python instead of replaying a CUDA graph of the step")
     ap.add_argument("--exchange-ctas", type=int, default=64, help="grid of the peer exchange kernel (512-thread CTAs, two per SM)")
@@ -535,7 +538,12 @@ def run_native(args):
                         plans[name] = sp
                     continue
                 if (args.src_calls == "auto" and fan >= rule) or name in args.src_calls.split(","):
-                    sp = fgnn_b200.SourcePlan(idx, n_src)
+                    # the variable-side tables pad with (index 0, all-zero edge type): the generator knows which slots
+                    # (FactorType.pad_f2v), the plan leaves them out and the second pass aggregates a literal 0 for them
+                    zs = None
+                    if halo is None and not args.no_zero_slots and name.startswith("f2v") and ty.pad_f2v.any():
+                        zs = torch.from_numpy(ty.pad_f2v).to(dev)
+                    sp = fgnn_b200.SourcePlan(idx, n_src, zero_slots=zs)
                     if args.src_calls != "auto" or sp.n_rows * 1.25 <= idx.numel():
                         plans[name] = sp        # (hub sources -- the reference's pad target -- are split into virtual rows)
 
@@ -701,6 +709,8 @@ def run_native(args):
                                        "bn.num_batches_tracked": torch.tensor(0)})
                     m.kernel = kernel
                     m.index_check = "async"          # range scan without a host round trip (reference CUDA semantics)
+                    if d == "f2v" and not args.no_zero_slots and types[j].pad_f2v.any():
+                        m.zero_edge_type_slots = torch.from_numpy(types[j].pad_f2v).to(dev)     # the generator's padding
                     pair[d] = m.to(dev).eval().enable_weight_cache()
                 row.append(pair)
             mods.append(row)

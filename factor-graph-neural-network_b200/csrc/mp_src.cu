@@ -623,6 +623,11 @@ __device__ __forceinline__ void ldg256(const float* src, float (&v)[8]) {
                : "l"(src));
 }
 
+// slot_edge value of a slot that is present but known to carry an all-zero edge-type vector (the reference's padding:
+// a valid index + zero edge type): its message is the constant 0 -- it takes part in the aggregate without having an
+// edge, a virtual row or a stored message
+constexpr int32_t kZeroSlot = -2;
+
 // aggregate -> bias / eval BN / activation -> store (or accumulate) of eight channels of destination row g
 template <int AGG>
 __device__ __forceinline__ void reduce_finish(const MpParams& p, const float (&a)[8], const float (&s)[8], float live, int64_t g, int o,
@@ -674,11 +679,16 @@ mp_reduce_kernel(const MpParams p, const float* __restrict__ msg, const int32_t*
       for (int j = 0; j < KB; ++j) e[j] = k0 + j < kt ? __ldg(se + k0 + j) : -1;
       float v[KB][8];
 #pragma unroll
-      for (int j = 0; j < KB; ++j)
+      for (int j = 0; j < KB; ++j) {
         if (e[j] >= 0) ldg256(msg + (int64_t)e[j] * p.O + o, v[j]);
+        else if (e[j] == kZeroSlot) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[j][c] = 0.f;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < KB; ++j) {
-        if (e[j] < 0) continue;
+        if (e[j] < 0 && e[j] != kZeroSlot) continue;
         live += 1.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -725,7 +735,13 @@ mp_reduce_small_kernel(const MpParams p, const float* __restrict__ msg, const in
     for (int u = 0; u < U; ++u)
 #pragma unroll
       for (int k = 0; k < K; ++k)
+      {
         if (e[u][k] >= 0) ldg256(msg + (int64_t)e[u][k] * p.O + o[u], v[u][k]);
+        else if (e[u][k] == kZeroSlot) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[u][k][c] = 0.f;
+        }
+      }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (g[u] < 0) continue;
@@ -735,7 +751,7 @@ mp_reduce_small_kernel(const MpParams p, const float* __restrict__ msg, const in
       float live = 0.f;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        if (e[u][k] < 0) continue;
+        if (e[u][k] < 0 && e[u][k] != kZeroSlot) continue;
         live += 1.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {

@@ -193,13 +193,22 @@ class SourcePlan:
     _cache = {}
     TILE_COST = {3: 1.0, 6: 1.4}       # relative cost of a 128-row tile (row_cap 6 reads the accumulators twice)
 
-    def __init__(self, nn_idx, n_src, mask_negative=False, row_cap=None, device=None, batch_local=False):
+    def __init__(self, nn_idx, n_src, mask_negative=False, row_cap=None, device=None, batch_local=False, zero_slots=None):
+        """zero_slots (bool [B,M,K] or [M,K], optional): slots the caller KNOWS to carry an all-zero edge-type vector --
+        the reference's padding convention (a valid index, usually 0, with a zero edge type: lib/data/ldpc_dataset.py:36-37).
+        Their message is the constant 0, so they are left out of the plan (no edge, no virtual row -- the pad target
+        otherwise collects every padded slot of the table) and the second pass feeds a literal 0 into the aggregate
+        (slot_edge = -2).  Bit-identical to evaluating them as long as the pad target's features are finite."""
         B, M, K = nn_idx.shape
         self.rows_per_batch = 0
         if batch_local:
+            if zero_slots is not None:
+                raise ValueError("a batch-local plan has no zero slots (every slot is live)")
             self._build_batch_local(nn_idx, n_src)
             return
         if not nn_idx.is_cuda:
+            if zero_slots is not None:
+                raise ValueError("zero_slots needs a table on the device (the torch builder)")
             # a host table (what a DataLoader hands over): the library's own O(E) counting-sort builder
             # (csrc/plan.cu, fgnn_plan_build_host); `device` = where the plan's arrays go
             self._build_native(nn_idx, n_src, row_cap, device)
@@ -208,6 +217,10 @@ class SourcePlan:
         R = B * n_src
         flat = nn_idx.reshape(B, M * K).long()
         valid = (flat >= 0) & (flat < n_src)          # anything else is an empty slot here; range errors are the validator's job
+        zero = None
+        if zero_slots is not None:
+            zero = torch.as_tensor(zero_slots, device=dev).bool().expand(B, M, K).reshape(B, M * K) & valid
+            valid = valid & ~zero
         key = flat + torch.arange(B, device=dev, dtype=torch.long)[:, None] * n_src
         key = torch.where(valid, key, torch.full_like(key, R)).reshape(-1)
         order = torch.argsort(key, stable=True)
@@ -231,6 +244,8 @@ class SourcePlan:
         self.edge_slot = order[:E][perm].to(torch.int32).contiguous()             # [E] slot of every edge
         self.slot_edge = torch.full((B * M * K,), -1, dtype=torch.int32, device=dev)
         self.slot_edge[self.edge_slot.long()] = torch.arange(E, dtype=torch.int32, device=dev)
+        if zero is not None:
+            self.slot_edge[zero.reshape(-1)] = -2                                  # present, message == 0 (include/fgnn_b200.h)
         vcounts = torch.bincount(vrow, minlength=V)[:V] if E else torch.zeros(V, dtype=torch.long, device=dev)
         self.src_ptr = torch.zeros(V + 1, dtype=torch.int32, device=dev)
         self.src_ptr[1:] = torch.cumsum(vcounts, 0).to(torch.int32)
@@ -323,12 +338,12 @@ class SourcePlan:
         self._et = None
 
     @classmethod
-    def for_table(cls, nn_idx, n_src, mask_negative=False, batch_local=False):
-        key = (id(nn_idx), bool(batch_local))
+    def for_table(cls, nn_idx, n_src, mask_negative=False, batch_local=False, zero_slots=None):
+        key = (id(nn_idx), bool(batch_local), None if zero_slots is None else (id(zero_slots), zero_slots._version))
         ent = cls._cache.get(key)
         if ent is not None and ent[0]() is nn_idx and ent[1:4] == (nn_idx._version, nn_idx.data_ptr(), n_src):
             return ent[4]
-        plan = cls(nn_idx, n_src, mask_negative, batch_local=batch_local)
+        plan = cls(nn_idx, n_src, mask_negative, batch_local=batch_local, zero_slots=zero_slots)
         ref = weakref.ref(nn_idx, lambda _r, key=key: cls._cache.pop(key, None))
         cls._cache[key] = (ref, nn_idx._version, nn_idx.data_ptr(), n_src, plan)
         return plan
@@ -716,6 +731,9 @@ class mp_conv_v2(base_mp_nn):
         # source-stationary evaluation (SourcePlan): True / False / "auto" = when the table's sources feed
         # enough slots for the saved tensor work to pay for the message round trip (measured)
         self.source_stationary = "auto"
+        # optional hint for source-stationary plans: a bool tensor [B,M,K] / [M,K] of the slots the caller pads with an
+        # all-zero edge type (the reference's convention); see SourcePlan(zero_slots=...)
+        self.zero_edge_type_slots = None
         self._ws = None
         self._nonce = int.from_bytes(os.urandom(5), "little")      # distinguishes modules that reuse freed addresses
 
@@ -858,7 +876,7 @@ class mp_conv_v2(base_mp_nn):
                 return None                 # the plan builder trusts validated tables only
             if _table_use_count(nn_idx) < self.AUTO_MIN_USES:
                 return None                 # not (yet) known to be static: a plan would cost more than it saves
-        plan = SourcePlan.for_table(nn_idx, n_src)
+        plan = SourcePlan.for_table(nn_idx, n_src, zero_slots=self.zero_edge_type_slots)
         if mode == "auto" and plan.n_rows * 1.25 > B * M * K:
             return None                     # (hub rows split into virtual rows) too few row-products saved
         return plan

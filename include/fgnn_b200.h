@@ -134,7 +134,10 @@ typedef struct fgnn_mp_args {
      edges of rows that have more (the reference pads with a valid index and a zero edge type, so the pad target
      collects every padded slot).  Edges are numbered virtual row by virtual row. */
   const int32_t* src_ptr;    /* [n_src_rows + 1]: the edges of virtual row v are src_ptr[v] .. src_ptr[v+1]-1 (<= src_row_cap) */
-  const int32_t* slot_edge;  /* [B*M*K]: edge number of slot (b*M + m)*K + k, -1 = empty slot                    */
+  const int32_t* slot_edge;  /* [B*M*K]: edge number of slot (b*M + m)*K + k; -1 = empty slot (not aggregated);
+                                -2 = a slot the caller KNOWS to carry an all-zero edge-type vector (the reference's
+                                padding: valid index + zero edge type): it is no edge of the plan, its message is the
+                                constant 0 and it takes part in the aggregate like any other slot                */
   const void* etype_edges;   /* [E, T]: edge-type vector of every edge, edge-major (fgnn_src_permute_etype)      */
   void* messages;            /* [E, O] scratch for the per-edge messages, 32-byte aligned                       */
   int64_t n_edges;           /* E                                                                                */

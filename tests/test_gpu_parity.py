@@ -564,6 +564,35 @@ def test_source_stationary_masked_accumulate_and_module_auto():
 
 
 @pytest.mark.parametrize("agg", ["max", "softmax", "mean"])
+def test_source_plan_zero_slots_equal_evaluated_padding(agg):
+    """SourcePlan(zero_slots=...): padded slots (valid index 0 + all-zero edge type, the reference's convention) are left
+    out of the plan and aggregated as constant-zero messages -- bit-identical to evaluating them (destination-stationary
+    kernel and a plan without the hint), while the pad target no longer collects an edge per padded slot."""
+    rng = np.random.default_rng(11)
+    N, M, K, T, C = 700, 1500, 3, 16, 64
+    idx = rng.integers(0, N, (1, M, K))
+    pad = rng.random((M, K)) < 0.35
+    pad[:, 0] = False                                                  # every destination keeps a real slot
+    idx[0][pad] = 0
+    et = rng.standard_normal((1, T, M, K)).astype(np.float32)
+    et[0][:, pad] = 0.0
+    x = t(rng.standard_normal((1, N, C)).astype(np.float32)).permute(0, 2, 1).unsqueeze(-1)
+    W = t(rng.uniform(-0.1, 0.1, (C, C * T)).astype(np.float32))
+    bias = t(rng.uniform(0, 0.05, C).astype(np.float32))
+    d_idx, d_et = t(idx), t(et)
+    code = {"max": _lib.AGG_MAX, "softmax": _lib.AGG_SOFTMAX, "mean": _lib.AGG_MEAN}[agg]
+    run = lambda plan: fgnn_b200.mp_forward(x, d_idx, d_et, W, bias, None, None, extension=0, aggregator=code,
+                                            kernel=_lib.KERNEL_TCGEN05, plan=plan)
+    ref = run(None)
+    plain = fgnn_b200.SourcePlan(d_idx, N, row_cap=3)
+    hinted = fgnn_b200.SourcePlan(d_idx, N, row_cap=3, zero_slots=t(pad))
+    assert hinted.n_edges == int((~pad).sum()) and hinted.n_rows < plain.n_rows
+    assert int((hinted.slot_edge == -2).sum()) == int(pad.sum())
+    assert torch.equal(run(plain), ref)
+    assert torch.equal(run(hinted), ref)
+
+
+@pytest.mark.parametrize("agg", ["max", "softmax", "mean"])
 @pytest.mark.parametrize("direction", ["v2f", "f2v"])
 def test_fused_aggregation_ldpc_shapes(direction, agg):
     """The LDPC decoding graph (96.3.963 tables of the golden fixture, batch of codewords, T = 4): with a plan the
