@@ -413,6 +413,23 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def clocks_record(clocks, sustained, timed_ms):
+    """nvidia-smi samples every 100 ms; a timed region of a few tens of milliseconds catches 0-2 of them.  When that
+    happens the samples of the sustained run (the same step replayed back to back for seconds, its own timed region) are
+    reported beside them, so the record always carries clocks and throttle reasons measured under this load."""
+    if clocks is None:
+        return None
+    out = dict(clocks)
+    if (out.get("samples") or 0) < 3 and sustained and sustained.get("clocks"):
+        sc = sustained["clocks"]
+        out["note"] = (f"timed region {timed_ms:.0f} ms against a 100 ms sampling period; under the same steps replayed for "
+                       f"{sustained['seconds']:.1f} s: sm {sc.get('sm_mhz')} MHz median over {sc.get('samples')} samples, reasons {sc.get('reasons')}")
+        if out.get("sm_mhz") is None:
+            out["sm_mhz"], out["sm_max_mhz"] = sc.get("sm_mhz"), sc.get("sm_max_mhz")
+            out["reasons"] = sc.get("reasons", [])
+    return out
+
+
 def hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -863,7 +880,7 @@ def run_native(args):
                                 "note": "bf16 MMA flops actually issued per GPU (3 split-bf16 terms for fp32 parity; one row-product per "
                                         "virtual source row in source-stationary calls, per slot otherwise) against the sustained cuBLAS "
                                         "bf16 rate: at T=16 the tensor pipe and tensor-memory reads, not HBM, bound pass 1 (DESIGN.md 3)"}},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches), "clocks": clocks_record(clocks, sustained, ms),
     }
     if sustained is not None:
         sustained["roofline_frac"] = bytes_layer * L / (sustained["ms_per_step"] * 1e-3) / 1e9 / world / peak
