@@ -38,6 +38,33 @@ call(1, 500, 900, 2, 16, plan_cap=3)                       # source-stationary, 
 call(1, 200, 900, 2, 16, plan_cap=6)                       # source-stationary, edge split, hub rows
 call(2, 300, 300, 4, 16, ext=2)                            # ORIG_WITH_DIFF on tensor cores (two-atom rows)
 call(1, 257, 300, 5, 3, O=6, C=5)                          # SIMT kernel
+# padded slots left out of the plan (slot_edge = -2), int32 table
+idx = rng.integers(0, 400, (1, 700, 3))
+pad = rng.random((700, 3)) < 0.3
+pad[:, 0] = False
+idx[0][pad] = 0
+et = rng.standard_normal((1, 16, 700, 3)).astype(np.float32)
+et[0][:, pad] = 0
+d_idx = t(idx).int()
+fgnn_b200.mp_forward(nm(t(rng.standard_normal((1, 400, 64)).astype(np.float32))), d_idx, t(et),
+                     t((rng.uniform(-1, 1, (64, 1024)) * 0.1).astype(np.float32)), None, None, None, extension=0, aggregator=0,
+                     plan=fgnn_b200.SourcePlan(d_idx, 400, zero_slots=t(pad)))
+# fused aggregation (one batch element per tile) on LDPC-shaped tables
+Bq = 70
+tbl = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ldpc_factornn.npz"))["idx_v2f"]
+idx = t(np.broadcast_to(tbl[None], (Bq, 48, 6)).copy())
+fgnn_b200.mp_forward(nm(t(rng.standard_normal((Bq, 96, 64)).astype(np.float32))), idx, t(rng.standard_normal((Bq, 4, 48, 6)).astype(np.float32)),
+                     t((rng.uniform(-1, 1, (64, 256)) * 0.1).astype(np.float32)), None, None, None, extension=0, aggregator=0,
+                     plan=fgnn_b200.SourcePlan(idx, 96, batch_local=True))
+# 1x1 maps through the identity table: C = 64 and the two-slot / two-type form of C = 256, accumulating
+from fgnn_b200.mp_nn import conv1x1_native  # noqa: E402
+for cin in (64, 256):
+    conv = torch.nn.Conv2d(cin, 128, 1).to(dev)
+    xm = torch.randn(40, cin, 120, 1, device=dev).contiguous(memory_format=torch.channels_last)
+    acc = torch.zeros(40, 128, 120, 1, device=dev).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        assert conv1x1_native(xm, conv.weight, conv.bias, out=acc, accumulate=True) is acc
+torch.cuda.synchronize()
 # edge model + backward
 em = torch.nn.Sequential(torch.nn.Conv2d(7, 64, 1), torch.nn.ReLU(), torch.nn.Conv2d(64, 4, 1)).to(dev)
 fgnn_b200.emodel_forward(em, torch.randn(3, 7, 96, 3, device=dev))
