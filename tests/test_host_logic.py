@@ -3,6 +3,7 @@ behaviour, graph-table builders, the drop-in install, and the no-fallback rule."
 import io
 import contextlib
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -394,3 +395,45 @@ def test_static_table_use_counter():
     assert mp_nn._table_use_count(t) == 1
     u = torch.zeros(1, 4, 2, dtype=torch.long)
     assert mp_nn._table_use_count(u) == 1 and mp_nn._table_use_count(t) == 2
+
+
+def _bench_args(*argv):
+    import bench
+    old = sys.argv
+    sys.argv = ["bench.py", *argv]
+    try:
+        return bench, bench.parse_args()
+    finally:
+        sys.argv = old
+
+
+def test_bench_algorithmic_bytes_match_the_survey_figures():
+    """The roofline numerator: bytes = B [4 M K + s T M K + s C N + s O M] per call, summed over types and both
+    directions -- 387.0 MB / 1 500 000 messages per layer for cfg 2 at T = 16, 349.2 MB / 2 359 296 for the LDPC config."""
+    bench, a = _bench_args()
+    types = bench.build_graph(a)
+    assert abs(bench.algorithmic_bytes_per_layer(a, types) / 1e6 - 387.0) < 0.05
+    assert sum(t.real_messages for t in types) == 1_500_000
+    bench, a = _bench_args("--config", "cfg3")
+    types = bench.build_graph(a)
+    assert abs(bench.algorithmic_bytes_per_layer(a, types) / 1e6 - 349.2) < 0.05
+    assert sum(t.real_messages for t in types) * a.batch == 2_359_296
+    bench, a = _bench_args("--edge-types", "4")
+    assert abs(bench.algorithmic_bytes_per_layer(a, bench.build_graph(a)) / 1e6 - 312.6) < 0.05
+
+
+def test_bench_reference_arm_contract_small():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the native one): one JSON line with the contract's
+    keys, honouring --steps / --warmup, at a size that runs in seconds here."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--vars", "1000", "--pairwise", "3000",
+                          "--high", "500", "--steps", "2", "--warmup", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rec = json.loads(out.stdout.strip().splitlines()[-1])
+    assert rec["impl"] == "reference" and rec["metric"] == "factor_messages_per_sec_per_fgnn_layer" and rec["unit"] == "messages/s"
+    assert rec["steps"] == 2 and rec["warmup"] == 1 and rec["higher_is_better"] is True and rec["value"] > 0
+    assert rec["cpu_baseline"]["kind"] in ("port", "port-torch") and rec["cpu_baseline"]["cores"] >= 1
+    assert rec["e2e"]["h2d_bytes_per_step"] == 0 and rec["e2e"]["d2h_bytes_per_step"] == 0 and rec["e2e"]["value"] == rec["value"]
