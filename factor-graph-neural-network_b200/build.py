@@ -44,6 +44,9 @@ def build(force=False, verbose=False, trace=False, debug=False):
         return _compile(LIB.replace(".so", "_trace%s.so" % tag), verbose, ["-DFGNN_TC_TRACE"] + extra)
     if debug:       # watchdog time-outs print the barrier they were waiting on before trapping
         return _compile(LIB.replace(".so", "_debug.so"), verbose, ["-DFGNN_TC_DEBUG"])
+    extra = os.environ.get("FGNN_BUILD_DEFS", "").split()          # experiment switches (-DFGNN_...) for A/B builds
+    if extra:
+        return _compile(LIB.replace(".so", os.environ.get("FGNN_BUILD_TAG", "_exp") + ".so"), verbose, extra)
     if not force and not _stale():
         return LIB
     return _compile(LIB, verbose, [])
