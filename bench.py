@@ -558,8 +558,9 @@ def run_native(args):
                     # the variable-side tables pad with (index 0, all-zero edge type): the generator knows which slots
                     # (FactorType.pad_f2v), the plan leaves them out and the second pass aggregates a literal 0 for them
                     zs = None
-                    if halo is None and not args.no_zero_slots and name.startswith("f2v") and ty.pad_f2v.any():
-                        zs = torch.from_numpy(ty.pad_f2v).to(dev)
+                    if not args.no_zero_slots and name.startswith("f2v") and ty.pad_f2v.any():
+                        # (sharded: the rows of this rank's table are its own variables, in order)
+                        zs = torch.from_numpy(ty.pad_f2v if halo is None else np.ascontiguousarray(ty.pad_f2v[halo.v0:halo.v1])).to(dev)
                     sp = fgnn_b200.SourcePlan(idx, n_src, zero_slots=zs)
                     if args.src_calls != "auto" or sp.n_rows * 1.25 <= idx.numel():
                         plans[name] = sp        # (hub sources -- the reference's pad target -- are split into virtual rows)
