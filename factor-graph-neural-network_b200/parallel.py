@@ -55,6 +55,9 @@ class LocalF2V:
         self.slot_live = np.take_along_axis(live[order], pos, axis=1)
         local = np.take_along_axis(idx_f2v[order], pos, axis=1) - f_lo
         self.idx = np.where(self.slot_live, local, -1).astype(np.int64)              # [rows, kmax], -1 = empty
+        # live slots that are the reference's padding (valid index + all-zero edge type): a source-stationary plan of this
+        # table leaves them out (SourcePlan(zero_slots=...)) -- they all name the same factor, on the rank that owns it
+        self.slot_pad = np.take_along_axis(np.asarray(pad_f2v, dtype=bool)[order], pos, axis=1) & self.slot_live
         self.var = order.astype(np.int32)                                            # out_rows
         self.kmax = kmax
         n_tiles = (self.n_rows + TILE - 1) // TILE
@@ -504,6 +507,34 @@ class ShardedLayerPlan:
         ef = [l.gather_etype(e) for l, e in zip(self.f2v, et_f2v_full)]
         return ev, ef
 
+    # -- source-stationary plans of the local tables --------------------------------------------
+    def source_plan(self, direction, j, T):
+        """SourcePlan of this rank's V->F / compacted F->V table of type j, or None when the call is better off
+        destination-stationary (mp_conv_v2's own rule: T = 16, at least 1.4 edges per source row, enough row-products
+        saved).  Built once (the tables are static)."""
+        from .mp_nn import SourcePlan, mp_conv_v2
+        key = (direction, j)
+        cache = self.__dict__.setdefault("_src_plans", {})
+        if key in cache:
+            return cache[key]
+        plan = None
+        if self.use_source_plans and T == 16:
+            lo, hi = self.ranges[j]
+            if direction == "v2f":
+                idx, n_src, zero = self.idx_v2f[j], self.n_vars, None
+            else:
+                idx, n_src = self.idx_f2v[j], hi - lo
+                zero = torch.from_numpy(self.f2v[j].slot_pad).to(self.device) if self.f2v[j].slot_pad.any() else None
+            edges = int((idx >= 0).sum().item()) - (int(zero.sum().item()) if zero is not None else 0)
+            if idx.numel() >= 50_000 and edges >= mp_conv_v2.AUTO_FAN_OUT[16] * n_src:
+                cand = SourcePlan(idx, n_src, mask_negative=True, zero_slots=zero)
+                if cand.n_rows * 1.25 <= idx.numel():
+                    plan = cand
+        cache[key] = plan
+        return plan
+
+    use_source_plans = True
+
     # -- peer-memory exchange ----------------------------------------------------------------
     def peer_buffers(self, J, O):
         """The two arena-backed variable-feature buffers [1,N,O] (layer l reads [l & 1], writes [(l + 1) & 1])."""
@@ -541,7 +572,8 @@ class ShardedLayerPlan:
                            extension=0, aggregator=_lib.AGG_MAX, activation=_lib.ACT_NONE, kernel=kernel,
                            mask_negative=True, out=nm(view), tile_slots=self.tile_slots[j], out_rows=self.out_rows[j],
                            workspace=wsj.get("f2v"), filters_version=wsj.get("ver_f2v", 0),
-                           sm_limit=sms if self.limit_f2v else 0)
+                           sm_limit=sms if self.limit_f2v else 0,
+                           plan=self.source_plan("f2v", j, et_f2v_local[j].shape[1]) if kernel != _lib.KERNEL_SIMT else None)
         bias, scale, shift = self._epilogue_params(weights)
         ready = torch.cuda.Event()
         ready.record(main)
@@ -561,7 +593,8 @@ class ShardedLayerPlan:
                 mp_forward(nm(x_v), self.idx_v2f[j], et_v2f_local[j], w["filters"], w["bias"], w["scale"], w["shift"],
                            extension=0, aggregator=_lib.AGG_MAX, activation=_lib.ACT_RELU, kernel=kernel,
                            out=nm(out_f_local[j]), workspace=wsj.get("v2f"), filters_version=wsj.get("ver_v2f", 0),
-                           sm_limit=sms)
+                           sm_limit=sms,
+                           plan=self.source_plan("v2f", j, et_v2f_local[j].shape[1]) if kernel != _lib.KERNEL_SIMT else None)
         return xv[src ^ 1]
 
     def _epilogue_params(self, weights):
