@@ -750,6 +750,56 @@ def test_full_size_cfg2_all_four_calls_vs_oracle(T):
             assert_close(y[:, :, torch.from_numpy(rows).to(DEV)].cpu().numpy(), ref, RTOL, f"{ty.name} {name} T={T}")
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_local_tables_source_stationary_equal_destination_stationary(world):
+    """ShardedLayerPlan.source_plan: the shard-local tables (V->F over all variables; the compacted, masked F->V table with
+    tile_slots / out_rows and the padded slots left out) evaluated source-stationary give bit for bit what the
+    destination-stationary kernel gives for them -- the factor-sharded layers use these plans (cfg 2, T = 16)."""
+    from fgnn_b200 import parallel
+    rng = np.random.default_rng(21)
+    C = O = 64
+    T = 16
+    types = graphs.synthetic_map_graph(20_000, 60_000, 10_000, 3, seed=4)
+    dev = torch.device(DEV)
+    nm = lambda a: a.permute(0, 2, 1).unsqueeze(-1)
+    x_v = t(rng.random((1, types[0].n_vars, C), dtype=np.float32))
+    x_f = [t(np.abs(rng.standard_normal((1, ty.n_factors, C))).astype(np.float32)) for ty in types]
+    et_v2f = [t(rng.standard_normal((1, T, ty.n_factors, ty.order)).astype(np.float32)) for ty in types]
+    et_f2v = []
+    for ty in types:
+        e = rng.standard_normal((1, T, ty.n_vars, ty.kv)).astype(np.float32)
+        e[np.broadcast_to(ty.pad_f2v[None, None], e.shape)] = 0.0
+        et_f2v.append(t(e))
+    W = t((rng.uniform(-1, 1, (C, O * T)) * 0.1).astype(np.float32))
+    bias = t(rng.uniform(-0.2, 0.2, O).astype(np.float32))
+    used = 0
+    for rank in (0, world - 1):                                   # rank 0 owns factor 0, the pad target
+        plan = parallel.ShardedLayerPlan(types, rank, world, dev)
+        xf_loc = plan.local_factor_features(x_f)
+        ev, ef = plan.local_etypes(et_v2f, et_f2v)
+        for j in range(len(types)):
+            sp = plan.source_plan("v2f", j, T)
+            if sp is not None:
+                used += 1
+                a = fgnn_b200.mp_forward(nm(x_v), plan.idx_v2f[j], ev[j], W, bias, None, None, extension=0, aggregator=0)
+                b = fgnn_b200.mp_forward(nm(x_v), plan.idx_v2f[j], ev[j], W, bias, None, None, extension=0, aggregator=0, plan=sp)
+                assert torch.equal(a, b)
+            sp = plan.source_plan("f2v", j, T)
+            if sp is not None:
+                used += 1
+                raws = []
+                for pl in (None, sp):
+                    raw = torch.full((1, types[0].n_vars, O), float("-inf"), device=dev)
+                    fgnn_b200.mp_forward(nm(xf_loc[j]), plan.idx_f2v[j], ef[j], W, None, None, None, extension=0, aggregator=0,
+                                         activation=_lib.ACT_NONE, mask_negative=True, out=nm(raw), tile_slots=plan.tile_slots[j],
+                                         out_rows=plan.out_rows[j], plan=pl)
+                    raws.append(raw)
+                assert torch.equal(raws[0], raws[1])
+                if rank == 0 and plan.f2v[j].slot_pad.any():
+                    assert int((sp.slot_edge == -2).sum()) == int(plan.f2v[j].slot_pad.sum())
+    assert used >= 3
+
+
 # ---------------------------------------------------------------------------------------------
 # factor-sharded layer (SURVEY 8e): N-GPU result == 1-GPU result, ranks simulated on one device
 # ---------------------------------------------------------------------------------------------
