@@ -759,7 +759,7 @@ def test_sharded_local_tables_source_stationary_equal_destination_stationary(wor
     rng = np.random.default_rng(21)
     C = O = 64
     T = 16
-    types = graphs.synthetic_map_graph(20_000, 60_000, 10_000, 3, seed=4)
+    types = graphs.synthetic_map_graph(10_000 * world, 30_000 * world, 5_000 * world, 3, seed=4)      # shards big enough to plan
     dev = torch.device(DEV)
     nm = lambda a: a.permute(0, 2, 1).unsqueeze(-1)
     x_v = t(rng.random((1, types[0].n_vars, C), dtype=np.float32))
@@ -797,7 +797,7 @@ def test_sharded_local_tables_source_stationary_equal_destination_stationary(wor
                 assert torch.equal(raws[0], raws[1])
                 if rank == 0 and plan.f2v[j].slot_pad.any():
                     assert int((sp.slot_edge == -2).sum()) == int(plan.f2v[j].slot_pad.sum())
-    assert used >= 3
+    assert used >= 2
 
 
 # ---------------------------------------------------------------------------------------------
