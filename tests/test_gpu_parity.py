@@ -590,6 +590,19 @@ def test_source_plan_zero_slots_equal_evaluated_padding(agg):
     assert int((hinted.slot_edge == -2).sum()) == int(pad.sum())
     assert torch.equal(run(plain), ref)
     assert torch.equal(run(hinted), ref)
+    if agg == "max":                                                   # the module-level hint reaches the plan
+        mod = fgnn_b200.mp_conv_v2(C, C, T, extension=fgnn_b200.mp_conv_type.NO_EXTENSION, aggregtor="max").to(DEV).eval()
+        mod.source_stationary = True
+        with torch.no_grad():
+            y_plain = mod(x, d_idx, d_et)
+            mod2 = fgnn_b200.mp_conv_v2(C, C, T, extension=fgnn_b200.mp_conv_type.NO_EXTENSION, aggregtor="max").to(DEV).eval()
+            mod2.load_state_dict(mod.state_dict())
+            mod2.source_stationary = True
+            mod2.zero_edge_type_slots = t(pad)
+            idx2 = d_idx.clone()                                       # its own table object: its own cached plan
+            y_hint = mod2(x, idx2, d_et)
+        assert torch.equal(y_plain, y_hint)
+        assert int((fgnn_b200.SourcePlan.for_table(idx2, N, zero_slots=mod2.zero_edge_type_slots).slot_edge == -2).sum()) == int(pad.sum())
 
 
 @pytest.mark.parametrize("agg", ["max", "softmax", "mean"])
