@@ -362,6 +362,19 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = msgs * args.layers * args.steps / dt
     full = scale == 1 and batch == args.batch
+    # beside it, for the record: the reference's OWN op chain (mm -> int64 index repeat -> gather -> bmm -> max, mp_nn.py:115-175)
+    # through PyTorch on the same host threads, one layer of the same instance -- the port above is the FASTER of the two,
+    # so the arm's number is the conservative denominator
+    op_chain = None
+    try:
+        import torch
+        torch.set_num_threads(cores)
+        t_torch = torch_layer_pass(args, types, inp, weights[0], device="cpu", reps=1)
+        op_chain = {"value": msgs / t_torch, "unit": UNIT, "kind": "port-torch", "seconds_per_layer": t_torch,
+                    "what": "oracle/fgnn_oracle_torch.py (the reference's ATen op chain) on PyTorch CPU, same instance and threads, "
+                            "1 layer pass after 1 warm-up"}
+    except Exception as e:  # noqa: BLE001
+        op_chain = {"unavailable": f"{type(e).__name__}: {e}"}
     sample = (f"each step = {args.layers} FGNN layers on {'the full workload' if full else ('a 1/%d-scale instance' % scale if args.config != 'cfg3' else 'a batch of %d' % batch)} "
               f"({types[0].n_vars} vars, {msgs} messages/layer), oracle/fgnn_oracle.c (C restatement of mp_nn.py:115-175, OpenMP, {cores} threads)")
     print(json.dumps({
@@ -369,7 +382,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "sample": sample, "full_scale": full},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "reference_op_chain_torch": op_chain},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
