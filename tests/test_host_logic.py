@@ -341,6 +341,16 @@ def test_native_locality_order_matches_numpy():
         assert np.array_equal(x.idx_v2f, y.idx_v2f) and np.array_equal(x.idx_f2v, y.idx_f2v)
 
 
+def test_source_plan_zero_slots_need_the_device_builder():
+    """SourcePlan(zero_slots=...) is a feature of the on-device builder; the host (native) builder and the batch-local plan
+    say so instead of ignoring the hint."""
+    idx = torch.randint(0, 50, (1, 80, 3))
+    with pytest.raises(ValueError):
+        fgnn_b200.SourcePlan(idx, 50, zero_slots=torch.zeros(80, 3, dtype=torch.bool))
+    with pytest.raises(ValueError):
+        fgnn_b200.SourcePlan(idx, 50, batch_local=True, zero_slots=torch.zeros(80, 3, dtype=torch.bool))
+
+
 def test_source_plan_picks_row_cap_by_cost():
     import torch
     import fgnn_b200

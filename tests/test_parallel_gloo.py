@@ -92,6 +92,11 @@ def test_compacted_table_invariants():
             orig = np.take_along_axis(t.idx_f2v[loc.var], loc.slot_pos, axis=1)
             assert (np.where(live, orig - lo, -1) == loc.idx).all()
             total += int(cnt.sum())
+            # the padded slots (index 0 + zero edge type) are live only on the rank that owns factor 0, and marked there
+            orig_pad = np.take_along_axis(t.pad_f2v[loc.var], loc.slot_pos, axis=1)
+            assert (loc.slot_pad == (orig_pad & live)).all()
+            assert loc.slot_pad.any() == (bool(t.pad_f2v.any()) and lo == 0)
+            assert (loc.idx[loc.slot_pad] == 0).all()
         assert total == t.idx_f2v.size                                          # every slot live on exactly one rank
 
 
