@@ -979,7 +979,9 @@ def _can_add_into(acc, B, O, M):
 
 class mp_conv_residual(base_mp_nn):
     """conv1 (1x1 + BN + LeakyReLU) -> mp_conv_v2 -> conv2 (1x1 + BN + LeakyReLU) [+ residual];
-    reference mp_nn_residual.py:8-56.  The 1x1 maps stay in PyTorch."""
+    reference mp_nn_residual.py:8-56.  In eval mode on a CUDA device each 1x1 map (C in {64, 128, 256}) is ONE launch of
+    the tensor-core kernel with the BatchNorm folded in (`conv1x1_native`); train mode and other shapes run the module's
+    own PyTorch sequence (the maps are separate launches, not yet part of the core call)."""
 
     def __init__(self, nin, nmed, netype, extension=mp_conv_type.ORIG_WITH_DIFF, with_residual=True,
                  with_hop=False, aggregator='max', nout=None):
