@@ -116,3 +116,46 @@ def test_factor_mpnn_merged_tables():
     assert_close(out_f[1], g["out_f1"], 5e-5, "out_f1")
     labels = out_v[..., 0].argmax(1)
     assert np.array_equal(labels, g["labels"]) and 0 < labels.sum() < labels.size
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_three_oracles_agree_on_seeded_random_shapes(seed):
+    """numpy restatement == C restatement == torch restatement (the reference's own ATen op order) on shapes and option
+    mixes the goldens do not enumerate: ragged sizes, every extension x aggregator, with / without bias and BN, batched
+    tables with repeated and boundary indices.  The goldens pin each of them to the real reference; this pins them to
+    each other everywhere else."""
+    import torch
+    from oracle import fgnn_oracle_torch as orct
+    rng = np.random.default_rng(1000 + seed)
+    B = int(rng.integers(1, 4))
+    C = int(rng.choice([2, 3, 8, 17, 64]))
+    O = int(rng.choice([2, 5, 16, 64]))
+    T = int(rng.choice([1, 2, 4, 16]))
+    ext = int(rng.integers(0, 3))
+    N = int(rng.integers(3, 40))
+    M = N if ext else int(rng.integers(1, 50))
+    K = int(rng.integers(1, 7))
+    agg = [None, "max", "softmax", "mean"][int(rng.integers(0, 4))] if seed % 4 else "max"
+    x = rng.standard_normal((B, C, N, 1)).astype(np.float32)
+    idx = rng.integers(0, N, (B, M, K)).astype(np.int64)
+    idx[:, 0, 0] = N - 1                                          # boundary index
+    idx[:, -1, :] = idx[:, -1, :1]                                # repeated sources in one row
+    et = rng.standard_normal((B, T, M, K)).astype(np.float32)
+    if K > 1:
+        et[:, :, :, -1] = 0.0                                     # the reference's padding: a zero edge type on a valid index
+    W = (rng.uniform(-1, 1, ((2 if ext else 1) * C, O * T)) * 0.3).astype(np.float32)
+    bias = rng.uniform(-0.2, 0.2, O).astype(np.float32) if seed % 3 else None
+    bn = None
+    if seed % 2:
+        bn = dict(weight=rng.uniform(0.5, 1.5, O).astype(np.float32), bias=rng.uniform(-0.2, 0.2, O).astype(np.float32),
+                  running_mean=rng.uniform(-0.2, 0.2, O).astype(np.float32), running_var=rng.uniform(0.5, 1.5, O).astype(np.float32))
+    act = "relu" if seed % 5 else None
+    a = orc.mp_conv_forward(x, idx, et, W, bias, bn, extension=ext, aggregator=agg, activation=act)
+    c = orc.mp_conv_forward_c(x, idx, et, W, bias, bn, extension=ext, aggregator=agg, activation=act)
+    t = torch.from_numpy
+    tb = {k: t(v) for k, v in bn.items()} if bn is not None else None
+    p = orct.mp_conv_forward_torch(t(x), t(idx), t(et), t(W), t(bias) if bias is not None else None, tb, extension=ext,
+                                   aggregator=agg, activation=act).numpy()
+    assert a.shape == c.shape == p.shape == (B, O, M, K if agg is None else 1)
+    assert_close(c, a, ORACLE_RTOL, f"C vs numpy (seed {seed})")
+    assert_close(p, a, ORACLE_RTOL, f"torch vs numpy (seed {seed})")
