@@ -15,8 +15,10 @@
 //   B[rank] = epoch   "I have read every raw buffer and written my rows everywhere"  (set by the last block)
 // Every block waits for all A before reading and for all B before exiting, so when the kernel completes on
 // a rank (a) all rows of its own next-layer buffer are in place and (b) nobody still reads its raw buffer.
-// All ranks must launch the kernel with the same epoch; the grid is small (<= 64 CTAs of 1024 threads) so that it is always
-// co-resident beside the persistent tensor-core kernels (which are given sm_limit SMs meanwhile).
+// All ranks must launch the kernel with the same epoch.  Every block spins on flags other blocks (here and on the peers)
+// set, so ALL blocks of the grid must be resident at once: the grid is small (<= 128 CTAs of 512 threads, two per SM;
+// launch_exchange refuses a grid beyond what the occupancy calculator says the device can hold) and the caller gives
+// the persistent tensor-core kernels that run beside it sm_limit = SMs - ceil(ctas / 2), so its SMs are free.
 #include <cstring>
 
 #include "common.cuh"
@@ -274,6 +276,16 @@ halo_kernel(const HaloParams p) {
 
 template <int WORLD, int UNROLL, int kJ>
 cudaError_t launch_exchange(const ExParams& p, int ctas, cudaStream_t st) {
+  // co-residency of the whole grid is a correctness condition (see the header comment): check it against the device
+  static int capacity = 0;
+  if (!capacity) {
+    int per_sm = 0, dev = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, exchange_kernel<WORLD, UNROLL, kJ>, 512, 0) != cudaSuccess ||
+        cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return cudaErrorUnknown;
+    capacity = per_sm * sms;
+  }
+  if (ctas > capacity) return cudaErrorLaunchOutOfResources;
   exchange_kernel<WORLD, UNROLL, kJ><<<ctas, 512, 0, st>>>(p);
   return cudaGetLastError();
 }
