@@ -79,7 +79,13 @@ class iid_mapping_in(torch.nn.Module):
                                         _InstanceNorm2d(nout), torch.nn.ReLU())
 
     def forward(self, x):
-        y = conv_in_relu(self.main[0], self.main[1], x, self.training)
+        norm = self.main[1]
+        if (x.dim() == 4 and x.shape[2] * x.shape[3] == 1 and isinstance(norm, _InstanceNorm2d)
+                and not norm.track_running_stats and not norm.affine):
+            # a single spatial element (the LDPC "global" factor): the norm returns zeros whatever the map computes
+            # (_InstanceNorm2d above), so the map is not run at all
+            return torch.zeros((x.shape[0], self.main[0].out_channels, 1, 1), dtype=x.dtype, device=x.device)
+        y = conv_in_relu(self.main[0], norm, x, self.training)
         return y if y is not None else self.main(x)
 
 
